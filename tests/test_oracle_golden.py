@@ -1,0 +1,169 @@
+"""Pins oracle/vq_oracle.py against outputs of the live reference (tests/golden/vq_golden.npz)."""
+import hashlib
+
+import numpy as np
+import pytest
+from conftest import gsub
+from synth import large_case_inputs
+
+from oracle import vq_oracle as O
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def mk(g, K_per, L=1, **kw):
+    return O.OracleQuantizer(K_per, g["E"].shape[1], num_quantizers=L, embedding=g["E"], **kw)
+
+
+def test_small_single_eval(golden):
+    g = gsub(golden, "small_single")
+    q = mk(g, 64)
+    st, zq, idx, stats = q.forward(g["z"], do_ema_update=False)
+    assert np.array_equal(idx, g["idx"])
+    assert np.array_equal(zq, g["zq"])
+    assert np.array_equal(st, g["zq_st"])           # two-rounding straight-through value, bitwise
+    np.testing.assert_allclose(stats, g["stats"], rtol=1e-6)
+    assert np.array_equal(q._ep_usage, g["ep_usage"])
+    assert np.array_equal(q._ep_cnt, g["ep_cnt"])
+    np.testing.assert_allclose(O.commitment_mse(zq, g["z"]), g["commit"], rtol=1e-6)
+
+
+def test_small_single_mask(golden):
+    g0 = gsub(golden, "small_single")
+    g = gsub(golden, "small_single_mask")
+    q = mk(g0, 64)
+    _, _, idx, stats = q.forward(g0["z"], do_ema_update=False, mask=g["mask"])
+    assert np.array_equal(idx, g["idx"])
+    np.testing.assert_allclose(stats, g["stats"], rtol=1e-6)
+    assert np.array_equal(q._ep_usage, g["ep_usage"])
+    assert np.array_equal(q._ep_cnt, g["ep_cnt"])
+
+
+def test_small_single_train(golden):
+    g = gsub(golden, "small_single_train")
+    q = mk(g, 64, decay=float(g["decay"]))
+    q.training = True
+    for step in range(3):
+        s = gsub(golden, f"small_single_train/step{step}")
+        _, zq, idx, stats = q.forward(s["z"], do_ema_update=True)
+        assert np.array_equal(idx, s["idx"])
+        if step == 0:
+            assert np.array_equal(zq, s["zq"])      # gathered from the PRE-update codebook, bitwise
+        else:                                       # codebook carries summation-order noise from step 0 on
+            np.testing.assert_allclose(zq, s["zq"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(q.ema_cluster_size, s["ema_cluster_size"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(q.ema_embedding, s["ema_embedding"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(q.embedding, s["embedding"], rtol=1e-5, atol=1e-6)
+    e = gsub(golden, "small_single_train/epoch")
+    es = q.epoch_stats()
+    assert es["n_positions"] == int(e["n_positions"])
+    np.testing.assert_allclose(es["perplexity"], float(e["perplexity"]), rtol=1e-5)
+    np.testing.assert_allclose(es["dead_ratio"], float(e["dead_ratio"]), rtol=1e-6)
+
+
+def test_small_single_train_mask(golden):
+    g0 = gsub(golden, "small_single")
+    gm = gsub(golden, "small_single_mask")
+    g = gsub(golden, "small_single_train_mask")
+    q = mk(g0, 64, decay=0.95)
+    q.training = True
+    _, _, idx, stats = q.forward(g0["z"], do_ema_update=True, mask=gm["mask"])
+    assert np.array_equal(idx, g["idx"])
+    np.testing.assert_allclose(q.ema_cluster_size, g["ema_cluster_size"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(q.embedding, g["embedding"], rtol=1e-5, atol=1e-6)
+
+
+def test_small_grad(golden):
+    g0 = gsub(golden, "small_single")
+    g = gsub(golden, "small_single_grad")
+    q = mk(g0, 64)
+    _, zq, _, _ = q.forward(g0["z"], do_ema_update=False)
+    grad = O.commit_backward(g["w"], g0["z"], zq, float(g["beta"]))
+    np.testing.assert_allclose(grad, g["grad"], rtol=1e-6, atol=1e-7)
+
+
+def test_small_rvq(golden):
+    g = gsub(golden, "small_rvq")
+    q = mk(g, int(g["K_per"]), int(g["L"]))
+    st, zq, idx, stats = q.forward(g["z"], do_ema_update=False)
+    assert idx.shape == g["idx"].shape and np.array_equal(idx, g["idx"])   # [L*N] level-major, global ids
+    assert np.array_equal(zq, g["zq"])              # level-order sum, bitwise
+    assert np.array_equal(st, g["zq_st"])
+    np.testing.assert_allclose(stats, g["stats"], rtol=1e-6)
+    assert np.array_equal(q._ep_cnt, g["ep_cnt"])   # += L*N
+    # wire formats either side
+    B = g["z"].shape[0]
+    bf = O.rvq_indices_batch_first(idx, B, int(g["L"]))
+    assert bf.shape == (B, g["z"].shape[1] * int(g["L"]))
+    lat = O.indices_to_latent(bf[0], g["E"], int(g["L"]))
+    assert np.array_equal(lat[0], zq[0])
+
+
+def test_small_rvq_train(golden):
+    g = gsub(golden, "small_rvq")
+    gt = gsub(golden, "small_rvq_train")
+    q = mk(g, int(g["K_per"]), int(g["L"]), decay=float(gt["decay"]))
+    q.training = True
+    for step in range(3):
+        s = gsub(golden, f"small_rvq_train/step{step}")
+        st, zq, idx, stats = q.forward(s["z"], do_ema_update=True)
+        assert np.array_equal(idx, s["idx"])
+        np.testing.assert_allclose(zq, s["zq"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(q.ema_cluster_size, s["ema_cluster_size"], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(q.embedding, s["embedding"], rtol=1e-5, atol=1e-6)
+    gm = gsub(golden, "small_rvq_train_mask")
+    q = mk(g, int(g["K_per"]), int(g["L"]), decay=0.9)
+    q.training = True
+    _, _, idx, stats = q.forward(g["z"], do_ema_update=True, mask=gm["mask"])
+    assert np.array_equal(idx, gm["idx"])
+    np.testing.assert_allclose(q.embedding, gm["embedding"], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(q._ep_usage, gm["ep_usage"])      # RVQ histogram ignores the mask
+
+
+def test_semantics(golden):
+    d = gsub(golden, "sem_dup")
+    assert np.array_equal(O.nearest_code(d["z"][0], d["E"]), d["idx"][0])
+    assert d["idx"][0][0] == 3 and d["idx"][0][1] == 3      # lowest twin wins
+    n = gsub(golden, "sem_nan_row")
+    assert np.array_equal(O.nearest_code(n["z"][0], d["E"]), n["idx"][0])
+    c = gsub(golden, "sem_nan_code")
+    assert np.array_equal(O.nearest_code(d["z"][0], c["E"]), c["idx"][0])
+    assert (c["idx"] == 5).all()                            # first NaN code wins every row
+    k = gsub(golden, "sem_collapsed")
+    assert np.array_equal(O.nearest_code(d["z"][0], k["E"]), k["idx"][0])
+
+
+LARGE = ["c2_like", "c2_clustered", "ragged_k", "one_row", "c3_like", "c3_clustered",
+         "stage2_rvq", "d128_scaled"]
+
+
+@pytest.mark.parametrize("name", LARGE)
+def test_large_cases(golden, name):
+    g = gsub(golden, name)
+    K_per, D, L, B, M = (int(g[k]) for k in ("K_per", "D", "L", "B", "M"))
+    scale = None if float(g["scale"]) < 0 else float(g["scale"])
+    E, z = large_case_inputs(int(g["seed"]), K_per, D, L, B, M, scale, bool(int(g["clustered"])))
+    assert sha(E) == str(g["sha_E"]) and sha(z) == str(g["sha_z"])
+    q = O.OracleQuantizer(K_per, D, num_quantizers=L, embedding=E)
+    st, zq, idx, stats = q.forward(z, do_ema_update=False)
+    ref = g["idx"].astype(np.int64).reshape(idx.shape)
+    if L == 1:
+        mm, outside = O.near_tie_rows(z.reshape(-1, D), E, idx.reshape(-1), ref.reshape(-1))
+        assert outside.size == 0, f"{outside.size} rows differ outside the 1e-6 near-tie allowance"
+        assert mm.size <= 2
+    else:
+        # chain-aware: once a row flips at level l, deeper levels of it are excluded
+        N = B * M
+        a, b = idx.reshape(L, N), ref.reshape(L, N)
+        alive = np.ones(N, bool)
+        for lvl in range(L):
+            bad = alive & (a[lvl] != b[lvl])
+            assert bad.sum() <= 2
+            alive &= ~bad
+        assert alive.mean() > 0.999
+    if np.array_equal(idx, ref):
+        assert sha(zq) == str(g["sha_zq"]) and sha(st) == str(g["sha_zq_st"])
+        np.testing.assert_allclose(stats, g["stats"], rtol=1e-6)
+    np.testing.assert_allclose(O.commitment_mse(zq, z), float(g["commit"]), rtol=1e-5)
