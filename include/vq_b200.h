@@ -1,0 +1,152 @@
+/* vq_b200.h -- C ABI of libvqb200.so: the B200 (sm_100a) vector-quantizer hot path.
+ *
+ * The reference (jluuser/PyTorch-VAE) has no FFI: its "plugin API" for this path is the
+ * Python class models/vq_vae.py:19 VectorQuantizerEMA, whose arithmetic is a sequence of
+ * ATen calls.  Each entry point below replaces one group of those calls (cited per
+ * function, paths relative to the reference root) and is what a ctypes/cffi/pybind binding
+ * on the reference side would bind; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory unless it says "host"
+ *   - row-major, contiguous; float rows must be 16-byte aligned (D % 4 == 0)
+ *   - caller allocates every output and workspace; the library keeps no state
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises
+ *   - return 0 on success, a negative VQB200_E* for argument errors, or a positive
+ *     cudaError_t from the launch.  Nothing throws.  No CPU fallback exists.
+ */
+#ifndef VQ_B200_H_
+#define VQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define VQB200_API __attribute__((visibility("default")))
+#else
+#define VQB200_API
+#endif
+
+#define VQB200_ABI_VERSION 1
+#define VQB200_MAX_LEVELS 32
+#define VQB200_LEVEL_META_FLOATS 4 /* per level: max|e|, non-finite flag, max|bf16(e)|, reserved */
+
+enum {
+  VQB200_OK = 0,
+  VQB200_EINVAL = -1,     /* null pointer / negative size */
+  VQB200_ESHAPE = -2,     /* unsupported D, K or level layout */
+  VQB200_EALIGN = -3,     /* pointer not 16-byte aligned */
+  VQB200_EWORKSPACE = -4, /* workspace too small */
+  VQB200_EDRIVER = -5     /* tensor-map encode / driver entry point failure */
+};
+
+enum {
+  VQB200_MODE_FP32_EXACT = 0, /* indices of the fp32 inputs; tensor-core candidates are re-ranked exactly */
+  VQB200_MODE_BF16_INPUT = 1  /* inputs rounded to bf16 (RN), products and sums in fp32 */
+};
+
+enum { VQB200_IDX_I16 = 2, VQB200_IDX_I32 = 4, VQB200_IDX_I64 = 8 };
+
+VQB200_API int vqb200_abi_version(void);
+VQB200_API const char* vqb200_status_string(int status);
+
+/* Which search kernel `vqb200_search` picks for a shape: 0 = SIMT fp32, 1 = tcgen05 tensor core. */
+VQB200_API int vqb200_search_path(int64_t N, int K, int D, int mode);
+
+/* Per-code cache refresh.  Replaces `self.embedding.pow(2).sum(1)` (models/vq_vae.py:186,241),
+ * recomputed by the reference on every forward, plus the operand conversion for the tensor path.
+ *   E          [K_total, D] fp32 codebook (the module's `embedding` buffer, source of truth)
+ *   K_per      codes per residual level (K_total % K_per == 0, at most VQB200_MAX_LEVELS levels)
+ *   E_bf16     [K_total, D] bf16 (RN) copy
+ *   ee_half    [2, K_total]: plane 0 = |e|^2/2 of the fp32 rows, plane 1 = of the bf16-rounded rows
+ *   level_meta [levels, 4] fp32, see VQB200_LEVEL_META_FLOATS
+ */
+VQB200_API int vqb200_codebook_prepare(const float* E, int K_total, int D, int K_per, uint16_t* E_bf16,
+                            float* ee_half, float* level_meta, void* stream);
+
+/* Nearest-code search for ONE level: replaces the distance assembly + argmin
+ * (models/vq_vae.py:183-188 and :238-245).  The N x K distance matrix is never written.
+ *   z          [N, D] fp32 latents (or the RVQ residual)
+ *   E, E_bf16, ee_half(plane 0), ee_half_bf16(plane 1), level_meta: this level's slices of the cache
+ *   idx_out    [N] int64 = idx_offset + argmin_k |z - e_k|^2; first index on exact ties; a NaN
+ *              distance counts as the minimum (torch.argmin semantics)
+ */
+VQB200_API size_t vqb200_search_workspace_bytes(int64_t N, int K, int D, int mode);
+VQB200_API int vqb200_search(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16,
+                  const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K,
+                  int mode, int64_t idx_offset, int64_t* idx_out, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/* Gather + everything elementwise that follows it, in one pass over the rows.
+ * Replaces F.embedding (:189,248), the straight-through expression (:199,263), the RVQ
+ * residual update (:258) and level sum (:261), F.mse_loss partial sums (:1293) and
+ * torch.bincount (:205-207,266).  Every output is optional (NULL = skip).
+ *   idx           [N] int64 GLOBAL code ids (rows of E)
+ *   zq_out        [N, D]: = E[idx], or += E[idx] when zq_accumulate != 0 (RVQ levels > 0)
+ *   zq_st_out     [N, D]: fl(z + fl(E[idx] - z))
+ *   residual_out  [N, D]: fl(z - E[idx])
+ *   sqerr_sum     [1] double, += sum (E[idx] - z)^2   (caller zeroes)
+ *   hist          [K_total] int32, += 1 per row with row_mask[row] != 0 (row_mask NULL = all rows)
+ */
+VQB200_API int vqb200_gather(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int K_total,
+                  float* zq_out, int zq_accumulate, float* zq_st_out, float* residual_out,
+                  double* sqerr_sum, int32_t* hist, const uint8_t* row_mask, void* stream);
+
+/* Straight-through value and commitment partial sum from z and an already-summed z_q
+ * (the RVQ tail, models/vq_vae.py:263 and :1293). */
+VQB200_API int vqb200_st_loss(const float* z, const float* zq, int64_t n_elems, float* zq_st_out,
+                   double* sqerr_sum, void* stream);
+
+/* Usage statistics: replaces the ~12 small ATen kernels of models/vq_vae.py:209-222, 267-280.
+ *   stats_out [3] = perplexity, dead_ratio, commitment mse (= *sqerr_sum * inv_elems; 0 if NULL)
+ *   ep_usage  [K_total] += usage;  ep_cnt [1] += count_add   (either may be NULL)
+ */
+VQB200_API int vqb200_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
+                          double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out,
+                          void* stream);
+
+/* EMA codebook update, part 1: segment sums.  Replaces the dense one-hot GEMM of
+ * models/vq_vae.py:81-83.  seg_sum [K_total, D] and seg_cnt [K_total] are zeroed by the caller. */
+VQB200_API int vqb200_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D,
+                       int K_total, float* seg_sum, float* seg_cnt, void* stream);
+
+/* EMA codebook update, part 2 (models/vq_vae.py:85-89) fused with the cache refresh:
+ *   cs <- fl(fl(cs*decay) + fl(n*(1-decay)));  es likewise;  E <- es / (cs + eps)  for ALL codes.
+ * one_minus_decay is passed separately because the reference forms it in double. */
+VQB200_API int vqb200_ema_finalize(const float* seg_sum, const float* seg_cnt, float decay, float one_minus_decay,
+                        float eps, int K_total, int D, int K_per, float* ema_cluster_size,
+                        float* ema_embedding, float* E, uint16_t* E_bf16, float* ee_half,
+                        float* level_meta, void* stream);
+
+/* Backward of the two differentiable outputs (straight-through + commitment):
+ *   grad_z = grad_st + (*grad_commit) * scale * (z - zq),  scale = 2 / (N D)
+ * grad_st may be NULL (treated as 0); grad_commit is a DEVICE scalar (no host sync), NULL = 0. */
+VQB200_API int vqb200_commit_backward(const float* grad_st, const float* grad_commit, const float* z,
+                           const float* zq, int64_t n_elems, float scale, float* grad_z_out,
+                           void* stream);
+
+/* Wire formats either side of the path.
+ * Level-major flat RVQ ids [Q, B, M] -> token-major [B, M*Q], optionally narrowed
+ * (scripts/extract_code_indices.py:195-209, :494-549 narrows on the host). */
+VQB200_API int vqb200_relayout_indices(const int64_t* idx_level_major, int Q, int64_t B, int64_t M, void* out,
+                            int out_elem_bytes, void* stream);
+/* Token-major ids [n_tok * Q] -> z_q [n_tok, D] = sum over the Q levels in level order
+ * (scripts/decode_with_vqvae.py:110-130; models/vq_vae.py:1404-1418). */
+VQB200_API int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok, int Q, const float* E,
+                             int K_total, int D, float* zq_out, void* stream);
+
+/* Codebook-sharded search support: a (distance, index) pair packed into one
+ * orderable uint64 so that an all-reduce(MIN) performs a tie-stable min-loc.
+ *   search_packed: like vqb200_search but writes packed[N] = key(d) << 32 | (idx_offset + argmin)
+ *   unpack: packed -> int64 ids */
+VQB200_API int vqb200_search_packed(const float* z, int64_t N, int D, const float* E, const float* ee_half, int K,
+                         int64_t idx_offset, uint64_t* packed_out, void* stream);
+VQB200_API int vqb200_minloc_unpack(const uint64_t* packed, int64_t N, int64_t* idx_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQ_B200_H_ */

@@ -1,0 +1,160 @@
+// extern "C" entry points of libvqb200.so: argument validation + dispatch.  See include/vq_b200.h.
+#include "common.cuh"
+
+using namespace vqb;
+
+#define VQ_REQUIRE(cond, code) \
+  do {                         \
+    if (!(cond)) return (code); \
+  } while (0)
+
+static bool shape_ok(int D) { return D >= 4 && D % 4 == 0 && D <= 4096; }
+
+extern "C" {
+
+int vqb200_abi_version(void) { return VQB200_ABI_VERSION; }
+
+const char* vqb200_status_string(int status) {
+  switch (status) {
+    case VQB200_OK: return "ok";
+    case VQB200_EINVAL: return "invalid argument (null pointer or negative size)";
+    case VQB200_ESHAPE: return "unsupported shape (D must be a multiple of 4, K_total a multiple of K_per)";
+    case VQB200_EALIGN: return "pointer not 16-byte aligned";
+    case VQB200_EWORKSPACE: return "workspace too small";
+    case VQB200_EDRIVER: return "CUDA driver entry point / tensor-map failure";
+    default: return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown status";
+  }
+}
+
+int vqb200_search_path(int64_t N, int K, int D, int mode) {
+  (void)N; (void)K; (void)D; (void)mode;
+  return 0;
+}
+
+int vqb200_codebook_prepare(const float* E, int K_total, int D, int K_per, uint16_t* E_bf16, float* ee_half,
+                            float* level_meta, void* stream) {
+  VQ_REQUIRE(E && E_bf16 && ee_half && level_meta, VQB200_EINVAL);
+  VQ_REQUIRE(K_total > 0 && K_per > 0, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D) && K_total % K_per == 0 && K_total / K_per <= VQB200_MAX_LEVELS, VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(E) && aligned16(E_bf16), VQB200_EALIGN);
+  return launch_codebook_refresh(false, nullptr, nullptr, 0.f, 0.f, 0.f, K_total, D, K_per, nullptr, nullptr,
+                                 const_cast<float*>(E), E_bf16, ee_half, level_meta,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+size_t vqb200_search_workspace_bytes(int64_t N, int K, int D, int mode) {
+  (void)N; (void)K; (void)D; (void)mode;
+  return 256;
+}
+
+int vqb200_search(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
+                  const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
+                  int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream) {
+  VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && idx_out), VQB200_EINVAL);
+  VQ_REQUIRE(E && E_bf16 && ee_half && ee_half_bf16 && level_meta, VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E), VQB200_EALIGN);
+  VQ_REQUIRE(workspace_bytes >= vqb200_search_workspace_bytes(N, K, D, mode) && (workspace || N == 0),
+             VQB200_EWORKSPACE);
+  const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  return launch_search_simt(z, nullptr, N, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0, idx_offset, idx_out,
+                            nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_gather(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int K_total, float* zq_out,
+                  int zq_accumulate, float* zq_st_out, float* residual_out, double* sqerr_sum, int32_t* hist,
+                  const uint8_t* row_mask, void* stream) {
+  VQ_REQUIRE(N >= 0 && K_total > 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && E && idx), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(zq_out) && aligned16(zq_st_out) && aligned16(residual_out),
+             VQB200_EALIGN);
+  return launch_gather(z, E, idx, N, D, K_total, zq_out, zq_accumulate, zq_st_out, residual_out, sqerr_sum, hist,
+                       row_mask, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_st_loss(const float* z, const float* zq, int64_t n_elems, float* zq_st_out, double* sqerr_sum,
+                   void* stream) {
+  VQ_REQUIRE(n_elems >= 0, VQB200_EINVAL);
+  VQ_REQUIRE(n_elems == 0 || (z && zq), VQB200_EINVAL);
+  VQ_REQUIRE(n_elems % 4 == 0, VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(zq) && aligned16(zq_st_out), VQB200_EALIGN);
+  return launch_st_loss(z, zq, n_elems, zq_st_out, sqerr_sum, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
+                          double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out, void* stream) {
+  VQ_REQUIRE(hist && stats_out && K_total > 0, VQB200_EINVAL);
+  return launch_stats_finalize(hist, K_total, count_add, sqerr_sum, inv_elems, ep_usage, ep_cnt, stats_out,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
+                       float* seg_sum, float* seg_cnt, void* stream) {
+  VQ_REQUIRE(N >= 0 && K_total > 0 && seg_sum && seg_cnt, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && idx), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(seg_sum), VQB200_EALIGN);
+  return launch_scatter_add(z, idx, row_mask, N, D, K_total, seg_sum, seg_cnt, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_ema_finalize(const float* seg_sum, const float* seg_cnt, float decay, float one_minus_decay, float eps,
+                        int K_total, int D, int K_per, float* ema_cluster_size, float* ema_embedding, float* E,
+                        uint16_t* E_bf16, float* ee_half, float* level_meta, void* stream) {
+  VQ_REQUIRE(seg_sum && seg_cnt && ema_cluster_size && ema_embedding && E && E_bf16 && ee_half && level_meta,
+             VQB200_EINVAL);
+  VQ_REQUIRE(K_total > 0 && K_per > 0, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D) && K_total % K_per == 0 && K_total / K_per <= VQB200_MAX_LEVELS, VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(seg_sum) && aligned16(ema_embedding) && aligned16(E) && aligned16(E_bf16), VQB200_EALIGN);
+  return launch_codebook_refresh(true, seg_sum, seg_cnt, decay, one_minus_decay, eps, K_total, D, K_per,
+                                 ema_cluster_size, ema_embedding, E, E_bf16, ee_half, level_meta,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_commit_backward(const float* grad_st, const float* grad_commit, const float* z, const float* zq,
+                           int64_t n_elems, float scale, float* grad_z_out, void* stream) {
+  VQ_REQUIRE(n_elems >= 0, VQB200_EINVAL);
+  VQ_REQUIRE(n_elems == 0 || (z && zq && grad_z_out), VQB200_EINVAL);
+  VQ_REQUIRE(n_elems % 4 == 0, VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(grad_st) && aligned16(z) && aligned16(zq) && aligned16(grad_z_out), VQB200_EALIGN);
+  return launch_commit_backward(grad_st, grad_commit, z, zq, n_elems, scale, grad_z_out,
+                                static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_relayout_indices(const int64_t* idx_level_major, int Q, int64_t B, int64_t M, void* out,
+                            int out_elem_bytes, void* stream) {
+  VQ_REQUIRE(Q > 0 && B >= 0 && M >= 0, VQB200_EINVAL);
+  VQ_REQUIRE(B * M == 0 || (idx_level_major && out), VQB200_EINVAL);
+  return launch_relayout(idx_level_major, Q, B, M, out, out_elem_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok, int Q, const float* E, int K_total,
+                             int D, float* zq_out, void* stream) {
+  VQ_REQUIRE(Q > 0 && n_tok >= 0 && K_total > 0, VQB200_EINVAL);
+  VQ_REQUIRE(n_tok == 0 || (idx && E && zq_out), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(E) && aligned16(zq_out), VQB200_EALIGN);
+  return launch_indices_to_latent(idx, idx_elem_bytes, n_tok, Q, E, K_total, D, zq_out,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_search_packed(const float* z, int64_t N, int D, const float* E, const float* ee_half, int K,
+                         int64_t idx_offset, uint64_t* packed_out, void* stream) {
+  VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && packed_out), VQB200_EINVAL);
+  VQ_REQUIRE(E && ee_half, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E), VQB200_EALIGN);
+  return launch_search_simt(z, nullptr, N, D, E, ee_half, K, 0, idx_offset, nullptr, packed_out,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_minloc_unpack(const uint64_t* packed, int64_t N, int64_t* idx_out, void* stream) {
+  VQ_REQUIRE(N >= 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (packed && idx_out), VQB200_EINVAL);
+  return launch_minloc_unpack(packed, N, idx_out, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

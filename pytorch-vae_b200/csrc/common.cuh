@@ -1,0 +1,85 @@
+// Shared device helpers for libvqb200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vq_b200.h"
+
+#ifndef __CUDA_ARCH_FEAT_SM100_ALL
+#if defined(__CUDA_ARCH__)
+#error "libvqb200 is written for sm_100a only: compile with -gencode arch=compute_100a,code=sm_100a"
+#endif
+#endif
+
+namespace vqb {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// Order-preserving float -> uint32 key with torch.argmin's NaN rule folded in:
+// NaN maps to 0, which sorts below -inf (key 0x007fffff), so a packed min picks the first NaN.
+__device__ __forceinline__ uint32_t dist_key(float d) {
+  uint32_t u = __float_as_uint(d);
+  uint32_t k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return (d != d) ? 0u : k;
+}
+__device__ __forceinline__ uint64_t pack_minloc(float d, uint32_t idx) {
+  return (static_cast<uint64_t>(dist_key(d)) << 32) | idx;
+}
+__device__ __forceinline__ uint64_t umin64(uint64_t a, uint64_t b) { return a < b ? a : b; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Streaming 128-bit accesses: rows are touched once, keep them out of L1.
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(float4* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+inline int status_of(cudaError_t e) { return e == cudaSuccess ? VQB200_OK : static_cast<int>(e); }
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace vqb
+
+// Internal launchers (defined in the .cu files, called from cabi.cu).
+namespace vqb {
+int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, int D, const float* E,
+                       const float* ee_half, int K, int round_bf16, int64_t idx_offset, int64_t* idx_out,
+                       uint64_t* packed_out, cudaStream_t s);
+int launch_codebook_refresh(bool ema, const float* seg_sum, const float* seg_cnt, float decay, float omd,
+                            float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb, float* E,
+                            uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s);
+int launch_gather(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int K_total, float* zq_out,
+                  int zq_accumulate, float* zq_st_out, float* residual_out, double* sqerr_sum, int32_t* hist,
+                  const uint8_t* row_mask, cudaStream_t s);
+int launch_st_loss(const float* z, const float* zq, int64_t n_elems, float* st, double* sqerr_sum, cudaStream_t s);
+int launch_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
+                          double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out, cudaStream_t s);
+int launch_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
+                       float* seg_sum, float* seg_cnt, cudaStream_t s);
+int launch_commit_backward(const float* g, const float* gc, const float* z, const float* zq, int64_t n_elems,
+                           float scale, float* out, cudaStream_t s);
+int launch_relayout(const int64_t* in, int Q, int64_t B, int64_t M, void* out, int bytes, cudaStream_t s);
+int launch_indices_to_latent(const void* idx, int bytes, int64_t n_tok, int Q, const float* E, int K_total, int D,
+                             float* out, cudaStream_t s);
+int launch_minloc_unpack(const uint64_t* p, int64_t N, int64_t* out, cudaStream_t s);
+}

@@ -1,0 +1,419 @@
+// HBM-bound row kernels of the VQ path: codebook cache refresh (+ fused EMA finalize), the
+// gather / straight-through / residual / loss / histogram pass, statistics, scatter-add,
+// backward, and the index wire formats.  All are coalesced 128-bit streaming kernels sized
+// in multiples of the SM count; none of them is GEMM-shaped.
+#include "common.cuh"
+
+namespace vqb {
+
+// --------------------------------------------------------------------------------------------
+// codebook refresh: one warp per code row
+// --------------------------------------------------------------------------------------------
+template <bool EMA>
+__global__ void __launch_bounds__(256)
+codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restrict__ seg_cnt, float decay,
+                        float omd, float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb,
+                        float* E, uint16_t* __restrict__ E_bf16, float* __restrict__ ee_half,
+                        float* __restrict__ level_meta) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= K_total) return;
+  const int D4 = D >> 2;
+  float denom = 1.f;
+  if (EMA) {
+    // models/vq_vae.py:85: cs.mul_(decay).add_(n * (1 - decay)) -- two roundings, no fma contraction
+    const float cs = __fadd_rn(__fmul_rn(ema_cs[row], decay), __fmul_rn(seg_cnt[row], omd));
+    __syncwarp();
+    if (lane == 0) ema_cs[row] = cs;
+    denom = __fadd_rn(cs, eps);
+  }
+  double acc = 0.0, accb = 0.0;
+  bool bad = false;
+  for (int c = lane; c < D4; c += 32) {
+    const int64_t o = static_cast<int64_t>(row) * D4 + c;
+    float4 e;
+    if (EMA) {
+      const float4 m = reinterpret_cast<const float4*>(ema_emb)[o];
+      const float4 s = reinterpret_cast<const float4*>(seg_sum)[o];
+      float4 n;
+      n.x = __fadd_rn(__fmul_rn(m.x, decay), __fmul_rn(s.x, omd));
+      n.y = __fadd_rn(__fmul_rn(m.y, decay), __fmul_rn(s.y, omd));
+      n.z = __fadd_rn(__fmul_rn(m.z, decay), __fmul_rn(s.z, omd));
+      n.w = __fadd_rn(__fmul_rn(m.w, decay), __fmul_rn(s.w, omd));
+      reinterpret_cast<float4*>(ema_emb)[o] = n;
+      e.x = __fdiv_rn(n.x, denom); e.y = __fdiv_rn(n.y, denom);       // :88 E = es / (cs + eps)
+      e.z = __fdiv_rn(n.z, denom); e.w = __fdiv_rn(n.w, denom);
+      reinterpret_cast<float4*>(E)[o] = e;
+    } else {
+      e = reinterpret_cast<const float4*>(E)[o];
+    }
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(e.x), b1 = __float2bfloat16_rn(e.y),
+                        b2 = __float2bfloat16_rn(e.z), b3 = __float2bfloat16_rn(e.w);
+    uint2 pk;
+    pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(b0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
+    pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(b2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b3)) << 16);
+    reinterpret_cast<uint2*>(E_bf16)[o] = pk;
+    const float f0 = __bfloat162float(b0), f1 = __bfloat162float(b1), f2 = __bfloat162float(b2),
+                f3 = __bfloat162float(b3);
+    acc += static_cast<double>(e.x) * e.x + static_cast<double>(e.y) * e.y +
+           static_cast<double>(e.z) * e.z + static_cast<double>(e.w) * e.w;
+    accb += static_cast<double>(f0) * f0 + static_cast<double>(f1) * f1 + static_cast<double>(f2) * f2 +
+            static_cast<double>(f3) * f3;
+    bad |= !(isfinite(e.x) && isfinite(e.y) && isfinite(e.z) && isfinite(e.w));
+  }
+  acc = warp_sum(acc);
+  accb = warp_sum(accb);
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    ee_half[row] = static_cast<float>(0.5 * acc);
+    ee_half[K_total + row] = static_cast<float>(0.5 * accb);
+    float* meta = level_meta + (row / K_per) * VQB200_LEVEL_META_FLOATS;
+    // round the norms UP a hair: they feed an error bound
+    const float n0 = static_cast<float>(sqrt(acc)) * 1.0000002f, n1 = static_cast<float>(sqrt(accb)) * 1.0000002f;
+    if (n0 == n0 && n0 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 0), __float_as_int(n0));
+    if (n1 == n1 && n1 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 2), __float_as_int(n1));
+    if (bad || !(acc == acc) || isinf(static_cast<float>(acc))) meta[1] = 1.0f;
+  }
+}
+
+int launch_codebook_refresh(bool ema, const float* seg_sum, const float* seg_cnt, float decay, float omd,
+                            float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb, float* E,
+                            uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s) {
+  const int levels = K_total / K_per;
+  cudaError_t e = cudaMemsetAsync(level_meta, 0, sizeof(float) * VQB200_LEVEL_META_FLOATS * levels, s);
+  if (e != cudaSuccess) return status_of(e);
+  const int wpb = 8;
+  const int blocks = (K_total + wpb - 1) / wpb;
+  if (ema)
+    codebook_refresh_kernel<true><<<blocks, wpb * 32, 0, s>>>(seg_sum, seg_cnt, decay, omd, eps, K_total, D,
+                                                             K_per, ema_cs, ema_emb, E, E_bf16, ee_half, level_meta);
+  else
+    codebook_refresh_kernel<false><<<blocks, wpb * 32, 0, s>>>(nullptr, nullptr, 0.f, 0.f, 0.f, K_total, D, K_per,
+                                                              nullptr, nullptr, E, E_bf16, ee_half, level_meta);
+  return status_of(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------------------------
+// gather + straight-through + residual + commitment partial sum + histogram
+// --------------------------------------------------------------------------------------------
+constexpr int ROW_THREADS = 256;
+
+__device__ __forceinline__ void block_add_double(double v, double* dst) {
+  __shared__ double part[ROW_THREADS / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < ROW_THREADS / 32) ? part[threadIdx.x] : 0.0;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(dst, t);
+  }
+}
+
+template <bool ACC>
+__global__ void __launch_bounds__(ROW_THREADS)
+gather_kernel(const float4* __restrict__ z, const float4* __restrict__ E, const int64_t* __restrict__ idx,
+              int64_t N, int D4, int d4_shift, int K_total, float4* zq_out, float4* __restrict__ zq_st_out,
+              float4* __restrict__ residual_out, double* sqerr_sum, int32_t* __restrict__ hist,
+              const uint8_t* __restrict__ row_mask) {
+  const int64_t total = N * D4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  float err = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t row;
+    int c;
+    if (d4_shift >= 0) { row = i >> d4_shift; c = static_cast<int>(i & ((1 << d4_shift) - 1)); }
+    else { row = i / D4; c = static_cast<int>(i - row * D4); }
+    const int64_t k = idx[row];
+    if (k < 0 || k >= K_total) continue;                    // never produced by vqb200_search
+    const float4 e = __ldg(E + k * D4 + c);
+    const float4 v = ld_stream(z + i);
+    float4 df;
+    df.x = __fsub_rn(e.x, v.x); df.y = __fsub_rn(e.y, v.y); df.z = __fsub_rn(e.z, v.z); df.w = __fsub_rn(e.w, v.w);
+    if (zq_out) {
+      float4 o = e;
+      if (ACC) { const float4 p = zq_out[i]; o.x = __fadd_rn(p.x, e.x); o.y = __fadd_rn(p.y, e.y);
+                 o.z = __fadd_rn(p.z, e.z); o.w = __fadd_rn(p.w, e.w); }
+      st_stream(zq_out + i, o);
+    }
+    if (zq_st_out) {                                        // fl(z + fl(zq - z)): bitwise != zq
+      float4 o;
+      o.x = __fadd_rn(v.x, df.x); o.y = __fadd_rn(v.y, df.y); o.z = __fadd_rn(v.z, df.z); o.w = __fadd_rn(v.w, df.w);
+      st_stream(zq_st_out + i, o);
+    }
+    if (residual_out) {                                     // fl(z - zq) (= -df exactly)
+      st_stream(residual_out + i, make_float4(-df.x, -df.y, -df.z, -df.w));
+    }
+    err = fmaf(df.x, df.x, err); err = fmaf(df.y, df.y, err);
+    err = fmaf(df.z, df.z, err); err = fmaf(df.w, df.w, err);
+    if (hist && c == 0 && (!row_mask || row_mask[row])) atomicAdd(hist + k, 1);
+  }
+  if (sqerr_sum) block_add_double(static_cast<double>(err), sqerr_sum);
+}
+
+int launch_gather(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int K_total, float* zq_out,
+                  int zq_accumulate, float* zq_st_out, float* residual_out, double* sqerr_sum, int32_t* hist,
+                  const uint8_t* row_mask, cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  const int D4 = D >> 2;
+  int shift = -1;
+  if ((D4 & (D4 - 1)) == 0) { shift = 0; while ((1 << shift) < D4) ++shift; }
+  const int64_t total = N * D4;
+  int64_t blocks = (total + ROW_THREADS - 1) / ROW_THREADS;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8 * 4;          // 8 resident CTAs/SM, ~4 items per thread
+  if (blocks > cap) blocks = cap;
+  auto Z = reinterpret_cast<const float4*>(z);
+  auto Ev = reinterpret_cast<const float4*>(E);
+  if (zq_accumulate)
+    gather_kernel<true><<<static_cast<unsigned>(blocks), ROW_THREADS, 0, s>>>(
+        Z, Ev, idx, N, D4, shift, K_total, reinterpret_cast<float4*>(zq_out), reinterpret_cast<float4*>(zq_st_out),
+        reinterpret_cast<float4*>(residual_out), sqerr_sum, hist, row_mask);
+  else
+    gather_kernel<false><<<static_cast<unsigned>(blocks), ROW_THREADS, 0, s>>>(
+        Z, Ev, idx, N, D4, shift, K_total, reinterpret_cast<float4*>(zq_out), reinterpret_cast<float4*>(zq_st_out),
+        reinterpret_cast<float4*>(residual_out), sqerr_sum, hist, row_mask);
+  return status_of(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(ROW_THREADS)
+st_loss_kernel(const float4* __restrict__ z, const float4* __restrict__ zq, int64_t n4, float4* __restrict__ st,
+               double* sqerr_sum) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  float err = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ld_stream(z + i), e = ld_stream(zq + i);
+    float4 df;
+    df.x = __fsub_rn(e.x, v.x); df.y = __fsub_rn(e.y, v.y); df.z = __fsub_rn(e.z, v.z); df.w = __fsub_rn(e.w, v.w);
+    if (st) {
+      float4 o;
+      o.x = __fadd_rn(v.x, df.x); o.y = __fadd_rn(v.y, df.y); o.z = __fadd_rn(v.z, df.z); o.w = __fadd_rn(v.w, df.w);
+      st_stream(st + i, o);
+    }
+    err = fmaf(df.x, df.x, err); err = fmaf(df.y, df.y, err);
+    err = fmaf(df.z, df.z, err); err = fmaf(df.w, df.w, err);
+  }
+  if (sqerr_sum) block_add_double(static_cast<double>(err), sqerr_sum);
+}
+
+static unsigned stream_grid(int64_t items) {
+  int64_t blocks = (items + ROW_THREADS - 1) / ROW_THREADS;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
+int launch_st_loss(const float* z, const float* zq, int64_t n_elems, float* st, double* sqerr_sum, cudaStream_t s) {
+  if (n_elems == 0) return VQB200_OK;
+  const int64_t n4 = n_elems >> 2;
+  st_loss_kernel<<<stream_grid(n4), ROW_THREADS, 0, s>>>(reinterpret_cast<const float4*>(z),
+                                                        reinterpret_cast<const float4*>(zq), n4,
+                                                        reinterpret_cast<float4*>(st), sqerr_sum);
+  return status_of(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------------------------
+// statistics: one CTA over the K_total-bin histogram
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+stats_finalize_kernel(const int32_t* __restrict__ hist, int K_total, float count_add,
+                      const double* __restrict__ sqerr_sum, double inv_elems, float* ep_usage, float* ep_cnt,
+                      float* __restrict__ stats_out) {
+  __shared__ double red[32];
+  __shared__ double s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double t = 0.0;
+  for (int k = tid; k < K_total; k += blockDim.x) t += static_cast<double>(hist[k]);
+  t = warp_sum(t);
+  if (lane == 0) red[warp] = t;
+  __syncthreads();
+  if (warp == 0) {
+    double v = (lane < (blockDim.x >> 5)) ? red[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) s_total = v < 1.0 ? 1.0 : v;             // total.clamp_min(1.0)
+  }
+  __syncthreads();
+  const double total = s_total;
+  double h = 0.0, dead = 0.0;
+  for (int k = tid; k < K_total; k += blockDim.x) {
+    const int c = hist[k];
+    if (c > 0) { const double p = static_cast<double>(c) / total; h += p * log(p); }
+    else dead += 1.0;
+    if (ep_usage) ep_usage[k] += static_cast<float>(c);
+  }
+  __syncthreads();
+  h = warp_sum(h);
+  dead = warp_sum(dead);
+  __shared__ double red2[32];
+  if (lane == 0) { red[warp] = h; red2[warp] = dead; }
+  __syncthreads();
+  if (warp == 0) {
+    double a = (lane < (blockDim.x >> 5)) ? red[lane] : 0.0;
+    double b = (lane < (blockDim.x >> 5)) ? red2[lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      const bool any = b < static_cast<double>(K_total);
+      stats_out[0] = any ? static_cast<float>(exp(-a)) : 0.f;
+      stats_out[1] = static_cast<float>(b / static_cast<double>(K_total));
+      stats_out[2] = sqerr_sum ? static_cast<float>(*sqerr_sum * inv_elems) : 0.f;
+      if (ep_cnt) ep_cnt[0] += count_add;
+    }
+  }
+}
+
+int launch_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
+                          double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out, cudaStream_t s) {
+  stats_finalize_kernel<<<1, 1024, 0, s>>>(hist, K_total, count_add, sqerr_sum, inv_elems, ep_usage, ep_cnt,
+                                           stats_out);
+  return status_of(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------------------------
+// EMA segment sums: warp per row, warp-aggregated counts, vector reductions into [K_total, D]
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+scatter_add_kernel(const float4* __restrict__ z, const int64_t* __restrict__ idx,
+                   const uint8_t* __restrict__ row_mask, int64_t N, int D4, int K_total,
+                   float* __restrict__ seg_sum, float* __restrict__ seg_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  // each warp owns 32 consecutive rows per step: lane l looks up row base+l, peers with the same code
+  // are merged so the count costs one atomic per distinct code (warp-aggregated atomics).
+  for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
+    const int64_t my_row = base + lane;
+    int64_t my_k = -1;
+    if (my_row < N && (!row_mask || row_mask[my_row])) {
+      my_k = idx[my_row];
+      if (my_k < 0 || my_k >= K_total) my_k = -1;
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, my_k);
+    if (my_k >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(seg_cnt + my_k, static_cast<float>(__popc(peers)));
+    for (int r = 0; r < 32; ++r) {
+      const int64_t k = __shfl_sync(0xffffffffu, my_k, r);
+      if (k < 0) continue;
+      const float4* src = z + (base + r) * D4;
+      float* dst = seg_sum + k * (static_cast<int64_t>(D4) * 4);
+      for (int c = lane; c < D4; c += 32) red_add_v4(dst + c * 4, ld_stream(src + c));
+    }
+  }
+}
+
+int launch_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
+                       float* seg_sum, float* seg_cnt, cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  int64_t warps = (N + 31) / 32;
+  int64_t blocks = (warps + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
+  if (blocks > cap) blocks = cap;
+  scatter_add_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(reinterpret_cast<const float4*>(z), idx, row_mask,
+                                                                  N, D >> 2, K_total, seg_sum, seg_cnt);
+  return status_of(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------------------------
+// backward
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS)
+commit_backward_kernel(const float4* __restrict__ g, const float* __restrict__ gc, const float4* __restrict__ z,
+                       const float4* __restrict__ zq, int64_t n4, float scale, float4* __restrict__ out) {
+  const float a = gc ? (*gc) * scale : 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = ld_stream(z + i), q = ld_stream(zq + i);
+    float4 o = g ? ld_stream(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x += a * (v.x - q.x); o.y += a * (v.y - q.y); o.z += a * (v.z - q.z); o.w += a * (v.w - q.w);
+    st_stream(out + i, o);
+  }
+}
+
+int launch_commit_backward(const float* g, const float* gc, const float* z, const float* zq, int64_t n_elems,
+                           float scale, float* out, cudaStream_t s) {
+  if (n_elems == 0) return VQB200_OK;
+  const int64_t n4 = n_elems >> 2;
+  commit_backward_kernel<<<stream_grid(n4), ROW_THREADS, 0, s>>>(
+      reinterpret_cast<const float4*>(g), gc, reinterpret_cast<const float4*>(z),
+      reinterpret_cast<const float4*>(zq), n4, scale, reinterpret_cast<float4*>(out));
+  return status_of(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------------------------
+// wire formats
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void relayout_kernel(const int64_t* __restrict__ in, int Q, int64_t B, int64_t M, T* __restrict__ out) {
+  // out[b, m*Q + q] = in[q, b, m]; consecutive threads walk the OUTPUT so stores coalesce
+  const int64_t total = static_cast<int64_t>(Q) * B * M;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t o = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; o < total; o += stride) {
+    const int q = static_cast<int>(o % Q);
+    const int64_t bm = o / Q;
+    out[o] = static_cast<T>(in[static_cast<int64_t>(q) * B * M + bm]);
+  }
+}
+
+int launch_relayout(const int64_t* in, int Q, int64_t B, int64_t M, void* out, int bytes, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(Q) * B * M;
+  if (total == 0) return VQB200_OK;
+  const unsigned grid = stream_grid(total);
+  if (bytes == VQB200_IDX_I16) relayout_kernel<int16_t><<<grid, ROW_THREADS, 0, s>>>(in, Q, B, M, static_cast<int16_t*>(out));
+  else if (bytes == VQB200_IDX_I32) relayout_kernel<int32_t><<<grid, ROW_THREADS, 0, s>>>(in, Q, B, M, static_cast<int32_t*>(out));
+  else if (bytes == VQB200_IDX_I64) relayout_kernel<int64_t><<<grid, ROW_THREADS, 0, s>>>(in, Q, B, M, static_cast<int64_t*>(out));
+  else return VQB200_EINVAL;
+  return status_of(cudaGetLastError());
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ROW_THREADS)
+indices_to_latent_kernel(const T* __restrict__ idx, int64_t n_tok, int Q, const float4* __restrict__ E, int K_total,
+                         int D4, float4* __restrict__ out) {
+  const int64_t total = n_tok * D4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t tok = i / D4;
+    const int c = static_cast<int>(i - tok * D4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < Q; ++q) {                           // level order 0..Q-1, as torch's sum(dim=2)
+      const int64_t k = static_cast<int64_t>(idx[tok * Q + q]);
+      if (k < 0 || k >= K_total) continue;
+      const float4 e = __ldg(E + k * D4 + c);
+      if (q == 0) acc = e;
+      else { acc.x = __fadd_rn(acc.x, e.x); acc.y = __fadd_rn(acc.y, e.y); acc.z = __fadd_rn(acc.z, e.z); acc.w = __fadd_rn(acc.w, e.w); }
+    }
+    st_stream(out + i, acc);
+  }
+}
+
+int launch_indices_to_latent(const void* idx, int bytes, int64_t n_tok, int Q, const float* E, int K_total, int D,
+                             float* out, cudaStream_t s) {
+  if (n_tok == 0) return VQB200_OK;
+  const int D4 = D >> 2;
+  const unsigned grid = stream_grid(n_tok * D4);
+  auto Ev = reinterpret_cast<const float4*>(E);
+  auto O = reinterpret_cast<float4*>(out);
+  if (bytes == VQB200_IDX_I16) indices_to_latent_kernel<int16_t><<<grid, ROW_THREADS, 0, s>>>(static_cast<const int16_t*>(idx), n_tok, Q, Ev, K_total, D4, O);
+  else if (bytes == VQB200_IDX_I32) indices_to_latent_kernel<int32_t><<<grid, ROW_THREADS, 0, s>>>(static_cast<const int32_t*>(idx), n_tok, Q, Ev, K_total, D4, O);
+  else if (bytes == VQB200_IDX_I64) indices_to_latent_kernel<int64_t><<<grid, ROW_THREADS, 0, s>>>(static_cast<const int64_t*>(idx), n_tok, Q, Ev, K_total, D4, O);
+  else return VQB200_EINVAL;
+  return status_of(cudaGetLastError());
+}
+
+__global__ void minloc_unpack_kernel(const uint64_t* __restrict__ p, int64_t N, int64_t* __restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride)
+    out[i] = static_cast<int64_t>(p[i] & 0xffffffffull);
+}
+
+int launch_minloc_unpack(const uint64_t* p, int64_t N, int64_t* out, cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  minloc_unpack_kernel<<<stream_grid(N), ROW_THREADS, 0, s>>>(p, N, out);
+  return status_of(cudaGetLastError());
+}
+
+}  // namespace vqb

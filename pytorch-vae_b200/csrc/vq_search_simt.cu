@@ -1,0 +1,134 @@
+// Exact nearest-code search on the fp32 CUDA cores, fused with the row argmin.
+//
+// Role: (1) the arbiter path for rows / codebooks the tensor-core kernel hands back (non-finite
+// values, candidate-list overflow), (2) every shape the tensor-core kernel does not take,
+// (3) the codebook-sharded packed min-loc search.  It is a register-tiled SGEMM
+// (128 rows x 128 codes per CTA, 8x8 per thread) whose epilogue keeps a running
+// (distance, index) minimum per row, so the N x K matrix never leaves the SM.
+//
+// Distance used: d' = |e|^2/2 - z.e  (the row-constant |z|^2 is dropped: it does not change the
+// argmin and only adds rounding noise).  z.e is one fp32 FMA chain over
+// D in ascending order, identical for every tile position, so bit-identical code rows give
+// bit-identical distances and the lowest index wins, as in torch.argmin.
+#include "common.cuh"
+
+namespace vqb {
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
+constexpr int SIMT_THREADS = 256;
+constexpr int PAD = 4;
+
+template <bool ROUND_BF16>
+__global__ void __launch_bounds__(SIMT_THREADS, 2)
+search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_list, int64_t n_rows,
+                   int D, const float* __restrict__ E, const float* __restrict__ ee_half, int K,
+                   int64_t idx_offset, int64_t* __restrict__ idx_out, uint64_t* __restrict__ packed_out) {
+  __shared__ float zs[BK][BM + PAD];
+  __shared__ float es[BK][BN + PAD];
+  __shared__ float ees[BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * BM;
+
+  // rows this thread stages into shared memory (2 float4 per tile step)
+  const int ld_r = tid >> 2, ld_c = (tid & 3) * 4;
+  int64_t src_row[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int64_t r = row0 + ld_r + 64 * i;
+    src_row[i] = (r < n_rows) ? (row_list ? static_cast<int64_t>(row_list[r]) : r) : -1;
+  }
+
+  uint64_t best[TM];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) best[i] = ~0ull;
+
+  for (int n0 = 0; n0 < K; n0 += BN) {
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    if (tid < BN) ees[tid] = (n0 + tid < K) ? ee_half[n0 + tid] : __int_as_float(0x7f800000);
+
+    for (int k0 = 0; k0 < D; k0 += BK) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src_row[i] >= 0 && k0 + ld_c < D)
+          v = *reinterpret_cast<const float4*>(z + src_row[i] * D + k0 + ld_c);
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        int code = n0 + ld_r + 64 * i;
+        if (code < K && k0 + ld_c < D)
+          w = *reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + k0 + ld_c);
+        if (ROUND_BF16) {
+          v.x = bf16_round(v.x); v.y = bf16_round(v.y); v.z = bf16_round(v.z); v.w = bf16_round(v.w);
+          w.x = bf16_round(w.x); w.y = bf16_round(w.y); w.z = bf16_round(w.z); w.w = bf16_round(w.w);
+        }
+        const int r = ld_r + 64 * i;
+        zs[ld_c + 0][r] = v.x; zs[ld_c + 1][r] = v.y; zs[ld_c + 2][r] = v.z; zs[ld_c + 3][r] = v.w;
+        es[ld_c + 0][r] = w.x; es[ld_c + 1][r] = w.y; es[ld_c + 2][r] = w.z; es[ld_c + 3][r] = w.w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[TM], b[TN];
+        *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&zs[k][ty * TM]);
+        *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&zs[k][ty * TM + 4]);
+        *reinterpret_cast<float4*>(&b[0]) = *reinterpret_cast<const float4*>(&es[k][tx * TN]);
+        *reinterpret_cast<float4*>(&b[4]) = *reinterpret_cast<const float4*>(&es[k][tx * TN + 4]);
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+
+    // fused argmin epilogue: packed (key(d'), code) minima, reduced over the 16 threads of a row
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      uint64_t m = ~0ull;
+#pragma unroll
+      for (int j = 0; j < TN; ++j) {
+        const int code = n0 + tx * TN + j;
+        if (code < K) m = umin64(m, pack_minloc(ees[tx * TN + j] - acc[i][j], static_cast<uint32_t>(code)));
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) m = umin64(m, __shfl_xor_sync(0xffffffffu, m, o));
+      best[i] = umin64(best[i], m);
+    }
+  }
+
+  if (tx == 0) {
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int64_t r = row0 + ty * TM + i;
+      if (r >= n_rows) continue;
+      const int64_t dst = row_list ? static_cast<int64_t>(row_list[r]) : r;
+      if (packed_out) packed_out[dst] = (best[i] & 0xffffffff00000000ull) |
+                                        static_cast<uint64_t>((best[i] & 0xffffffffull) + idx_offset);
+      if (idx_out) idx_out[dst] = static_cast<int64_t>(best[i] & 0xffffffffull) + idx_offset;
+    }
+  }
+}
+
+int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, int D, const float* E,
+                       const float* ee_half, int K, int round_bf16, int64_t idx_offset, int64_t* idx_out,
+                       uint64_t* packed_out, cudaStream_t s) {
+  if (n_rows == 0) return VQB200_OK;
+  const int64_t blocks = (n_rows + BM - 1) / BM;
+  if (blocks > 0x7fffffff) return VQB200_ESHAPE;
+  dim3 grid(static_cast<unsigned>(blocks));
+  if (round_bf16)
+    search_simt_kernel<true><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows, D, E, ee_half, K, idx_offset,
+                                                          idx_out, packed_out);
+  else
+    search_simt_kernel<false><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows, D, E, ee_half, K, idx_offset,
+                                                           idx_out, packed_out);
+  return status_of(cudaGetLastError());
+}
+
+}  // namespace vqb

@@ -1,0 +1,178 @@
+"""Tensor-level wrappers over the C ABI: validate, pass raw pointers, count kernel launches.
+
+PyTorch is plumbing here (device memory, the current stream); every function
+below enqueues hand-written sm_100a kernels from libvqb200.so and nothing else.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+from ._cabi import check, lib, ptr, stream_ptr
+
+# kernels launched by this process through the library (bench.py reports the delta per step)
+_launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _count(n: int):
+    global _launches
+    _launches += n
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pytorch-vae_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+
+
+def _f32c(t, name):
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+class CodebookCache:
+    """Per-code data derived from the codebook: bf16 copy, |e|^2/2 (fp32 and bf16-rounded), level norms."""
+
+    def __init__(self, K_total: int, D: int, K_per: int, device):
+        self.K_total, self.D, self.K_per = K_total, D, K_per
+        self.levels = K_total // K_per
+        self.E_bf16 = torch.empty(K_total, D, dtype=torch.bfloat16, device=device)
+        self.ee_half = torch.empty(2, K_total, dtype=torch.float32, device=device)
+        self.level_meta = torch.empty(self.levels, _cabi.LEVEL_META_FLOATS, dtype=torch.float32, device=device)
+        self.key = None
+
+    def prepare(self, E: torch.Tensor):
+        _need_cuda(E)
+        _f32c(E, "embedding")
+        check(lib.vqb200_codebook_prepare(ptr(E), self.K_total, self.D, self.K_per, ptr(self.E_bf16),
+                                          ptr(self.ee_half), ptr(self.level_meta), stream_ptr()),
+              "vqb200_codebook_prepare")
+        _count(1)
+
+
+def search(z: torch.Tensor, E: torch.Tensor, cache: CodebookCache, level: int, mode: int,
+           idx_out: torch.Tensor, idx_offset: int | None = None):
+    """idx_out[n] = idx_offset + argmin_k |z_n - E[level*K_per + k]|^2 (one level)."""
+    _need_cuda(z, E, idx_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    K = cache.K_per
+    s = level * K
+    if idx_offset is None:
+        idx_offset = s
+    ws_bytes = lib.vqb200_search_workspace_bytes(N, K, D, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    esz = E.element_size()
+    check(lib.vqb200_search(ptr(z), N, D, E.data_ptr() + s * D * esz, cache.E_bf16.data_ptr() + s * D * 2,
+                            cache.ee_half.data_ptr() + s * 4, cache.ee_half.data_ptr() + (cache.K_total + s) * 4,
+                            cache.level_meta.data_ptr() + level * _cabi.LEVEL_META_FLOATS * 4, K, mode,
+                            idx_offset, ptr(idx_out), ptr(ws), ws_bytes, stream_ptr()), "vqb200_search")
+    _count(search_launches(N, K, D, mode))
+
+
+def search_launches(N, K, D, mode) -> int:
+    return 1 if lib.vqb200_search_path(N, K, D, mode) == 0 else 3
+
+
+def gather(z, E, idx, zq_out=None, accumulate=False, zq_st_out=None, residual_out=None, sqerr_sum=None,
+           hist=None, row_mask=None):
+    _need_cuda(z, E, idx)
+    _f32c(z, "z")
+    N, D = z.shape
+    check(lib.vqb200_gather(ptr(z), ptr(E), ptr(idx), N, D, E.shape[0], ptr(zq_out), int(accumulate),
+                            ptr(zq_st_out), ptr(residual_out), ptr(sqerr_sum), ptr(hist), ptr(row_mask),
+                            stream_ptr()), "vqb200_gather")
+    _count(1)
+
+
+def st_loss(z, zq, zq_st_out=None, sqerr_sum=None):
+    _need_cuda(z, zq)
+    check(lib.vqb200_st_loss(ptr(z), ptr(zq), z.numel(), ptr(zq_st_out), ptr(sqerr_sum), stream_ptr()),
+          "vqb200_st_loss")
+    _count(1)
+
+
+def stats_finalize(hist, count_add, sqerr_sum, inv_elems, ep_usage, ep_cnt, stats_out):
+    check(lib.vqb200_stats_finalize(ptr(hist), hist.numel(), float(count_add), ptr(sqerr_sum), float(inv_elems),
+                                    ptr(ep_usage), ptr(ep_cnt), ptr(stats_out), stream_ptr()),
+          "vqb200_stats_finalize")
+    _count(1)
+
+
+def scatter_add(z, idx, row_mask, seg_sum, seg_cnt):
+    _need_cuda(z, idx, seg_sum)
+    _f32c(z, "z")
+    N, D = z.shape
+    check(lib.vqb200_scatter_add(ptr(z), ptr(idx), ptr(row_mask), N, D, seg_cnt.numel(), ptr(seg_sum),
+                                 ptr(seg_cnt), stream_ptr()), "vqb200_scatter_add")
+    _count(1)
+
+
+def ema_finalize(seg_sum, seg_cnt, decay, eps, ema_cluster_size, ema_embedding, E, cache: CodebookCache):
+    # the reference forms (1 - decay) in Python double and the multiply rounds it to fp32
+    check(lib.vqb200_ema_finalize(ptr(seg_sum), ptr(seg_cnt), float(decay), float(1 - decay), float(eps),
+                                  cache.K_total, cache.D, cache.K_per, ptr(ema_cluster_size), ptr(ema_embedding),
+                                  ptr(E), ptr(cache.E_bf16), ptr(cache.ee_half), ptr(cache.level_meta),
+                                  stream_ptr()), "vqb200_ema_finalize")
+    _count(1)
+
+
+def commit_backward(grad_st, grad_commit, z, zq, scale, out):
+    check(lib.vqb200_commit_backward(ptr(grad_st), ptr(grad_commit), ptr(z), ptr(zq), z.numel(), float(scale),
+                                     ptr(out), stream_ptr()), "vqb200_commit_backward")
+    _count(1)
+
+
+_IDX_BYTES = {torch.int16: 2, torch.int32: 4, torch.int64: 8}
+
+
+def relayout_indices(idx_level_major: torch.Tensor, Q: int, B: int, M: int, dtype=torch.int64) -> torch.Tensor:
+    """Level-major flat RVQ ids [Q*B*M] -> token-major [B, M*Q] (optionally narrowed), on the device."""
+    _need_cuda(idx_level_major)
+    if idx_level_major.dtype != torch.int64 or idx_level_major.numel() != Q * B * M:
+        raise RuntimeError(f"expected {Q * B * M} int64 indices, got {tuple(idx_level_major.shape)} "
+                           f"{idx_level_major.dtype}")
+    out = torch.empty(B, M * Q, dtype=dtype, device=idx_level_major.device)
+    check(lib.vqb200_relayout_indices(ptr(idx_level_major.contiguous()), Q, B, M, ptr(out), _IDX_BYTES[dtype],
+                                      stream_ptr()), "vqb200_relayout_indices")
+    _count(1)
+    return out
+
+
+def indices_to_latent(idx: torch.Tensor, E: torch.Tensor, Q: int) -> torch.Tensor:
+    """Token-major ids [n_tok*Q] -> z_q [n_tok, D], summing the Q levels in level order."""
+    _need_cuda(idx, E)
+    _f32c(E, "embedding")
+    if idx.dtype not in _IDX_BYTES:
+        raise RuntimeError(f"indices must be int16/int32/int64, got {idx.dtype}")
+    idx = idx.contiguous().view(-1)
+    if idx.numel() % Q != 0:
+        raise ValueError(f"flattened indices length {idx.numel()} is not divisible by num_quantizers={Q}")
+    n_tok = idx.numel() // Q
+    out = torch.empty(n_tok, E.shape[1], dtype=torch.float32, device=E.device)
+    check(lib.vqb200_indices_to_latent(ptr(idx), _IDX_BYTES[idx.dtype], n_tok, Q, ptr(E), E.shape[0], E.shape[1],
+                                       ptr(out), stream_ptr()), "vqb200_indices_to_latent")
+    _count(1)
+    return out
+
+
+def search_packed(z, E_slice, ee_half_slice, idx_offset, packed_out):
+    """Codebook-sharded search: packed[n] = key(d) << 32 | (idx_offset + argmin) over this shard's codes."""
+    _need_cuda(z, E_slice, packed_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    check(lib.vqb200_search_packed(ptr(z), N, D, ptr(E_slice), ptr(ee_half_slice), E_slice.shape[0], idx_offset,
+                                   ptr(packed_out), stream_ptr()), "vqb200_search_packed")
+    _count(1)
+
+
+def minloc_unpack(packed, idx_out):
+    check(lib.vqb200_minloc_unpack(ptr(packed), packed.numel(), ptr(idx_out), stream_ptr()),
+          "vqb200_minloc_unpack")
+    _count(1)

@@ -1,0 +1,333 @@
+"""B200-native drop-in for the reference's EMA vector quantizer.
+
+Mirrors the public surface of ``models/vq_vae.py:19-282`` (class
+``VectorQuantizerEMA``): constructor keywords, the nine registered buffers
+(so reference checkpoints load with ``strict=True``), ``forward`` returning
+``(z_q_st, z_q, indices, stats)``, ``_ema_update``, ``_maybe_reinit_dead_codes``,
+``reset_epoch_stats`` / ``get_epoch_stats`` / ``get_embedding_snapshot`` and the
+attributes callers poke (``K, K_per, D, num_quantizers, beta, decay, eps,
+embedding``).  All arithmetic runs in libvqb200.so (hand-written sm_100a
+kernels); this file is host-side sequencing only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _cabi, ops, sharding
+
+Tensor = torch.Tensor
+
+_MODES = {"fp32": _cabi.MODE_FP32_EXACT, "bf16_input": _cabi.MODE_BF16_INPUT}
+
+
+class _QuantizeFn(torch.autograd.Function):
+    """Forward of the whole quantizer; backward of its two differentiable outputs.
+
+    Outputs: z_q_st (grad -> identity to z_e), z_q, indices, stats
+    (non-differentiable) and the commitment mse ``mean((z_q - z_e)^2)`` whose gradient
+    w.r.t. z_e is ``2 (z_e - z_q) / (N D)`` (models/vq_vae.py:1293).
+    """
+
+    @staticmethod
+    def forward(ctx, z_e: Tensor, q: "VectorQuantizerEMA", do_ema: bool, mask: Optional[Tensor]):
+        z_q_st, z_q, indices, stats3 = q._run(z_e, do_ema, mask)
+        stats = stats3[:2]
+        commit = stats3[2]
+        ctx.save_for_backward(z_e, z_q)
+        ctx.mark_non_differentiable(z_q, indices, stats)
+        return z_q_st, z_q, indices, stats, commit
+
+    @staticmethod
+    def backward(ctx, g_st, _g_zq, _g_idx, _g_stats, g_commit):
+        z_e, z_q = ctx.saved_tensors
+        if g_st is None and g_commit is None:
+            return None, None, None, None
+        if g_commit is None:
+            return g_st, None, None, None                     # pure straight-through: no kernel at all
+        z = z_e.detach().contiguous()
+        out = torch.empty_like(z)
+        gst = None if g_st is None else g_st.contiguous()
+        gc = g_commit.to(torch.float32).contiguous()
+        ops.commit_backward(gst, gc, z, z_q.contiguous(), 2.0 / z.numel(), out)
+        return out.view_as(z_e), None, None, None
+
+
+class VectorQuantizerEMA(nn.Module):
+    """Nearest-code quantizer with EMA codebook; single level or residual (``num_quantizers > 1``).
+
+    ``num_embeddings`` is per level, as in the reference (models/vq_vae.py:37-38).
+    Extra keyword (not in the reference): ``search_mode`` = ``"fp32"`` (reference-exact
+    indices) or ``"bf16_input"`` (inputs rounded to bf16, fp32 products and sums).
+    """
+
+    def __init__(
+        self,
+        num_embeddings: int,
+        embedding_dim: int,
+        beta: float = 0.25,
+        decay: float = 0.98,
+        eps: float = 1e-5,
+        reinit_dead_codes: bool = True,
+        reinit_prob: float = 1.0,
+        dead_usage_threshold: int = 0,
+        print_init: bool = True,
+        diag_qe_cap: float = 10.0,
+        diag_qe_bins: int = 64,
+        num_quantizers: int = 1,
+        search_mode: str = "fp32",
+    ):
+        super().__init__()
+        self.num_quantizers = int(num_quantizers)
+        self.K_per = int(num_embeddings)
+        self.K = self.num_quantizers * self.K_per
+        self.D = int(embedding_dim)
+        if self.D % 4 != 0:
+            raise ValueError(f"embedding_dim must be a multiple of 4 for the 128-bit row kernels, got {self.D}")
+        if not 1 <= self.num_quantizers <= _cabi.MAX_LEVELS:
+            raise ValueError(f"num_quantizers must be in [1, {_cabi.MAX_LEVELS}]")
+        if search_mode not in _MODES:
+            raise ValueError(f"search_mode must be one of {sorted(_MODES)}")
+        self.search_mode = search_mode
+
+        self.beta = float(beta)
+        self.decay = float(decay)
+        self.eps = float(eps)
+        self.use_ema = True
+        self.reinit_dead_codes = bool(reinit_dead_codes)
+        self.reinit_prob = float(reinit_prob)
+        self.dead_usage_threshold = int(dead_usage_threshold)
+        self.diag_qe_cap = float(diag_qe_cap)
+        self.diag_qe_bins = int(diag_qe_bins)
+        # multi-GPU policy: "local" = reference behaviour (each rank
+        # updates from its own shard), "allreduce" = segment sums summed over ranks before the EMA.
+        self.ema_sync = "local"
+        self.stats_sync = False
+
+        # same nine buffers, same order, same init law as models/vq_vae.py:50-62
+        self.register_buffer("embedding", torch.randn(self.K, self.D) * (1.0 / math.sqrt(self.D)))
+        self.register_buffer("ema_cluster_size", torch.zeros(self.K))
+        self.register_buffer("ema_embedding", torch.zeros(self.K, self.D))
+        self.register_buffer("_ep_usage", torch.zeros(self.K))
+        self.register_buffer("_ep_top1_sum", torch.zeros(1))
+        self.register_buffer("_ep_top2_sum", torch.zeros(1))
+        self.register_buffer("_ep_cnt", torch.zeros(1))
+        self.register_buffer("_ep_qe_sum", torch.zeros(1))
+        self.register_buffer("_ep_qe_hist", torch.zeros(self.diag_qe_bins))
+
+        self._cache: Optional[ops.CodebookCache] = None
+        self.last_commit: Optional[Tensor] = None      # autograd-connected mean((z_q - z_e)^2) of the last forward
+        self._last_pair = None
+
+        if print_init:
+            kind = (f"[RVQ] EMA (L2): L={self.num_quantizers}, K_per={self.K_per}, K_total={self.K}"
+                    if self.num_quantizers > 1 else f"[VQ] EMA (L2): K={self.K}")
+            print(f"{kind}, D={self.D}, beta={self.beta}, decay={self.decay} [libvqb200 sm_100a]")
+
+    # ------------------------------------------------------------------ cache
+    def _codebook_cache(self) -> ops.CodebookCache:
+        """``embedding`` is the source of truth: it is mutated from outside at any time (load_state_dict,
+        init_codebook_from_centroids, dead-code re-init), so the derived cache is keyed on its storage
+        and version counter and rebuilt whenever either moves."""
+        E = self.embedding
+        if E.dtype != torch.float32 or not E.is_contiguous():
+            raise RuntimeError("quantizer.embedding must be a contiguous float32 tensor")
+        c = self._cache
+        if c is None or c.E_bf16.device != E.device:
+            c = self._cache = ops.CodebookCache(self.K, self.D, self.K_per, E.device)
+        key = (E.data_ptr(), E._version)
+        if c.key != key:
+            c.prepare(E)
+            c.key = key
+        return c
+
+    # ------------------------------------------------------------------ EMA
+    @torch.no_grad()
+    def _ema_update(self, flat_raw: Tensor, indices: Tensor, row_mask: Optional[Tensor] = None):
+        """models/vq_vae.py:77-89 without the dense one-hot: segment sums by scatter-add, then the
+        lerp / divide for ALL codes fused with the cache refresh."""
+        if flat_raw.numel() == 0 or indices.numel() == 0:
+            return
+        cache = self._codebook_cache()
+        flat = flat_raw.detach().reshape(-1, self.D).contiguous()
+        idx = indices.detach().reshape(-1).contiguous()
+        seg = torch.zeros(self.K * self.D + self.K, dtype=torch.float32, device=flat.device)
+        seg_sum, seg_cnt = seg[: self.K * self.D], seg[self.K * self.D:]
+        ops.scatter_add(flat, idx, row_mask, seg_sum, seg_cnt)
+        if self.ema_sync == "allreduce" and sharding.dist_ready():
+            torch.distributed.all_reduce(seg)
+        ops.ema_finalize(seg_sum, seg_cnt, self.decay, self.eps, self.ema_cluster_size, self.ema_embedding,
+                         self.embedding, cache)
+        cache.key = (self.embedding.data_ptr(), self.embedding._version)
+
+    @torch.no_grad()
+    def _maybe_reinit_dead_codes(self, flat_raw: Tensor, usage: Tensor):
+        """models/vq_vae.py:91-107: rare (every 500 steps), host RNG + one host sync, stays in PyTorch."""
+        if not self.reinit_dead_codes or self.reinit_prob <= 0.0:
+            return
+        dead = usage <= float(self.dead_usage_threshold)
+        n_dead = int(dead.sum().item())
+        if n_dead <= 0 or flat_raw.numel() == 0:
+            return
+        if torch.rand(()) > self.reinit_prob:
+            return
+        rows = torch.randint(0, flat_raw.size(0), (n_dead,), device=flat_raw.device)
+        fresh = flat_raw[rows]
+        self.embedding[dead] = fresh
+        self.ema_embedding[dead] = fresh.clone()
+        self.ema_cluster_size[dead] = 1.0
+
+    # ------------------------------------------------------------------ epoch statistics
+    @torch.no_grad()
+    def reset_epoch_stats(self):
+        for name in ("_ep_usage", "_ep_top1_sum", "_ep_top2_sum", "_ep_cnt", "_ep_qe_sum", "_ep_qe_hist"):
+            getattr(self, name).zero_()
+
+    @torch.no_grad()
+    def get_epoch_stats(self) -> dict:
+        """Same keys and formulas as models/vq_vae.py:118-164 (margin/qe fields are never written by
+        the reference either, so they stay 0)."""
+        usage = self._ep_usage.detach().cpu()
+        cnt = float(self._ep_cnt.item())
+        out = {"usage_hist": usage, "margin_mean": 0.0, "qe_mean": 0.0, "qe_p90": 0.0, "n_positions": 0,
+               "perplexity": 0.0, "dead_ratio": 0.0}
+        if cnt <= 0:
+            return out
+        out["n_positions"] = int(cnt)
+        out["margin_mean"] = float(((self._ep_top1_sum - self._ep_top2_sum) / cnt).item())
+        out["qe_mean"] = float((self._ep_qe_sum / cnt).item())
+        total = float(usage.sum().item())
+        if total > 0:
+            p = (usage / max(total, 1e-12)).clamp_min(1e-12)
+            out["perplexity"] = float(torch.exp(-(p * p.log()).sum()).item())
+            out["dead_ratio"] = float((usage == 0).float().mean().item())
+        hist = self._ep_qe_hist.detach().cpu()
+        mass = float(hist.sum().item())
+        if mass > 0:
+            cdf = torch.cumsum(hist, 0) / max(mass, 1e-12)
+            hit = (cdf >= 0.9).nonzero(as_tuple=True)[0]
+            b = int(hit[0].item()) if hit.numel() else self.diag_qe_bins - 1
+            out["qe_p90"] = float((b + 0.5) * self.diag_qe_cap / max(self.diag_qe_bins, 1))
+        return out
+
+    @torch.no_grad()
+    def get_embedding_snapshot(self) -> Tensor:
+        return self.embedding.detach().clone()
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, z_e: Tensor, do_ema_update: bool = True, allow_reinit: bool = True,
+                mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+        B, M, D = z_e.shape                                    # non-3-D input -> ValueError, like the reference
+        if not z_e.is_cuda:
+            raise RuntimeError("VectorQuantizerEMA (libvqb200) needs CUDA tensors on an sm_100a device; "
+                               "there is no CPU fallback")
+        if z_e.dtype != torch.float32:
+            raise RuntimeError(f"expected z_e of dtype float32 (the codebook's dtype), got {z_e.dtype}")
+        if D != self.D:
+            raise RuntimeError(f"z_e has last dim {D}, the codebook has D={self.D}")
+        do_ema = bool(self.training and do_ema_update)
+        z_q_st, z_q, indices, stats, commit = _QuantizeFn.apply(z_e, self, do_ema, mask)
+        self.last_commit = commit
+        self._last_pair = (z_q, z_e)
+        return z_q_st, z_q, indices, stats
+
+    def commitment_loss(self, z_q: Tensor, z_e: Tensor) -> Tensor:
+        """``F.mse_loss(z_q.detach(), z_e)`` (models/vq_vae.py:1293).  When called with the pair the
+        last forward produced, returns the value the gather pass already accumulated (its backward is
+        the fused commit_backward kernel); otherwise runs the fused st_loss kernel on the pair."""
+        if self._last_pair is not None and z_q is self._last_pair[0] and z_e is self._last_pair[1]:
+            return self.last_commit
+        return _CommitFn.apply(z_e, z_q.detach())
+
+    # the actual work; runs under no_grad inside _QuantizeFn.forward
+    def _run(self, z_e: Tensor, do_ema: bool, mask: Optional[Tensor]):
+        B, M, D = z_e.shape
+        dev = z_e.device
+        flat = z_e.detach().reshape(-1, D)
+        if not flat.is_contiguous():
+            flat = flat.contiguous()
+        N = flat.shape[0]
+        mode = _MODES[self.search_mode]
+        cache = self._codebook_cache()
+        E = self.embedding
+        L = self.num_quantizers
+
+        # one zeroed scratch: [sqerr_sum (double) | hist int32[K]]
+        scratch = torch.zeros(2 + self.K, dtype=torch.int32, device=dev)
+        sqerr = scratch[:2].view(torch.float64)
+        hist = scratch[2:]
+        stats3 = torch.empty(3, dtype=torch.float32, device=dev)
+        z_q = torch.empty(N, D, dtype=torch.float32, device=dev)
+        z_q_st = torch.empty(N, D, dtype=torch.float32, device=dev)
+
+        valid_u8 = None
+        if mask is not None:
+            valid_u8 = mask.reshape(-1).to(device=dev, dtype=torch.uint8).contiguous()
+        # the reference skips the EMA entirely when no row is valid (:196,253): same host sync, mask only
+        ema_ok = do_ema and N > 0 and (valid_u8 is None or bool(valid_u8.any()))
+
+        if L == 1:
+            idx = torch.empty(N, dtype=torch.int64, device=dev)
+            if N > 0:
+                ops.search(flat, E, cache, 0, mode, idx)
+                ops.gather(flat, E, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist,
+                           row_mask=valid_u8)                # z_q is gathered BEFORE the EMA mutates E (:189 -> :193)
+                if ema_ok:
+                    self._ema_update(flat, idx, valid_u8)
+            self._finalize_stats(hist, float(N), sqerr, N * D, stats3)
+            return z_q_st.view(B, M, D), z_q.view(B, M, D), idx.view(B, M), stats3
+
+        idx_all = torch.empty(L * N, dtype=torch.int64, device=dev)   # level-major, global ids (:260)
+        if N > 0:
+            residual = flat
+            spare = [torch.empty(N, D, dtype=torch.float32, device=dev) for _ in range(min(2, L - 1))]
+            for level in range(L):
+                idx_l = idx_all[level * N:(level + 1) * N]
+                if level > 0 and do_ema:
+                    cache = self._codebook_cache()
+                ops.search(residual, E, cache, level, mode, idx_l)
+                nxt = spare[level % 2] if level < L - 1 else None
+                # level sum in level order (:261); RVQ histogram ignores the mask (:266)
+                ops.gather(residual, E, idx_l, zq_out=z_q, accumulate=level > 0, residual_out=nxt, hist=hist)
+                if ema_ok:
+                    self._ema_update(residual, idx_l, valid_u8)
+                if nxt is not None:
+                    residual = nxt
+            ops.st_loss(flat, z_q, zq_st_out=z_q_st, sqerr_sum=sqerr)
+        self._finalize_stats(hist, float(L * N), sqerr, N * D, stats3)
+        return z_q_st.view(B, M, D), z_q.view(B, M, D), idx_all, stats3
+
+    def _finalize_stats(self, hist, count_add, sqerr, n_elems, stats3):
+        inv = 1.0 / max(n_elems, 1)
+        if self.stats_sync and sharding.dist_ready():
+            # global statistics: ONE small all-reduce instead of the reference's
+            # per-rank perplexities averaged by sync_dist
+            sqerr, hist = sharding.allreduce_stats(sqerr, n_elems, hist)    # sqerr is now the global mean
+            inv = 1.0
+        ops.stats_finalize(hist, count_add, sqerr, inv, self._ep_usage, self._ep_cnt, stats3)
+
+
+class _CommitFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z_e, z_q):
+        z = z_e.detach().contiguous()
+        zq = z_q.contiguous()
+        sq = torch.zeros(1, dtype=torch.float64, device=z.device)
+        ops.st_loss(z, zq, None, sq)
+        ctx.save_for_backward(z, zq)
+        ctx.shape = z_e.shape
+        return (sq / max(z.numel(), 1)).to(torch.float32).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        z, zq = ctx.saved_tensors
+        out = torch.empty_like(z)
+        ops.commit_backward(None, g.to(torch.float32).contiguous(), z, zq, 2.0 / z.numel(), out)
+        return out.view(ctx.shape), None
+
+
+# north-star name for the same class (BASELINE.json calls it VectorQuantizer)
+VectorQuantizer = VectorQuantizerEMA

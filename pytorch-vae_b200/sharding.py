@@ -1,0 +1,78 @@
+"""Multi-GPU layout of the path: one process per GPU, rows sharded, codebook replicated.
+
+Rows are independent, so the forward needs NO data-path collective.  The only
+exchanges are (1) one small all-reduce(SUM) of ``[sum sq err | element count | histogram]`` for
+global statistics / loss, (2) in training one all-reduce(SUM) of the EMA segment sums, and
+(3) for codebooks too large to replicate, an all-reduce(MIN) over packed ``(distance key, index)``
+words.  Everything here is backend-agnostic host logic (NCCL on the GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+_SIGN = -(2 ** 63)
+
+
+def shard_rows(n_rows: int, world: int, rank: int):
+    """Contiguous balanced partition of ``n_rows``: the first ``n_rows % world`` ranks get one extra row.
+    (The reference pads by duplicating samples, scripts/extract_code_indices.py:135-140; a contiguous
+    split needs no padding and keeps every row exactly once.)"""
+    base, extra = divmod(int(n_rows), int(world))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_codes(k_codes: int, world: int, rank: int, multiple: int = 8):
+    """Contiguous code ranges for the codebook-sharded search, aligned to ``multiple`` codes."""
+    per = -(-k_codes // world)
+    per = -(-per // multiple) * multiple
+    start = min(rank * per, k_codes)
+    return start, min(start + per, k_codes)
+
+
+def dist_ready() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def allreduce_stats(sqerr_sum: torch.Tensor, n_elems: int, hist: torch.Tensor, group=None):
+    """ONE all-reduce of ``[sum sq err | element count | histogram]`` (float64: counts stay exact to 2^53).
+
+    Returns (global mean sq err as float64[1], global histogram as int32[K]).
+    """
+    pack = torch.cat([sqerr_sum.reshape(1).to(torch.float64),
+                      torch.tensor([float(n_elems)], dtype=torch.float64, device=hist.device),
+                      hist.to(torch.float64)])
+    dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
+    mean = (pack[:1] / pack[1:2].clamp_min(1.0)).contiguous()
+    return mean, pack[2:].to(torch.int32)
+
+
+def allreduce_minloc(packed: torch.Tensor, group=None) -> torch.Tensor:
+    """Tie-stable min-loc across ranks.  ``packed`` holds uint64 words ``key(d) << 32 | idx`` stored in an
+    int64 tensor; flipping the sign bit turns unsigned order into signed order so ReduceOp.MIN (NCCL has
+    no MINLOC) picks the smallest distance and, on equal distances, the smallest index."""
+    flipped = packed ^ _SIGN
+    dist.all_reduce(flipped, op=dist.ReduceOp.MIN, group=group)
+    return flipped ^ _SIGN
+
+
+def codebook_sharded_search(q, flat: torch.Tensor, group=None) -> torch.Tensor:
+    """Nearest code when the codebook is split over ranks: every rank holds all rows ``flat`` [N, D] and
+    scans only its slice of the (single-level) codebook; the winners are combined with one
+    all-reduce(MIN) of N packed words.  Returns int64 indices [N], identical on every rank."""
+    from . import ops
+    if q.num_quantizers != 1:
+        raise NotImplementedError("codebook-sharded search is defined for single-level codebooks")
+    world = dist.get_world_size(group) if dist_ready() else 1
+    rank = dist.get_rank(group) if dist_ready() else 0
+    s, e = shard_codes(q.K, world, rank)
+    cache = q._codebook_cache()
+    packed = torch.full((flat.shape[0],), -1, dtype=torch.int64, device=flat.device)   # all ones = +inf key
+    if e > s:
+        ops.search_packed(flat.contiguous(), q.embedding[s:e], cache.ee_half[0, s:e], s, packed)
+    if world > 1:
+        packed = allreduce_minloc(packed, group)
+    out = torch.empty_like(packed)
+    ops.minloc_unpack(packed, out)
+    return out

@@ -1,0 +1,116 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, the Python class mirrors the reference's surface, and nothing falls back to a CPU path."""
+import inspect
+import os
+import re
+import subprocess
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+import pytorch_vae_b200 as vq  # noqa: E402
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "vq_b200.h")).read()
+    return sorted(set(re.findall(r"VQB200_API[^;]*?\b(vqb200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 16
+    assert sorted(vq._cabi.SIGNATURES) == syms            # binding and header agree one to one
+    out = subprocess.run(["nm", "-D", "--defined-only", vq._cabi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (vqb200_\w+)", out))
+    assert exported == set(syms)
+    # no-compute calls work without a GPU
+    assert vq._cabi.lib.vqb200_abi_version() == vq._cabi.ABI_VERSION
+    assert vq._cabi.lib.vqb200_status_string(-2).startswith(b"unsupported shape")
+    assert vq._cabi.lib.vqb200_search_workspace_bytes(1 << 20, 512, 64, 0) > 0
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", vq._cabi.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+REF_CTOR = ["num_embeddings", "embedding_dim", "beta", "decay", "eps", "reinit_dead_codes", "reinit_prob",
+            "dead_usage_threshold", "print_init", "diag_qe_cap", "diag_qe_bins", "num_quantizers"]
+REF_BUFFERS = [("embedding", (96, 16)), ("ema_cluster_size", (96,)), ("ema_embedding", (96, 16)),
+               ("_ep_usage", (96,)), ("_ep_top1_sum", (1,)), ("_ep_top2_sum", (1,)), ("_ep_cnt", (1,)),
+               ("_ep_qe_sum", (1,)), ("_ep_qe_hist", (64,))]
+
+
+def test_class_surface_matches_reference():
+    params = list(inspect.signature(vq.VectorQuantizerEMA.__init__).parameters)[1:]
+    assert params[:len(REF_CTOR)] == REF_CTOR             # same names, same order (models/vq_vae.py:20-34)
+    fwd = list(inspect.signature(vq.VectorQuantizerEMA.forward).parameters)[1:]
+    assert fwd == ["z_e", "do_ema_update", "allow_reinit", "mask"]
+    q = vq.VectorQuantizerEMA(32, 16, num_quantizers=3, print_init=False)
+    sd = q.state_dict()
+    assert [(k, tuple(v.shape)) for k, v in sd.items()] == REF_BUFFERS
+    assert all(v.dtype == torch.float32 for v in sd.values())
+    assert (q.K, q.K_per, q.D, q.num_quantizers) == (96, 32, 16, 3)
+    assert len(list(q.parameters())) == 0                 # buffers only: nothing for DDP to all-reduce
+    assert abs(float(q.embedding.std()) - 0.25) < 0.03    # randn / sqrt(D)
+    for name in ("_ema_update", "_maybe_reinit_dead_codes", "reset_epoch_stats", "get_epoch_stats",
+                 "get_embedding_snapshot"):
+        assert callable(getattr(q, name))
+    assert vq.VectorQuantizer is vq.VectorQuantizerEMA
+    es = q.get_epoch_stats()
+    assert set(es) == {"usage_hist", "margin_mean", "qe_mean", "qe_p90", "n_positions", "perplexity", "dead_ratio"}
+    if os.path.isdir("/root/reference"):                  # build container only: compare with the live class
+        sys.path.insert(0, "/root/reference")
+        from models.vq_vae import VectorQuantizerEMA as Ref
+        r = Ref(32, 16, num_quantizers=3, print_init=False)
+        assert [(k, tuple(v.shape)) for k, v in r.state_dict().items()] == REF_BUFFERS
+        assert list(inspect.signature(Ref.__init__).parameters)[1:] == REF_CTOR
+        q.load_state_dict(r.state_dict(), strict=True)
+        assert torch.equal(q.embedding, r.embedding)
+
+
+def test_no_cpu_fallback():
+    q = vq.VectorQuantizerEMA(32, 16, print_init=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        q(torch.randn(2, 4, 16))
+    with pytest.raises(ValueError):
+        q(torch.randn(8, 16))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        vq.ops.gather(torch.zeros(4, 16), torch.zeros(8, 16), torch.zeros(4, dtype=torch.int64))
+    with pytest.raises(ValueError):
+        vq.VectorQuantizerEMA(32, 18, print_init=False)
+    # the product never touches the oracle
+    pkg = os.path.join(ROOT, "pytorch-vae_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dp, fn)).read().lower(), fn
+
+
+def test_install_rebinds_reference_global():
+    fake = types.ModuleType("fake_models_vq_vae")
+    fake.VectorQuantizerEMA = object
+    sys.modules[fake.__name__] = fake
+    vq.install(fake.__name__)
+    assert fake.VectorQuantizerEMA is vq.VectorQuantizerEMA
+    vq.uninstall(fake.__name__)
+    assert fake.VectorQuantizerEMA is object
+
+
+def test_shard_partitions():
+    from pytorch_vae_b200 import sharding as S
+    for n, w in [(0, 4), (7, 8), (1 << 22, 8), (1000003, 3)]:
+        spans = [S.shard_rows(n, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+    for k, w in [(8192, 8), (1000, 3), (16, 8)]:
+        spans = [S.shard_codes(k, w, r) for r in range(w)]
+        assert spans[0][0] == 0 and max(e for _, e in spans) == k
+        assert all(a[1] == b[0] or b[0] == b[1] == k for a, b in zip(spans, spans[1:]))

@@ -167,3 +167,19 @@ def test_large_cases(golden, name):
         assert sha(zq) == str(g["sha_zq"]) and sha(st) == str(g["sha_zq_st"])
         np.testing.assert_allclose(stats, g["stats"], rtol=1e-6)
     np.testing.assert_allclose(O.commitment_mse(zq, z), float(g["commit"]), rtol=1e-5)
+
+
+def test_torch_port_matches_golden(golden):
+    """The timed CPU baseline (oracle/torch_port.py) is pinned to the same golden vectors."""
+    import torch
+
+    from oracle import torch_port
+    for name in ("c2_like", "stage2_rvq"):
+        g = gsub(golden, name)
+        K_per, D, L, B, M = (int(g[k]) for k in ("K_per", "D", "L", "B", "M"))
+        E, z = large_case_inputs(int(g["seed"]), K_per, D, L, B, M)
+        zq, idx, usage = torch_port.forward_eval(torch.from_numpy(z).reshape(-1, D), torch.from_numpy(E), K_per, L,
+                                                 chunk=1000)
+        assert np.array_equal(idx.numpy(), g["idx"].astype(np.int64).reshape(-1))
+        assert sha(zq.numpy()) == str(g["sha_zq"])
+        assert float(usage.sum()) == L * B * M
