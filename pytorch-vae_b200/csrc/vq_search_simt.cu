@@ -51,6 +51,7 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+    __syncthreads();   // the previous tile's epilogue may still be reading ees
     if (tid < BN) ees[tid] = (n0 + tid < K) ? ee_half[n0 + tid] : __int_as_float(0x7f800000);
 
     for (int k0 = 0; k0 < D; k0 += BK) {
