@@ -27,8 +27,8 @@ const char* vqb200_status_string(int status) {
 }
 
 int vqb200_search_path(int64_t N, int K, int D, int mode) {
-  (void)N; (void)K; (void)D; (void)mode;
-  return 0;
+  (void)mode;
+  return tc_supported(N, K, D) ? 1 : 0;
 }
 
 int vqb200_codebook_prepare(const float* E, int K_total, int D, int K_per, uint16_t* E_bf16, float* ee_half,
@@ -43,8 +43,8 @@ int vqb200_codebook_prepare(const float* E, int K_total, int D, int K_per, uint1
 }
 
 size_t vqb200_search_workspace_bytes(int64_t N, int K, int D, int mode) {
-  (void)N; (void)K; (void)D; (void)mode;
-  return 256;
+  (void)mode;
+  return tc_supported(N, K, D) ? tc_workspace_bytes(N, K, D) : 256;
 }
 
 int vqb200_search(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
@@ -59,6 +59,12 @@ int vqb200_search(const float* z, int64_t N, int D, const float* E, const uint16
   VQ_REQUIRE(workspace_bytes >= vqb200_search_workspace_bytes(N, K, D, mode) && (workspace || N == 0),
              VQB200_EWORKSPACE);
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  if (N == 0) return VQB200_OK;
+  if (tc_supported(N, K, D)) {
+    VQ_REQUIRE(aligned16(E_bf16) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, VQB200_EALIGN);
+    return launch_search_tc(z, N, D, E, E_bf16, ee_half, ee_half_bf16, level_meta, K, mode, idx_offset, idx_out,
+                            workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+  }
   return launch_search_simt(z, nullptr, N, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0, idx_offset, idx_out,
                             nullptr, static_cast<cudaStream_t>(stream));
 }

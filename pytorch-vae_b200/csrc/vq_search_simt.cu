@@ -20,8 +20,8 @@ constexpr int PAD = 4;
 
 template <bool ROUND_BF16>
 __global__ void __launch_bounds__(SIMT_THREADS, 2)
-search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_list, int64_t n_rows,
-                   int D, const float* __restrict__ E, const float* __restrict__ ee_half, int K,
+search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_list,
+                   const int* __restrict__ n_rows_dev, int64_t n_rows, int D, const float* __restrict__ E, const float* __restrict__ ee_half, int K,
                    int64_t idx_offset, int64_t* __restrict__ idx_out, uint64_t* __restrict__ packed_out) {
   __shared__ float zs[BK][BM + PAD];
   __shared__ float es[BK][BN + PAD];
@@ -30,6 +30,8 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * BM;
+  if (n_rows_dev) n_rows = *n_rows_dev;      // row-list length produced on the device (no host sync)
+  if (row0 >= n_rows) return;
 
   // rows this thread stages into shared memory (2 float4 per tile step)
   const int ld_r = tid >> 2, ld_c = (tid & 3) * 4;
@@ -116,20 +118,33 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
   }
 }
 
-int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, int D, const float* E,
-                       const float* ee_half, int K, int round_bf16, int64_t idx_offset, int64_t* idx_out,
-                       uint64_t* packed_out, cudaStream_t s) {
+static int launch_impl(const float* z, const int32_t* row_list, const int* n_rows_dev, int64_t n_rows, int D,
+                       const float* E, const float* ee_half, int K, int round_bf16, int64_t idx_offset,
+                       int64_t* idx_out, uint64_t* packed_out, cudaStream_t s) {
   if (n_rows == 0) return VQB200_OK;
   const int64_t blocks = (n_rows + BM - 1) / BM;
   if (blocks > 0x7fffffff) return VQB200_ESHAPE;
   dim3 grid(static_cast<unsigned>(blocks));
   if (round_bf16)
-    search_simt_kernel<true><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows, D, E, ee_half, K, idx_offset,
+    search_simt_kernel<true><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows_dev, n_rows, D, E, ee_half, K, idx_offset,
                                                           idx_out, packed_out);
   else
-    search_simt_kernel<false><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows, D, E, ee_half, K, idx_offset,
+    search_simt_kernel<false><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows_dev, n_rows, D, E, ee_half, K, idx_offset,
                                                            idx_out, packed_out);
   return status_of(cudaGetLastError());
+}
+
+int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, int D, const float* E,
+                       const float* ee_half, int K, int round_bf16, int64_t idx_offset, int64_t* idx_out,
+                       uint64_t* packed_out, cudaStream_t s) {
+  return launch_impl(z, row_list, nullptr, n_rows, D, E, ee_half, K, round_bf16, idx_offset, idx_out, packed_out, s);
+}
+
+// Row list whose length lives on the device: the grid covers max_rows, surplus CTAs exit at once.
+int launch_search_simt_list(const float* z, const int32_t* row_list, const int* n_rows_dev, int64_t max_rows, int D,
+                            const float* E, const float* ee_half, int K, int round_bf16, int64_t idx_offset,
+                            int64_t* idx_out, cudaStream_t s) {
+  return launch_impl(z, row_list, n_rows_dev, max_rows, D, E, ee_half, K, round_bf16, idx_offset, idx_out, nullptr, s);
 }
 
 }  // namespace vqb

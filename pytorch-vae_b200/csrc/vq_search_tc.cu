@@ -1,0 +1,600 @@
+// Tensor-core nearest-code search for sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands
+// staged by TMA, and a fused per-row candidate/argmax epilogue read straight out of TMEM, so the
+// N x K score matrix never reaches shared memory, L2 or HBM.
+//
+// Exactness (BASELINE.json north_star: reference-exact codes from fp32 inputs).  A single bf16 pass
+// cannot decide near-ties, so the epilogue does not pick a winner; it keeps, per row, every code
+// whose approximate score  s~ = z~.e~ - |e|^2/2  lies within a RIGOROUS error bound of the running
+// maximum:
+//     |z~.e~ - z.e| <= (2u + u^2) |z||e|,  u = 2^-9 (bf16 round-to-nearest)  [+ fp32 accumulation slack]
+// so the true argmax a satisfies  s~_a >= max s~ - margin,  margin = 2 (2u+u^2) |z| max_k|e_k| * 1.02.
+// A tiny re-rank kernel then evaluates the few survivors exactly (fp64 accumulation of the fp32
+// inputs) and takes the lowest index among exact ties.  Rows whose list overflows, rows with
+// non-finite values and non-finite codebooks are handed to the exact SIMT kernel.  In bf16-input
+// mode the products are exact and only the accumulation order differs; the same machinery runs
+// with a much smaller margin and re-ranks on the bf16-rounded values.
+//
+// Kernel anatomy (one CTA per SM, persistent over (row tile, code split) work items):
+//   warp 0   : TMA producer  - z tile [BM x D] once per item, codebook blocks [128 x 64] in a ring
+//   warp 1   : MMA issuer    - one thread issues tcgen05.mma M=128 N=128 K=16, accumulators in TMEM
+//                              (2 buffers x BM/128 halves x 128 columns = all 512 columns at BM=256)
+//   warps 2+ : epilogue      - tcgen05.ld 32 columns at a time, subtract |e|^2/2, running max and
+//                              candidate append; overlaps the MMAs of the next code tile
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace vqb {
+
+constexpr int TC_BN = 128;          // codes per accumulator tile (UMMA N)
+constexpr int TC_KB = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int TC_CAND = 32;         // candidate slots per (row, code split)
+constexpr int TC_STAGE_BYTES = TC_BN * TC_KB * 2;   // 16 KB
+constexpr int TC_SMEM_LIMIT = 232448;               // 227 KB
+constexpr uint32_t TC_SPIN_LIMIT = 1u << 22;
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > TC_SPIN_LIMIT) __trap();   // a protocol bug must fault, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle, 8-row atoms 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(1) << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
+         (static_cast<uint64_t>(2) << 61);
+}
+// kind::f16, A = B = bf16, D = fp32, both K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
+
+#define TC_LD32(taddr, v)                                                                                          \
+  asm volatile(                                                                                                    \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"    \
+      "%28,%29,%30,%31}, [%32];"                                                                                   \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),           \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),     \
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),   \
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])    \
+      : "r"(taddr))
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------ z pre-pass
+// z fp32 -> bf16 (RN) plus the per-row admission margin.  One warp per row.
+__global__ void __launch_bounds__(256)
+zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const float* __restrict__ level_meta,
+             __nv_bfloat16* __restrict__ zb, float* __restrict__ margin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int D4 = D >> 2;
+  const float emax = mode == VQB200_MODE_BF16_INPUT ? level_meta[2] : level_meta[0];
+  const bool code_bad = level_meta[1] != 0.f;
+  // fp32 mode: 2 (2u + u^2) with u = 2^-9, +2% for the fp32 accumulation inside the tensor core
+  // bf16 mode: inputs are exact, only accumulation order differs: 2 (D + 32) 2^-23
+  const float coef = mode == VQB200_MODE_BF16_INPUT ? 2.f * static_cast<float>(D + 32) * 1.1920929e-7f
+                                                    : 2.f * 0.00391007f * 1.02f;
+  for (int64_t row = warp; row < n; row += nwarps) {
+    float ss = 0.f;
+    for (int c = lane; c < D4; c += 32) {
+      const float4 v = ld_stream(reinterpret_cast<const float4*>(z) + row * D4 + c);
+      const __nv_bfloat16 b0 = __float2bfloat16_rn(v.x), b1 = __float2bfloat16_rn(v.y),
+                          b2 = __float2bfloat16_rn(v.z), b3 = __float2bfloat16_rn(v.w);
+      uint2 pk;
+      pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(b0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
+      pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(b2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b3)) << 16);
+      reinterpret_cast<uint2*>(zb)[row * D4 + c] = pk;
+      if (mode == VQB200_MODE_BF16_INPUT) {
+        const float f0 = __bfloat162float(b0), f1 = __bfloat162float(b1), f2 = __bfloat162float(b2),
+                    f3 = __bfloat162float(b3);
+        ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
+      } else {
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      float m = coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f;
+      if (code_bad || !(ss < __int_as_float(0x7f800000))) m = __int_as_float(0x7fc00000);   // NaN: exact path
+      margin[row] = m;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ the tensor kernel
+struct TcParams {
+  int64_t n_rows;        // rows in this chunk
+  int D, K;
+  int row_tiles, ksplit, tiles_per_split, code_tiles;
+  int stages;
+  const float* ee_half;  // [K] (plane chosen by mode)
+  const float* margin;   // [n_rows]
+  uint2* cand;           // [n_rows][ksplit][TC_CAND]
+  int* cnt;              // [n_rows][ksplit]
+  float* best;           // [n_rows][ksplit]
+};
+
+template <int BM>
+__global__ void __launch_bounds__(64 + BM, 1)
+search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
+                 const TcParams p) {
+  constexpr int NHALF = BM / 128;
+  constexpr int NEPI = BM / 32;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int KBLK = p.D / TC_KB;
+  const uint32_t z_smem = base;                                    // KBLK slabs of [BM rows x 128 B]
+  const uint32_t e_smem = z_smem + static_cast<uint32_t>(BM) * p.D * 2;   // ring of [128 codes x 128 B]
+  const uint32_t ee_smem = e_smem + static_cast<uint32_t>(p.stages) * TC_STAGE_BYTES;   // [NEPI][2][128] fp32
+  const uint32_t bar0 = ee_smem + NEPI * 2 * TC_BN * 4;
+  // barrier map (8 bytes each)
+  const uint32_t bar_full = bar0;                         // [stages]
+  const uint32_t bar_empty = bar0 + 8 * 8;                // [stages]
+  const uint32_t bar_tfull = bar0 + 16 * 8;               // [2]
+  const uint32_t bar_tempty = bar0 + 18 * 8;              // [2]
+  const uint32_t bar_zfull = bar0 + 20 * 8;
+  const uint32_t bar_zempty = bar0 + 21 * 8;
+  const uint32_t tmem_slot = bar0 + 22 * 8;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to the aligned base
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, NEPI); }
+    mbar_init(bar_zfull, 1);
+    mbar_init(bar_zempty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int n_items = p.row_tiles * p.ksplit;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
+        const int t0 = ks * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
+        mbar_wait(bar_zempty, (it & 1) ^ 1);
+        mbar_expect_tx(bar_zfull, static_cast<uint32_t>(BM) * p.D * 2);
+        for (int kb = 0; kb < KBLK; ++kb)
+          tma_load_2d(z_smem + kb * (BM * 128), &tmap_z, bar_zfull, kb * TC_KB, rt * BM);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < KBLK; ++kb) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+            tma_load_2d(e_smem + stage * TC_STAGE_BYTES, &tmap_e, bar_full + 8 * stage, kb * TC_KB, t * TC_BN);
+            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, it = 0, tg = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
+        const int t0 = ks * p.tiles_per_split;
+        const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
+        mbar_wait(bar_zfull, it & 1);
+        for (int t = t0; t < t1; ++t, ++tg) {
+          const uint32_t b = tg & 1;
+          mbar_wait(bar_tempty + 8 * b, ((tg >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < KBLK; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+#pragma unroll
+            for (int h = 0; h < NHALF; ++h) {
+              const uint32_t d_tmem = tmem_base + b * (NHALF * TC_BN) + h * TC_BN;
+#pragma unroll
+              for (int k = 0; k < TC_KB / 16; ++k) {
+                const uint64_t ad = umma_desc(z_smem + kb * (BM * 128) + h * (128 * 128) + k * 32);
+                const uint64_t bd = umma_desc(e_smem + stage * TC_STAGE_BYTES + k * 32);
+                tc_mma_bf16(d_tmem, ad, bd, kIdesc, (kb | k) ? 1u : 0u);
+              }
+            }
+            tc_commit(bar_empty + 8 * stage);          // frees the smem stage when these MMAs retire
+            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(bar_tfull + 8 * b);                // accumulator tile complete
+        }
+        tc_commit(bar_zempty);                         // z tile may be overwritten
+      }
+    }
+  } else {
+    // ============================== epilogue ==============================
+    const int we = warp - 2;                           // 0 .. NEPI-1
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
+    const int half = we >> 2;
+    float* ee_mine = reinterpret_cast<float*>(gen + (ee_smem - base)) + we * 2 * TC_BN;
+    uint32_t tg = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
+      const int t0 = ks * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
+      const int64_t row = static_cast<int64_t>(rt) * BM + half * 128 + quarter * 32 + lane;
+      const bool row_ok = row < p.n_rows;
+      const float margin = row_ok ? p.margin[row] : __int_as_float(0x7fc00000);
+      uint2* cand_row = p.cand + (row_ok ? (row * p.ksplit + ks) * TC_CAND : 0);
+      float best = __int_as_float(0xff800000);
+      int cnt = 0;
+
+      float4 ee_next;
+      {
+        const int c = t0 * TC_BN + lane * 4;
+        ee_next.x = c + 0 < p.K ? p.ee_half[c + 0] : __int_as_float(0x7f800000);
+        ee_next.y = c + 1 < p.K ? p.ee_half[c + 1] : __int_as_float(0x7f800000);
+        ee_next.z = c + 2 < p.K ? p.ee_half[c + 2] : __int_as_float(0x7f800000);
+        ee_next.w = c + 3 < p.K ? p.ee_half[c + 3] : __int_as_float(0x7f800000);
+      }
+      for (int t = t0; t < t1; ++t, ++tg) {
+        const uint32_t b = tg & 1;
+        float* ee = ee_mine + b * TC_BN;
+        __syncwarp();
+        reinterpret_cast<float4*>(ee)[lane] = ee_next;
+        __syncwarp();
+        if (t + 1 < t1) {
+          const int c = (t + 1) * TC_BN + lane * 4;
+          ee_next.x = c + 0 < p.K ? p.ee_half[c + 0] : __int_as_float(0x7f800000);
+          ee_next.y = c + 1 < p.K ? p.ee_half[c + 1] : __int_as_float(0x7f800000);
+          ee_next.z = c + 2 < p.K ? p.ee_half[c + 2] : __int_as_float(0x7f800000);
+          ee_next.w = c + 3 < p.K ? p.ee_half[c + 3] : __int_as_float(0x7f800000);
+        }
+        mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * (NHALF * TC_BN) +
+                               half * TC_BN;
+#pragma unroll 1
+        for (int c = 0; c < TC_BN / 32; ++c) {
+          uint32_t v[32];
+          TC_LD32(taddr + c * 32, v);
+          tc_wait_ld();
+          float s[32];
+          float m = __int_as_float(0xff800000);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 e4 = *reinterpret_cast<const float4*>(ee + c * 32 + j);
+            s[j + 0] = __uint_as_float(v[j + 0]) - e4.x;
+            s[j + 1] = __uint_as_float(v[j + 1]) - e4.y;
+            s[j + 2] = __uint_as_float(v[j + 2]) - e4.z;
+            s[j + 3] = __uint_as_float(v[j + 3]) - e4.w;
+            m = fmaxf(m, fmaxf(fmaxf(s[j], s[j + 1]), fmaxf(s[j + 2], s[j + 3])));
+          }
+          if (m >= best - margin) {                    // rare after the first few tiles
+            best = fmaxf(best, m);
+            const float thr = best - margin;
+            const uint32_t code0 = static_cast<uint32_t>(t * TC_BN + c * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (s[j] >= thr) {
+                if (cnt < TC_CAND) cand_row[cnt] = make_uint2(code0 + j, __float_as_uint(s[j]));
+                ++cnt;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+      }
+      if (row_ok) {
+        p.cnt[row * p.ksplit + ks] = cnt;
+        p.best[row * p.ksplit + ks] = best;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ exact re-rank
+// One warp per row: prune the candidate lists against the final maximum, score the survivors
+// exactly (fp64 accumulation of the fp32 -- or bf16-rounded -- inputs), lowest index wins ties.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, const float* __restrict__ E,
+              const __nv_bfloat16* __restrict__ Eb, int64_t n, int D, int ksplit, const float* __restrict__ margin,
+              const uint2* __restrict__ cand, const int* __restrict__ cnt, const float* __restrict__ best,
+              int64_t idx_offset, int64_t* __restrict__ idx_out, int* __restrict__ fb_rows, int* __restrict__ fb_count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = warp; row < n; row += nwarps) {
+    float bmax = __int_as_float(0xff800000);
+    bool bad = false;
+    for (int ks = 0; ks < ksplit; ++ks) {
+      const int c = cnt[row * ksplit + ks];
+      bad |= (c <= 0 || c > TC_CAND);
+      bmax = fmaxf(bmax, best[row * ksplit + ks]);
+    }
+    const float mg = margin[row];
+    if (bad || !(mg == mg)) {                          // overflow / nothing admitted / non-finite: exact SIMT path
+      if (lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(row);
+      continue;
+    }
+    const float thr = bmax - mg;
+    double top = -1e300;
+    uint32_t top_idx = 0xffffffffu;
+    int n_surv = 0;
+    uint32_t only = 0;
+    // pass 1: count survivors (lists are in ascending code order, splits too)
+    for (int ks = 0; ks < ksplit; ++ks) {
+      const int c = cnt[row * ksplit + ks];
+      const uint2 ent = lane < c ? cand[(row * ksplit + ks) * TC_CAND + lane] : make_uint2(0, 0xff800000u);
+      const unsigned surv = __ballot_sync(0xffffffffu, lane < c && __uint_as_float(ent.y) >= thr);
+      if (surv) {
+        if (n_surv == 0) only = __shfl_sync(0xffffffffu, ent.x, __ffs(surv) - 1);
+        n_surv += __popc(surv);
+      }
+    }
+    if (n_surv == 1) {                                 // certified by the error bound: no arithmetic needed
+      if (lane == 0) idx_out[row] = idx_offset + only;
+      continue;
+    }
+    for (int ks = 0; ks < ksplit; ++ks) {
+      const int c = cnt[row * ksplit + ks];
+      const uint2 ent = lane < c ? cand[(row * ksplit + ks) * TC_CAND + lane] : make_uint2(0, 0xff800000u);
+      unsigned surv = __ballot_sync(0xffffffffu, lane < c && __uint_as_float(ent.y) >= thr);
+      while (surv) {
+        const int src = __ffs(surv) - 1;
+        surv &= surv - 1;
+        const uint32_t code = __shfl_sync(0xffffffffu, ent.x, src);
+        double dot = 0.0, ee = 0.0;
+        for (int d = lane; d < D; d += 32) {
+          double zv, ev;
+          if (BF16) { zv = __bfloat162float(zb[row * D + d]); ev = __bfloat162float(Eb[static_cast<int64_t>(code) * D + d]); }
+          else { zv = z[row * D + d]; ev = E[static_cast<int64_t>(code) * D + d]; }
+          dot = fma(zv, ev, dot);
+          ee = fma(ev, ev, ee);
+        }
+        dot = warp_sum(dot);
+        ee = warp_sum(ee);
+        const double sc = dot - 0.5 * ee;
+        if (sc > top) { top = sc; top_idx = code; }    // ascending code order + strict '>' = lowest index on ties
+      }
+    }
+    if (lane == 0) idx_out[row] = idx_offset + top_idx;
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+static bool make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 2};
+  cuuint32_t box[2] = {TC_KB, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct TcPlan {
+  int BM, stages, smem_bytes;
+  int64_t chunk_rows;
+  int ksplit_max;
+};
+
+static bool tc_plan(int64_t N, int K, int D, TcPlan* pl) {
+  if (D % TC_KB != 0 || D < 64 || D > 512 || K < TC_BN || N < 64) return false;
+  pl->BM = (D <= 256) ? 256 : 128;
+  const int nepi = pl->BM / 32;
+  const int fixed = 1024 + pl->BM * D * 2 + nepi * 2 * TC_BN * 4 + 256;
+  int st = (TC_SMEM_LIMIT - fixed) / TC_STAGE_BYTES;
+  if (st > 8) st = 8;
+  if (st < 2) return false;
+  pl->stages = st;
+  pl->smem_bytes = fixed + st * TC_STAGE_BYTES;
+  // rows per pass: keep the bf16 copy + the fp32 rows of one chunk around the L2 size for small D,
+  // bound the workspace for large D
+  int64_t chunk = (static_cast<int64_t>(96) << 20) / (static_cast<int64_t>(D) * 6);
+  chunk = (chunk / 4096) * 4096;
+  if (chunk < 65536) chunk = 65536;
+  if (chunk > (1 << 20)) chunk = 1 << 20;
+  pl->chunk_rows = chunk;
+  pl->ksplit_max = 8;
+  return true;
+}
+
+// Split the code range over CTAs when there are too few row tiles to fill the SMs; never leaves a
+// split empty.  Returns the number of splits and sets *tiles_per_split.
+static int pick_ksplit(int64_t rows, int BM, int code_tiles, int ksplit_max, int* tiles_per_split) {
+  const int64_t row_tiles = (rows + BM - 1) / BM;
+  int want = 1;
+  while (want * 2 <= ksplit_max && want * 2 <= code_tiles && row_tiles * want * 2 <= kNumSMs) want *= 2;
+  const int tps = (code_tiles + want - 1) / want;
+  *tiles_per_split = tps;
+  return (code_tiles + tps - 1) / tps;
+}
+
+bool tc_supported(int64_t N, int K, int D) {
+  const char* f = std::getenv("VQB200_FORCE_SIMT");
+  if (f && f[0] == '1') return false;
+  TcPlan pl;
+  return tc_plan(N, K, D, &pl);
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+// (row, split) slots: code splits are only used while row_tiles * ksplit <= #SMs
+static size_t tc_slots(int64_t rows, int BM) {
+  const size_t few = static_cast<size_t>(kNumSMs) * BM;
+  return static_cast<size_t>(rows) > few ? static_cast<size_t>(rows) : few;
+}
+
+size_t tc_workspace_bytes(int64_t N, int K, int D) {
+  TcPlan pl;
+  if (!tc_plan(N, K, D, &pl)) return 0;
+  const int64_t rows = N < pl.chunk_rows ? N : pl.chunk_rows;
+  const size_t slots = tc_slots(rows, pl.BM);
+  size_t b = 256;
+  b += align_up(static_cast<size_t>(rows) * D * 2, 256);            // zb
+  b += align_up(static_cast<size_t>(rows) * 4, 256);                // margin
+  b += align_up(slots * 4, 256) * 2;                                // cnt, best
+  b += align_up(slots * TC_CAND * 8, 256);                          // cand
+  b += align_up(static_cast<size_t>(rows) * 4, 256);                // fb_rows
+  return b;
+}
+
+int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
+                     const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
+                     int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  TcPlan pl;
+  if (!tc_plan(N, K, D, &pl)) return VQB200_ESHAPE;
+  if (workspace_bytes < tc_workspace_bytes(N, K, D)) return VQB200_EWORKSPACE;
+  const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  const int64_t cap = N < pl.chunk_rows ? N : pl.chunk_rows;
+  const int ksm = pl.ksplit_max;
+  const size_t slots = tc_slots(cap, pl.BM);
+
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  int* fb_count = reinterpret_cast<int*>(w); w += 256;
+  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(w); w += align_up(static_cast<size_t>(cap) * D * 2, 256);
+  float* margin = reinterpret_cast<float*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
+  int* cnt = reinterpret_cast<int*>(w); w += align_up(slots * 4, 256);
+  float* best = reinterpret_cast<float*>(w); w += align_up(slots * 4, 256);
+  uint2* cand = reinterpret_cast<uint2*>(w); w += align_up(slots * TC_CAND * 8, 256);
+  int* fb_rows = reinterpret_cast<int*>(w);
+
+  CUtensorMap map_e;
+  if (!make_map(&map_e, E_bf16, K, D, TC_BN)) return VQB200_EDRIVER;
+  const int code_tiles = (K + TC_BN - 1) / TC_BN;
+
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[pl.BM == 256]) {
+    cudaError_t e = pl.BM == 256
+        ? cudaFuncSetAttribute(search_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT)
+        : cudaFuncSetAttribute(search_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    if (e != cudaSuccess) return status_of(e);
+    attr_done[pl.BM == 256] = true;
+  }
+
+  for (int64_t r0 = 0; r0 < N; r0 += pl.chunk_rows) {
+    const int64_t rows = (N - r0) < pl.chunk_rows ? (N - r0) : pl.chunk_rows;
+    const float* zc = z + r0 * D;
+    cudaError_t e = cudaMemsetAsync(fb_count, 0, sizeof(int), s);
+    if (e != cudaSuccess) return status_of(e);
+
+    int64_t warps = rows;
+    int64_t blocks = (warps + 7) / 8;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    zprep_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, rows, D, mode, level_meta, zb, margin);
+
+    CUtensorMap map_z;
+    if (!make_map(&map_z, zb, rows, D, pl.BM)) return VQB200_EDRIVER;
+    TcParams p;
+    p.n_rows = rows; p.D = D; p.K = K;
+    p.row_tiles = static_cast<int>((rows + pl.BM - 1) / pl.BM);
+    p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, ksm, &p.tiles_per_split);
+    p.code_tiles = code_tiles;
+    p.stages = pl.stages;
+    p.ee_half = bf ? ee_half_bf16 : ee_half;
+    p.margin = margin; p.cand = cand; p.cnt = cnt; p.best = best;
+    const int items = p.row_tiles * p.ksplit;
+    const int grid = items < kNumSMs ? items : kNumSMs;
+    if (pl.BM == 256)
+      search_tc_kernel<256><<<grid, 64 + 256, pl.smem_bytes, s>>>(map_z, map_e, p);
+    else
+      search_tc_kernel<128><<<grid, 64 + 128, pl.smem_bytes, s>>>(map_z, map_e, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return status_of(e);
+
+    blocks = (rows + 7) / 8;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
+    if (bf)
+      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit, margin, cand,
+                                                                       cnt, best, idx_offset, idx_out + r0, fb_rows, fb_count);
+    else
+      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit, margin, cand,
+                                                                        cnt, best, idx_offset, idx_out + r0, fb_rows, fb_count);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return status_of(e);
+    // rows handed back (overflow / non-finite): exact SIMT scan over the device-side row list
+    int st = launch_search_simt_list(zc, fb_rows, fb_count, rows, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0,
+                                     idx_offset, idx_out + r0, s);
+    if (st != VQB200_OK) return st;
+  }
+  return VQB200_OK;
+}
+
+}  // namespace vqb

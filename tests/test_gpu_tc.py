@@ -1,0 +1,124 @@
+"""The tcgen05 search path against the exact SIMT path and the fp64 oracle: same inputs, both
+kernels (VQB200_FORCE_SIMT=1 switches the dispatcher), including the rows the tensor path must hand
+back to the exact kernel (non-finite values, collapsed codebooks that overflow the candidate list)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from synth import large_case_inputs
+
+from oracle import vq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vq():
+    import pytorch_vae_b200 as m
+    return m
+
+
+def run_search(vq, z, E, K_per, mode="fp32", force_simt=False):
+    dev = torch.device("cuda:0")
+    D = z.shape[-1]
+    L = E.shape[0] // K_per
+    q = vq.VectorQuantizerEMA(K_per, D, num_quantizers=L, print_init=False, search_mode=mode).to(dev).eval()
+    q.embedding.copy_(torch.from_numpy(E).to(dev))
+    old = os.environ.get("VQB200_FORCE_SIMT")
+    os.environ["VQB200_FORCE_SIMT"] = "1" if force_simt else "0"
+    try:
+        path = vq._cabi.lib.vqb200_search_path(z.shape[0] * z.shape[1], K_per, D, 0)
+        out = q(torch.from_numpy(z).to(dev), do_ema_update=False)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("VQB200_FORCE_SIMT", None)
+        else:
+            os.environ["VQB200_FORCE_SIMT"] = old
+    return path, out[2].cpu().numpy().reshape(-1), q
+
+
+SHAPES = [
+    # K,   D,   N     (N as B*64 rows)
+    (128, 64, 64),            # one code tile, one partial row tile
+    (512, 64, 8192),          # C2 shape
+    (520, 64, 300 * 64 // 64 * 64),   # K tail (not a multiple of 128)
+    (2048, 128, 4096),
+    (8192, 256, 2048),        # C3 shape, code splits in play (few row tiles)
+    (8192, 256, 40000 // 64 * 64),    # C3 shape, persistent loop with >1 item per CTA
+    (1024, 512, 4096),        # stage-2 level shape (BM=128 variant)
+    (384, 192, 1024),         # D = 3 swizzle blocks
+]
+
+
+@pytest.mark.parametrize("K,D,N", SHAPES)
+def test_tc_matches_exact(vq, K, D, N):
+    E, z = large_case_inputs(700 + K + D, K, D, 1, N // 64, 64)
+    path_tc, idx_tc, _ = run_search(vq, z, E, K)
+    path_s, idx_s, _ = run_search(vq, z, E, K, force_simt=True)
+    assert path_tc == 1 and path_s == 0
+    ref = O.nearest_code64(z.reshape(-1, D), E)
+    flat = z.reshape(-1, D)
+    mm, outside = O.near_tie_rows(flat, E, idx_tc, ref)
+    assert outside.size == 0, f"tensor path: {outside.size} rows outside the allowance (of {mm.size} mismatches)"
+    assert mm.size <= 2
+    mm2, outside2 = O.near_tie_rows(flat, E, idx_s, ref)
+    assert outside2.size == 0 and mm2.size <= 2
+
+
+@pytest.mark.parametrize("K,D,N", [(512, 64, 8192), (4096, 256, 2048)])
+def test_tc_bf16_mode(vq, K, D, N):
+    E, z = large_case_inputs(800 + K, K, D, 1, N // 64, 64)
+    path, idx, _ = run_search(vq, z, E, K, mode="bf16_input")
+    assert path == 1
+    zb = torch.from_numpy(z).bfloat16().float().numpy().reshape(-1, D)
+    Eb = torch.from_numpy(E).bfloat16().float().numpy()
+    ref = O.nearest_code64(zb, Eb)
+    mm, outside = O.near_tie_rows(zb, Eb, idx, ref)
+    assert outside.size == 0 and mm.size <= 2
+
+
+def test_tc_clustered_and_scaled(vq):
+    # trained-model regime (z near a code) and badly scaled latents (|z| >> |e|): the margin scales with |z|
+    for seed, scale, clustered in ((1, None, True), (2, 25.0, False), (3, 1e-3, False)):
+        E, z = large_case_inputs(seed, 1024, 128, 1, 64, 64, scale, clustered)
+        path, idx, _ = run_search(vq, z, E, 1024)
+        assert path == 1
+        ref = O.nearest_code64(z.reshape(-1, 128), E)
+        mm, outside = O.near_tie_rows(z.reshape(-1, 128), E, idx, ref)
+        assert outside.size == 0 and mm.size <= 2
+
+
+def test_tc_hands_back_hard_rows(vq):
+    K, D = 256, 64
+    E, z = large_case_inputs(5, K, D, 1, 8, 64)
+    z = z.copy()
+    z[0, 3, 5] = np.nan
+    z[1, 7, 0] = np.inf
+    z[2, 1, 2] = -np.inf
+    z[3, 0] = 0.0                                          # zero row: margin degenerates to ~0
+    path, idx_tc, _ = run_search(vq, z, E, K)
+    _, idx_s, _ = run_search(vq, z, E, K, force_simt=True)
+    assert path == 1 and np.array_equal(idx_tc, idx_s)
+    assert np.array_equal(idx_tc, O.nearest_code(z.reshape(-1, D), E))
+    # NaN in the codebook: every row goes to the exact kernel; first NaN code wins everywhere
+    E2 = E.copy()
+    E2[77, 3] = np.nan
+    _, idx2, _ = run_search(vq, z, E2, K)
+    assert (idx2[np.isfinite(z.reshape(-1, D)).all(1)] == 77).all()
+    # collapsed codebook: 200 identical zero codes overflow the 32-slot list -> exact kernel, lowest twin
+    E3 = E.copy()
+    E3[40:240] = 0.0
+    _, idx3, _ = run_search(vq, z, E3, K)
+    _, idx3s, _ = run_search(vq, z, E3, K, force_simt=True)
+    assert np.array_equal(idx3, idx3s)
+    fin = np.isfinite(z.reshape(-1, D)).all(1)
+    assert np.array_equal(idx3[fin], O.nearest_code64(z.reshape(-1, D)[fin], E3))
+    # exact duplicates of a WINNING code: lowest index
+    E4 = E.copy()
+    E4[200] = E4[17]
+    z4 = z.copy()
+    z4[4, :] = E4[17] * 1.01
+    _, idx4, _ = run_search(vq, z4, E4, K)
+    assert (idx4[4 * 64:5 * 64] == 17).all()
