@@ -75,6 +75,8 @@ VQB200_API int vqb200_codebook_prepare(const float* E, int K_total, int D, int K
  *              distance counts as the minimum (torch.argmin semantics)
  */
 VQB200_API size_t vqb200_search_workspace_bytes(int64_t N, int K, int D, int mode);
+/* Number of kernels one vqb200_search call of this shape launches (for launch accounting). */
+VQB200_API int vqb200_search_launches(int64_t N, int K, int D, int mode);
 VQB200_API int vqb200_search(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16,
                   const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K,
                   int mode, int64_t idx_offset, int64_t* idx_out, void* workspace,

@@ -32,6 +32,7 @@ SIGNATURES = {
     "vqb200_search_path": (_i, [_i64, _i, _i, _i]),
     "vqb200_codebook_prepare": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "vqb200_search_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
+    "vqb200_search_launches": (_i, [_i64, _i, _i, _i]),
     "vqb200_search": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _i, _i, _i64, _p, _p, _sz, _p]),
     "vqb200_gather": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "vqb200_st_loss": (_i, [_p, _p, _i64, _p, _p, _p]),

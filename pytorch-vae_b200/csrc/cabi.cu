@@ -47,6 +47,12 @@ size_t vqb200_search_workspace_bytes(int64_t N, int K, int D, int mode) {
   return tc_supported(N, K, D) ? tc_workspace_bytes(N, K, D) : 256;
 }
 
+int vqb200_search_launches(int64_t N, int K, int D, int mode) {
+  (void)mode;
+  if (N <= 0) return 0;
+  return tc_supported(N, K, D) ? tc_launches(N, K, D) : 1;
+}
+
 int vqb200_search(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                   const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                   int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream) {

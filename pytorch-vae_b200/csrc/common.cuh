@@ -67,9 +67,10 @@ int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, 
                        uint64_t* packed_out, cudaStream_t s);
 int launch_search_simt_list(const float* z, const int32_t* row_list, const int* n_rows_dev, int64_t max_rows, int D,
                             const float* E, const float* ee_half, int K, int round_bf16, int64_t idx_offset,
-                            int64_t* idx_out, cudaStream_t s);
+                            uint64_t* packed, cudaStream_t s);
 bool tc_supported(int64_t N, int K, int D);
 size_t tc_workspace_bytes(int64_t N, int K, int D);
+int tc_launches(int64_t N, int K, int D);
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                      int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s);

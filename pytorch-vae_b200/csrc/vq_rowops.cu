@@ -110,8 +110,10 @@ __device__ __forceinline__ void block_add_double(double v, double* dst) {
   }
 }
 
+constexpr int GATHER_ILP = 4;   // independent 128-bit items per thread kept in flight (HBM latency x bandwidth)
+
 template <bool ACC>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, 3)
 gather_kernel(const float4* __restrict__ z, const float4* __restrict__ E, const int64_t* __restrict__ idx,
               int64_t N, int D4, int d4_shift, int K_total, float4* zq_out, float4* __restrict__ zq_st_out,
               float4* __restrict__ residual_out, double* sqerr_sum, int32_t* __restrict__ hist,
@@ -119,34 +121,54 @@ gather_kernel(const float4* __restrict__ z, const float4* __restrict__ E, const 
   const int64_t total = N * D4;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   float err = 0.f;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    int64_t row;
-    int c;
-    if (d4_shift >= 0) { row = i >> d4_shift; c = static_cast<int>(i & ((1 << d4_shift) - 1)); }
-    else { row = i / D4; c = static_cast<int>(i - row * D4); }
-    const int64_t k = idx[row];
-    if (k < 0 || k >= K_total) continue;                    // never produced by vqb200_search
-    const float4 e = __ldg(E + k * D4 + c);
-    const float4 v = ld_stream(z + i);
-    float4 df;
-    df.x = __fsub_rn(e.x, v.x); df.y = __fsub_rn(e.y, v.y); df.z = __fsub_rn(e.z, v.z); df.w = __fsub_rn(e.w, v.w);
-    if (zq_out) {
-      float4 o = e;
-      if (ACC) { const float4 p = zq_out[i]; o.x = __fadd_rn(p.x, e.x); o.y = __fadd_rn(p.y, e.y);
-                 o.z = __fadd_rn(p.z, e.z); o.w = __fadd_rn(p.w, e.w); }
-      st_stream(zq_out + i, o);
+  for (int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total;
+       i0 += stride * GATHER_ILP) {
+    int k[GATHER_ILP], row[GATHER_ILP];       // rows per call and code ids both fit 31 bits (checked by the launcher)
+    int c[GATHER_ILP];
+    float4 v[GATHER_ILP], e[GATHER_ILP], prev[GATHER_ILP];
+    bool ok[GATHER_ILP];
+#pragma unroll
+    for (int u = 0; u < GATHER_ILP; ++u) {                  // issue every load of the batch first
+      const int64_t i = i0 + u * stride;
+      ok[u] = i < total;
+      if (!ok[u]) continue;
+      if (d4_shift >= 0) { row[u] = static_cast<int>(i >> d4_shift); c[u] = static_cast<int>(i & ((1 << d4_shift) - 1)); }
+      else { row[u] = static_cast<int>(i / D4); c[u] = static_cast<int>(i - static_cast<int64_t>(row[u]) * D4); }
+      const int64_t kk = idx[row[u]];
+      k[u] = (kk >= 0 && kk < K_total) ? static_cast<int>(kk) : -1;
+      v[u] = ld_stream(z + i);
+      if (ACC) prev[u] = zq_out[i];
     }
-    if (zq_st_out) {                                        // fl(z + fl(zq - z)): bitwise != zq
-      float4 o;
-      o.x = __fadd_rn(v.x, df.x); o.y = __fadd_rn(v.y, df.y); o.z = __fadd_rn(v.z, df.z); o.w = __fadd_rn(v.w, df.w);
-      st_stream(zq_st_out + i, o);
+#pragma unroll
+    for (int u = 0; u < GATHER_ILP; ++u) {
+      ok[u] = ok[u] && k[u] >= 0;                           // out-of-range ids are never produced by vqb200_search
+      if (ok[u]) e[u] = __ldg(E + static_cast<int64_t>(k[u]) * D4 + c[u]);
     }
-    if (residual_out) {                                     // fl(z - zq) (= -df exactly)
-      st_stream(residual_out + i, make_float4(-df.x, -df.y, -df.z, -df.w));
+#pragma unroll
+    for (int u = 0; u < GATHER_ILP; ++u) {
+      if (!ok[u]) continue;
+      const int64_t i = i0 + u * stride;
+      float4 df;
+      df.x = __fsub_rn(e[u].x, v[u].x); df.y = __fsub_rn(e[u].y, v[u].y);
+      df.z = __fsub_rn(e[u].z, v[u].z); df.w = __fsub_rn(e[u].w, v[u].w);
+      if (zq_out) {
+        float4 o = e[u];
+        if (ACC) { o.x = __fadd_rn(prev[u].x, e[u].x); o.y = __fadd_rn(prev[u].y, e[u].y);
+                   o.z = __fadd_rn(prev[u].z, e[u].z); o.w = __fadd_rn(prev[u].w, e[u].w); }
+        st_stream(zq_out + i, o);
+      }
+      if (zq_st_out) {                                      // fl(z + fl(zq - z)): bitwise != zq
+        float4 o;
+        o.x = __fadd_rn(v[u].x, df.x); o.y = __fadd_rn(v[u].y, df.y);
+        o.z = __fadd_rn(v[u].z, df.z); o.w = __fadd_rn(v[u].w, df.w);
+        st_stream(zq_st_out + i, o);
+      }
+      if (residual_out)                                     // fl(z - zq) (= -df exactly)
+        st_stream(residual_out + i, make_float4(-df.x, -df.y, -df.z, -df.w));
+      err = fmaf(df.x, df.x, err); err = fmaf(df.y, df.y, err);
+      err = fmaf(df.z, df.z, err); err = fmaf(df.w, df.w, err);
+      if (hist && c[u] == 0 && (!row_mask || row_mask[row[u]])) atomicAdd(hist + k[u], 1);
     }
-    err = fmaf(df.x, df.x, err); err = fmaf(df.y, df.y, err);
-    err = fmaf(df.z, df.z, err); err = fmaf(df.w, df.w, err);
-    if (hist && c == 0 && (!row_mask || row_mask[row])) atomicAdd(hist + k, 1);
   }
   if (sqerr_sum) block_add_double(static_cast<double>(err), sqerr_sum);
 }
@@ -155,12 +177,14 @@ int launch_gather(const float* z, const float* E, const int64_t* idx, int64_t N,
                   int zq_accumulate, float* zq_st_out, float* residual_out, double* sqerr_sum, int32_t* hist,
                   const uint8_t* row_mask, cudaStream_t s) {
   if (N == 0) return VQB200_OK;
+  if (N > 0x7fffffff) return VQB200_ESHAPE;
   const int D4 = D >> 2;
   int shift = -1;
   if ((D4 & (D4 - 1)) == 0) { shift = 0; while ((1 << shift) < D4) ++shift; }
   const int64_t total = N * D4;
   int64_t blocks = (total + ROW_THREADS - 1) / ROW_THREADS;
-  const int64_t cap = static_cast<int64_t>(kNumSMs) * 8 * 4;          // 8 resident CTAs/SM, ~4 items per thread
+  blocks = (blocks + GATHER_ILP - 1) / GATHER_ILP;
+  const int64_t cap = static_cast<int64_t>(kNumSMs) * 3 * 4;          // 3 resident CTAs/SM, four waves
   if (blocks > cap) blocks = cap;
   auto Z = reinterpret_cast<const float4*>(z);
   auto Ev = reinterpret_cast<const float4*>(E);

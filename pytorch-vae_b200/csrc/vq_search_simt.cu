@@ -21,8 +21,8 @@ constexpr int PAD = 4;
 template <bool ROUND_BF16>
 __global__ void __launch_bounds__(SIMT_THREADS, 2)
 search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_list,
-                   const int* __restrict__ n_rows_dev, int64_t n_rows, int D, const float* __restrict__ E, const float* __restrict__ ee_half, int K,
-                   int64_t idx_offset, int64_t* __restrict__ idx_out, uint64_t* __restrict__ packed_out) {
+                   const int* __restrict__ n_rows_dev, int64_t n_rows, int D, const float* __restrict__ E,
+                   const float* __restrict__ ee_half, int K, int codes_per_cta, int64_t idx_offset, int64_t* __restrict__ idx_out, uint64_t* __restrict__ packed_out) {
   __shared__ float zs[BK][BM + PAD];
   __shared__ float es[BK][BN + PAD];
   __shared__ float ees[BN];
@@ -46,7 +46,11 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
 #pragma unroll
   for (int i = 0; i < TM; ++i) best[i] = ~0ull;
 
-  for (int n0 = 0; n0 < K; n0 += BN) {
+  // blockIdx.y selects a code range (the hand-back path splits K over CTAs so that a handful of rows
+  // does not serialise a whole codebook sweep in one CTA); results then merge through atomicMin.
+  const int k_begin = codes_per_cta > 0 ? static_cast<int>(blockIdx.y) * codes_per_cta : 0;
+  const int k_end = codes_per_cta > 0 ? min(K, k_begin + codes_per_cta) : K;
+  for (int n0 = k_begin; n0 < k_end; n0 += BN) {
     float acc[TM][TN];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
@@ -54,7 +58,7 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
       for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     __syncthreads();   // the previous tile's epilogue may still be reading ees
-    if (tid < BN) ees[tid] = (n0 + tid < K) ? ee_half[n0 + tid] : __int_as_float(0x7f800000);
+    if (tid < BN) ees[tid] = (n0 + tid < k_end) ? ee_half[n0 + tid] : __int_as_float(0x7f800000);
 
     for (int k0 = 0; k0 < D; k0 += BK) {
       __syncthreads();
@@ -65,7 +69,7 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
           v = *reinterpret_cast<const float4*>(z + src_row[i] * D + k0 + ld_c);
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
         int code = n0 + ld_r + 64 * i;
-        if (code < K && k0 + ld_c < D)
+        if (code < k_end && k0 + ld_c < D)
           w = *reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + k0 + ld_c);
         if (ROUND_BF16) {
           v.x = bf16_round(v.x); v.y = bf16_round(v.y); v.z = bf16_round(v.z); v.w = bf16_round(v.w);
@@ -97,7 +101,7 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
         const int code = n0 + tx * TN + j;
-        if (code < K) m = umin64(m, pack_minloc(ees[tx * TN + j] - acc[i][j], static_cast<uint32_t>(code)));
+        if (code < k_end) m = umin64(m, pack_minloc(ees[tx * TN + j] - acc[i][j], static_cast<uint32_t>(code)));
       }
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) m = umin64(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -111,25 +115,29 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
       const int64_t r = row0 + ty * TM + i;
       if (r >= n_rows) continue;
       const int64_t dst = row_list ? static_cast<int64_t>(row_list[r]) : r;
-      if (packed_out) packed_out[dst] = (best[i] & 0xffffffff00000000ull) |
-                                        static_cast<uint64_t>((best[i] & 0xffffffffull) + idx_offset);
+      if (packed_out) {
+        const uint64_t v = (best[i] & 0xffffffff00000000ull) |
+                           static_cast<uint64_t>((best[i] & 0xffffffffull) + idx_offset);
+        if (codes_per_cta > 0) atomicMin(reinterpret_cast<unsigned long long*>(packed_out + dst), v);
+        else packed_out[dst] = v;
+      }
       if (idx_out) idx_out[dst] = static_cast<int64_t>(best[i] & 0xffffffffull) + idx_offset;
     }
   }
 }
 
 static int launch_impl(const float* z, const int32_t* row_list, const int* n_rows_dev, int64_t n_rows, int D,
-                       const float* E, const float* ee_half, int K, int round_bf16, int64_t idx_offset,
-                       int64_t* idx_out, uint64_t* packed_out, cudaStream_t s) {
+                       const float* E, const float* ee_half, int K, int codes_per_cta, int round_bf16,
+                       int64_t idx_offset, int64_t* idx_out, uint64_t* packed_out, cudaStream_t s) {
   if (n_rows == 0) return VQB200_OK;
   const int64_t blocks = (n_rows + BM - 1) / BM;
   if (blocks > 0x7fffffff) return VQB200_ESHAPE;
-  dim3 grid(static_cast<unsigned>(blocks));
+  dim3 grid(static_cast<unsigned>(blocks), codes_per_cta > 0 ? (K + codes_per_cta - 1) / codes_per_cta : 1);
   if (round_bf16)
-    search_simt_kernel<true><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows_dev, n_rows, D, E, ee_half, K, idx_offset,
+    search_simt_kernel<true><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows_dev, n_rows, D, E, ee_half, K, codes_per_cta, idx_offset,
                                                           idx_out, packed_out);
   else
-    search_simt_kernel<false><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows_dev, n_rows, D, E, ee_half, K, idx_offset,
+    search_simt_kernel<false><<<grid, SIMT_THREADS, 0, s>>>(z, row_list, n_rows_dev, n_rows, D, E, ee_half, K, codes_per_cta, idx_offset,
                                                            idx_out, packed_out);
   return status_of(cudaGetLastError());
 }
@@ -137,14 +145,18 @@ static int launch_impl(const float* z, const int32_t* row_list, const int* n_row
 int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, int D, const float* E,
                        const float* ee_half, int K, int round_bf16, int64_t idx_offset, int64_t* idx_out,
                        uint64_t* packed_out, cudaStream_t s) {
-  return launch_impl(z, row_list, nullptr, n_rows, D, E, ee_half, K, round_bf16, idx_offset, idx_out, packed_out, s);
+  return launch_impl(z, row_list, nullptr, n_rows, D, E, ee_half, K, 0, round_bf16, idx_offset, idx_out, packed_out, s);
 }
 
-// Row list whose length lives on the device: the grid covers max_rows, surplus CTAs exit at once.
+// Row list whose length lives on the device: the grid covers max_rows x code ranges, surplus CTAs exit
+// at once.  packed[row] must hold ~0 on entry; it receives key(d) << 32 | (idx_offset + argmin).
 int launch_search_simt_list(const float* z, const int32_t* row_list, const int* n_rows_dev, int64_t max_rows, int D,
                             const float* E, const float* ee_half, int K, int round_bf16, int64_t idx_offset,
-                            int64_t* idx_out, cudaStream_t s) {
-  return launch_impl(z, row_list, n_rows_dev, max_rows, D, E, ee_half, K, round_bf16, idx_offset, idx_out, nullptr, s);
+                            uint64_t* packed, cudaStream_t s) {
+  int tiles = (K + BN - 1) / BN;
+  int per = (tiles + 63) / 64;                     // at most 64 code ranges
+  return launch_impl(z, row_list, n_rows_dev, max_rows, D, E, ee_half, K, per * BN, round_bf16, idx_offset, nullptr,
+                     packed, s);
 }
 
 }  // namespace vqb

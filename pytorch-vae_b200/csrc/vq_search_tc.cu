@@ -151,6 +151,7 @@ struct TcParams {
   int D, K;
   int row_tiles, ksplit, tiles_per_split, code_tiles;
   int stages;
+  int zbufs;             // 1 or 2 z-tile buffers (2 when shared memory allows: next item's rows prefetch)
   const float* ee_half;  // [K] (plane chosen by mode)
   const float* margin;   // [n_rows]
   uint2* cand;           // [n_rows][ksplit][TC_CAND]
@@ -167,8 +168,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int KBLK = p.D / TC_KB;
-  const uint32_t z_smem = base;                                    // KBLK slabs of [BM rows x 128 B]
-  const uint32_t e_smem = z_smem + static_cast<uint32_t>(BM) * p.D * 2;   // ring of [128 codes x 128 B]
+  const uint32_t z_bytes = static_cast<uint32_t>(BM) * p.D * 2;
+  const uint32_t z_smem = base;                                    // zbufs x KBLK slabs of [BM rows x 128 B]
+  const uint32_t e_smem = z_smem + p.zbufs * z_bytes;              // ring of [128 codes x 128 B]
   const uint32_t ee_smem = e_smem + static_cast<uint32_t>(p.stages) * TC_STAGE_BYTES;   // [NEPI][2][128] fp32
   const uint32_t bar0 = ee_smem + NEPI * 2 * TC_BN * 4;
   // barrier map (8 bytes each)
@@ -176,9 +178,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
   const uint32_t bar_empty = bar0 + 8 * 8;                // [stages]
   const uint32_t bar_tfull = bar0 + 16 * 8;               // [2]
   const uint32_t bar_tempty = bar0 + 18 * 8;              // [2]
-  const uint32_t bar_zfull = bar0 + 20 * 8;
-  const uint32_t bar_zempty = bar0 + 21 * 8;
-  const uint32_t tmem_slot = bar0 + 22 * 8;
+  const uint32_t bar_zfull = bar0 + 20 * 8;               // [2]
+  const uint32_t bar_zempty = bar0 + 22 * 8;              // [2]
+  const uint32_t tmem_slot = bar0 + 24 * 8;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));  // generic pointer to the aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,8 +188,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, NEPI); }
-    mbar_init(bar_zfull, 1);
-    mbar_init(bar_zempty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(bar_zfull + 8 * b, 1); mbar_init(bar_zempty + 8 * b, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -211,10 +212,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
         const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
         const int t0 = ks * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
-        mbar_wait(bar_zempty, (it & 1) ^ 1);
-        mbar_expect_tx(bar_zfull, static_cast<uint32_t>(BM) * p.D * 2);
+        const uint32_t zb = p.zbufs == 2 ? (it & 1) : 0;
+        const uint32_t zuse = p.zbufs == 2 ? (it >> 1) : it;
+        mbar_wait(bar_zempty + 8 * zb, (zuse & 1) ^ 1);
+        mbar_expect_tx(bar_zfull + 8 * zb, z_bytes);
         for (int kb = 0; kb < KBLK; ++kb)
-          tma_load_2d(z_smem + kb * (BM * 128), &tmap_z, bar_zfull, kb * TC_KB, rt * BM);
+          tma_load_2d(z_smem + zb * z_bytes + kb * (BM * 128), &tmap_z, bar_zfull + 8 * zb, kb * TC_KB, rt * BM);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < KBLK; ++kb) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -233,7 +236,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
         const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
         const int t0 = ks * p.tiles_per_split;
         const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
-        mbar_wait(bar_zfull, it & 1);
+        const uint32_t zb = p.zbufs == 2 ? (it & 1) : 0;
+        const uint32_t zuse = p.zbufs == 2 ? (it >> 1) : it;
+        mbar_wait(bar_zfull + 8 * zb, zuse & 1);
         for (int t = t0; t < t1; ++t, ++tg) {
           const uint32_t b = tg & 1;
           mbar_wait(bar_tempty + 8 * b, ((tg >> 1) & 1) ^ 1);
@@ -246,7 +251,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
               const uint32_t d_tmem = tmem_base + b * (NHALF * TC_BN) + h * TC_BN;
 #pragma unroll
               for (int k = 0; k < TC_KB / 16; ++k) {
-                const uint64_t ad = umma_desc(z_smem + kb * (BM * 128) + h * (128 * 128) + k * 32);
+                const uint64_t ad = umma_desc(z_smem + zb * z_bytes + kb * (BM * 128) + h * (128 * 128) + k * 32);
                 const uint64_t bd = umma_desc(e_smem + stage * TC_STAGE_BYTES + k * 32);
                 tc_mma_bf16(d_tmem, ad, bd, kIdesc, (kb | k) ? 1u : 0u);
               }
@@ -256,7 +261,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
           }
           tc_commit(bar_tfull + 8 * b);                // accumulator tile complete
         }
-        tc_commit(bar_zempty);                         // z tile may be overwritten
+        tc_commit(bar_zempty + 8 * zb);                // z tile may be overwritten
       }
     }
   } else {
@@ -351,18 +356,16 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------ exact re-rank
-// One warp per row: prune the candidate lists against the final maximum, score the survivors
-// exactly (fp64 accumulation of the fp32 -- or bf16-rounded -- inputs), lowest index wins ties.
-template <bool BF16>
+// Stage 1, one THREAD per row: prune the candidate lists against the final maximum.  One survivor
+// = certified by the error bound, written at once.  Several = compacted in place and queued for
+// stage 2.  Overflowed / empty / non-finite rows are queued for the exact SIMT kernel.
 __global__ void __launch_bounds__(256)
-rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, const float* __restrict__ E,
-              const __nv_bfloat16* __restrict__ Eb, int64_t n, int D, int ksplit, const float* __restrict__ margin,
-              const uint2* __restrict__ cand, const int* __restrict__ cnt, const float* __restrict__ best,
-              int64_t idx_offset, int64_t* __restrict__ idx_out, int* __restrict__ fb_rows, int* __restrict__ fb_count) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t row = warp; row < n; row += nwarps) {
+prune_kernel(int64_t n, int ksplit, const float* __restrict__ margin, uint2* __restrict__ cand,
+             int* __restrict__ cnt, const float* __restrict__ best, int64_t idx_offset,
+             int64_t* __restrict__ idx_out, int* __restrict__ multi_rows, int* __restrict__ fb_rows,
+             uint64_t* __restrict__ fb_packed, int* __restrict__ counters) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n; row += stride) {
     float bmax = __int_as_float(0xff800000);
     bool bad = false;
     for (int ks = 0; ks < ksplit; ++ks) {
@@ -371,52 +374,96 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
       bmax = fmaxf(bmax, best[row * ksplit + ks]);
     }
     const float mg = margin[row];
-    if (bad || !(mg == mg)) {                          // overflow / nothing admitted / non-finite: exact SIMT path
-      if (lane == 0) fb_rows[atomicAdd(fb_count, 1)] = static_cast<int>(row);
+    if (bad || !(mg == mg)) {
+      const int pos = atomicAdd(counters + 0, 1);
+      fb_rows[pos] = static_cast<int>(row);
+      fb_packed[row] = ~0ull;
       continue;
     }
     const float thr = bmax - mg;
+    uint2* out = cand + row * ksplit * TC_CAND;        // survivors are compacted to the front of the row's slots
+    int ns = 0;
+    uint32_t first = 0;
+    for (int ks = 0; ks < ksplit; ++ks) {
+      const int c = cnt[row * ksplit + ks];
+      const uint2* src = cand + (row * ksplit + ks) * TC_CAND;
+      for (int j = 0; j < c; ++j) {
+        const uint2 ent = src[j];
+        if (__uint_as_float(ent.y) >= thr) {
+          if (ns == 0) first = ent.x;
+          if (ns < TC_CAND) out[ns] = ent;             // out + ns <= src + j: never overtakes the read cursor
+          ++ns;
+        }
+      }
+    }
+    if (ns == 1) {
+      idx_out[row] = idx_offset + first;
+    } else if (ns <= TC_CAND) {
+      cnt[row * ksplit] = ns;
+      multi_rows[atomicAdd(counters + 1, 1)] = static_cast<int>(row);
+    } else {
+      const int pos = atomicAdd(counters + 0, 1);
+      fb_rows[pos] = static_cast<int>(row);
+      fb_packed[row] = ~0ull;
+    }
+  }
+}
+
+// Stage 2, one WARP per queued row: score the survivors exactly (fp64 accumulation of the fp32 -- or
+// bf16-rounded -- inputs); ascending code order + strict '>' keeps the lowest index on exact ties.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+exact_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, const float* __restrict__ E,
+             const __nv_bfloat16* __restrict__ Eb, int D, int ksplit, const uint2* __restrict__ cand,
+             const int* __restrict__ cnt, const int* __restrict__ multi_rows, const int* __restrict__ counters,
+             int64_t idx_offset, int64_t* __restrict__ idx_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int n_multi = counters[1];
+  for (int64_t i = warp; i < n_multi; i += nwarps) {
+    const int64_t row = multi_rows[i];
+    const int ns = cnt[row * ksplit];
+    const uint32_t my_code = lane < ns ? cand[row * ksplit * TC_CAND + lane].x : 0u;
     double top = -1e300;
     uint32_t top_idx = 0xffffffffu;
-    int n_surv = 0;
-    uint32_t only = 0;
-    // pass 1: count survivors (lists are in ascending code order, splits too)
-    for (int ks = 0; ks < ksplit; ++ks) {
-      const int c = cnt[row * ksplit + ks];
-      const uint2 ent = lane < c ? cand[(row * ksplit + ks) * TC_CAND + lane] : make_uint2(0, 0xff800000u);
-      const unsigned surv = __ballot_sync(0xffffffffu, lane < c && __uint_as_float(ent.y) >= thr);
-      if (surv) {
-        if (n_surv == 0) only = __shfl_sync(0xffffffffu, ent.x, __ffs(surv) - 1);
-        n_surv += __popc(surv);
-      }
-    }
-    if (n_surv == 1) {                                 // certified by the error bound: no arithmetic needed
-      if (lane == 0) idx_out[row] = idx_offset + only;
-      continue;
-    }
-    for (int ks = 0; ks < ksplit; ++ks) {
-      const int c = cnt[row * ksplit + ks];
-      const uint2 ent = lane < c ? cand[(row * ksplit + ks) * TC_CAND + lane] : make_uint2(0, 0xff800000u);
-      unsigned surv = __ballot_sync(0xffffffffu, lane < c && __uint_as_float(ent.y) >= thr);
-      while (surv) {
-        const int src = __ffs(surv) - 1;
-        surv &= surv - 1;
-        const uint32_t code = __shfl_sync(0xffffffffu, ent.x, src);
-        double dot = 0.0, ee = 0.0;
-        for (int d = lane; d < D; d += 32) {
-          double zv, ev;
-          if (BF16) { zv = __bfloat162float(zb[row * D + d]); ev = __bfloat162float(Eb[static_cast<int64_t>(code) * D + d]); }
-          else { zv = z[row * D + d]; ev = E[static_cast<int64_t>(code) * D + d]; }
-          dot = fma(zv, ev, dot);
-          ee = fma(ev, ev, ee);
+    for (int j = 0; j < ns; ++j) {
+      const uint32_t code = __shfl_sync(0xffffffffu, my_code, j);
+      double dot = 0.0, ee = 0.0;
+      for (int d = lane * 4; d < D; d += 128) {
+        float zv[4], ev[4];
+        if (BF16) {
+          const uint2 a = *reinterpret_cast<const uint2*>(zb + row * D + d);
+          const uint2 b = *reinterpret_cast<const uint2*>(Eb + static_cast<int64_t>(code) * D + d);
+          zv[0] = __uint_as_float(a.x << 16); zv[1] = __uint_as_float(a.x & 0xffff0000u);
+          zv[2] = __uint_as_float(a.y << 16); zv[3] = __uint_as_float(a.y & 0xffff0000u);
+          ev[0] = __uint_as_float(b.x << 16); ev[1] = __uint_as_float(b.x & 0xffff0000u);
+          ev[2] = __uint_as_float(b.y << 16); ev[3] = __uint_as_float(b.y & 0xffff0000u);
+        } else {
+          *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + row * D + d);
+          *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + d));
         }
-        dot = warp_sum(dot);
-        ee = warp_sum(ee);
-        const double sc = dot - 0.5 * ee;
-        if (sc > top) { top = sc; top_idx = code; }    // ascending code order + strict '>' = lowest index on ties
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
+          ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+        }
       }
+      dot = warp_sum(dot);
+      ee = warp_sum(ee);
+      const double sc = dot - 0.5 * ee;
+      if (sc > top) { top = sc; top_idx = code; }
     }
     if (lane == 0) idx_out[row] = idx_offset + top_idx;
+  }
+}
+
+__global__ void fb_unpack_kernel(const int* __restrict__ fb_rows, const uint64_t* __restrict__ fb_packed,
+                                 const int* __restrict__ counters, int64_t* __restrict__ idx_out) {
+  const int n = counters[0];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int row = fb_rows[i];
+    idx_out[row] = static_cast<int64_t>(fb_packed[row] & 0xffffffffull);
   }
 }
 
@@ -450,7 +497,7 @@ static bool make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int 
 }
 
 struct TcPlan {
-  int BM, stages, smem_bytes;
+  int BM, stages, smem_bytes, zbufs;
   int64_t chunk_rows;
   int ksplit_max;
 };
@@ -459,17 +506,25 @@ static bool tc_plan(int64_t N, int K, int D, TcPlan* pl) {
   if (D % TC_KB != 0 || D < 64 || D > 512 || K < TC_BN || N < 64) return false;
   pl->BM = (D <= 256) ? 256 : 128;
   const int nepi = pl->BM / 32;
-  const int fixed = 1024 + pl->BM * D * 2 + nepi * 2 * TC_BN * 4 + 256;
+  const int ztile = pl->BM * D * 2;
+  pl->zbufs = (2 * ztile + 4 * TC_STAGE_BYTES + nepi * 2 * TC_BN * 4 + 2048 <= TC_SMEM_LIMIT) ? 2 : 1;
+  const int fixed = 1024 + pl->zbufs * ztile + nepi * 2 * TC_BN * 4 + 256;
   int st = (TC_SMEM_LIMIT - fixed) / TC_STAGE_BYTES;
   if (st > 8) st = 8;
   if (st < 2) return false;
   pl->stages = st;
   pl->smem_bytes = fixed + st * TC_STAGE_BYTES;
-  // rows per pass: keep the bf16 copy + the fp32 rows of one chunk around the L2 size for small D,
-  // bound the workspace for large D
-  int64_t chunk = (static_cast<int64_t>(96) << 20) / (static_cast<int64_t>(D) * 6);
-  chunk = (chunk / 4096) * 4096;
-  if (chunk < 65536) chunk = 65536;
+  // rows per pass.  Small D is HBM-bound: keep one chunk's fp32 rows + bf16 copy within the 126 MB L2 so
+  // the pre-pass output and the re-rank / gather re-reads hit L2.  Large D is tensor-bound: big chunks
+  // (many waves per launch), bounded only by the workspace.
+  int64_t chunk;
+  if (D <= 128) {
+    chunk = (static_cast<int64_t>(96) << 20) / (static_cast<int64_t>(D) * 6);
+    chunk = (chunk / 4096) * 4096;
+    if (chunk < 65536) chunk = 65536;
+  } else {
+    chunk = 1 << 20;
+  }
   if (chunk > (1 << 20)) chunk = 1 << 20;
   pl->chunk_rows = chunk;
   pl->ksplit_max = 8;
@@ -511,8 +566,16 @@ size_t tc_workspace_bytes(int64_t N, int K, int D) {
   b += align_up(static_cast<size_t>(rows) * 4, 256);                // margin
   b += align_up(slots * 4, 256) * 2;                                // cnt, best
   b += align_up(slots * TC_CAND * 8, 256);                          // cand
-  b += align_up(static_cast<size_t>(rows) * 4, 256);                // fb_rows
+  b += align_up(static_cast<size_t>(rows) * 4, 256) * 2;            // fb_rows, multi_rows
+  b += align_up(static_cast<size_t>(rows) * 8, 256);                // fb_packed
   return b;
+}
+
+int tc_launches(int64_t N, int K, int D) {
+  TcPlan pl;
+  if (!tc_plan(N, K, D, &pl)) return 0;
+  const int64_t chunks = (N + pl.chunk_rows - 1) / pl.chunk_rows;
+  return static_cast<int>(chunks) * 6;   // zprep, tcgen05 search, prune, exact, SIMT hand-back, unpack
 }
 
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
@@ -527,13 +590,15 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   const size_t slots = tc_slots(cap, pl.BM);
 
   uint8_t* w = static_cast<uint8_t*>(workspace);
-  int* fb_count = reinterpret_cast<int*>(w); w += 256;
+  int* counters = reinterpret_cast<int*>(w); w += 256;   // [0] rows handed to the SIMT kernel, [1] multi-survivor rows
   __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(w); w += align_up(static_cast<size_t>(cap) * D * 2, 256);
   float* margin = reinterpret_cast<float*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
   int* cnt = reinterpret_cast<int*>(w); w += align_up(slots * 4, 256);
   float* best = reinterpret_cast<float*>(w); w += align_up(slots * 4, 256);
   uint2* cand = reinterpret_cast<uint2*>(w); w += align_up(slots * TC_CAND * 8, 256);
-  int* fb_rows = reinterpret_cast<int*>(w);
+  int* fb_rows = reinterpret_cast<int*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
+  int* multi_rows = reinterpret_cast<int*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
+  uint64_t* fb_packed = reinterpret_cast<uint64_t*>(w);
 
   CUtensorMap map_e;
   if (!make_map(&map_e, E_bf16, K, D, TC_BN)) return VQB200_EDRIVER;
@@ -551,7 +616,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   for (int64_t r0 = 0; r0 < N; r0 += pl.chunk_rows) {
     const int64_t rows = (N - r0) < pl.chunk_rows ? (N - r0) : pl.chunk_rows;
     const float* zc = z + r0 * D;
-    cudaError_t e = cudaMemsetAsync(fb_count, 0, sizeof(int), s);
+    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(int), s);
     if (e != cudaSuccess) return status_of(e);
 
     int64_t warps = rows;
@@ -567,6 +632,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, ksm, &p.tiles_per_split);
     p.code_tiles = code_tiles;
     p.stages = pl.stages;
+    p.zbufs = pl.zbufs;
     p.ee_half = bf ? ee_half_bf16 : ee_half;
     p.margin = margin; p.cand = cand; p.cnt = cnt; p.best = best;
     const int items = p.row_tiles * p.ksplit;
@@ -578,21 +644,30 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
 
-    blocks = (rows + 7) / 8;
+    blocks = (rows + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
-    if (bf)
-      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit, margin, cand,
-                                                                       cnt, best, idx_offset, idx_out + r0, fb_rows, fb_count);
-    else
-      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit, margin, cand,
-                                                                        cnt, best, idx_offset, idx_out + r0, fb_rows, fb_count);
+    prune_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(rows, p.ksplit, margin, cand, cnt, best, idx_offset,
+                                                              idx_out + r0, multi_rows, fb_rows, fb_packed, counters);
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
-    // rows handed back (overflow / non-finite): exact SIMT scan over the device-side row list
-    int st = launch_search_simt_list(zc, fb_rows, fb_count, rows, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0,
-                                     idx_offset, idx_out + r0, s);
+    blocks = (rows + 7) / 8;                           // one warp per queued row; surplus warps exit at once
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
+    if (bf)
+      exact_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, D, p.ksplit, cand, cnt, multi_rows,
+                                                                      counters, idx_offset, idx_out + r0);
+    else
+      exact_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, D, p.ksplit, cand, cnt, multi_rows,
+                                                                       counters, idx_offset, idx_out + r0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return status_of(e);
+    // rows handed back (overflow / non-finite): exact SIMT scan over the device-side row list, K split over CTAs
+    int st = launch_search_simt_list(zc, fb_rows, counters, rows, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0,
+                                     idx_offset, fb_packed, s);
     if (st != VQB200_OK) return st;
+    fb_unpack_kernel<<<64, 256, 0, s>>>(fb_rows, fb_packed, counters, idx_out + r0);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return status_of(e);
   }
   return VQB200_OK;
 }

@@ -77,7 +77,7 @@ def search(z: torch.Tensor, E: torch.Tensor, cache: CodebookCache, level: int, m
 
 
 def search_launches(N, K, D, mode) -> int:
-    return 1 if lib.vqb200_search_path(N, K, D, mode) == 0 else 3
+    return lib.vqb200_search_launches(N, K, D, mode)
 
 
 def gather(z, E, idx, zq_out=None, accumulate=False, zq_st_out=None, residual_out=None, sqerr_sum=None,
