@@ -30,7 +30,8 @@ namespace vqb {
 
 constexpr int TC_BN = 128;          // codes per accumulator tile (UMMA N)
 constexpr int TC_KB = 64;           // bf16 elements per 128-byte swizzle row
-constexpr int TC_CAND = 32;         // candidate slots per (row, code split)
+constexpr int TC_CAND = 31;         // candidate records per (row, code split); slot 31 is write scratch
+constexpr int TC_SLOTS = TC_CAND + 1;
 constexpr int TC_STAGE_BYTES = TC_BN * TC_KB * 2;   // 16 KB
 constexpr int TC_SMEM_LIMIT = 232448;               // 227 KB
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 22;
@@ -100,7 +101,8 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) <
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),     \
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),   \
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])    \
-      : "r"(taddr))
+      : "r"(taddr)                                                                                                 \
+      : "memory")
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------ z pre-pass
@@ -154,10 +156,47 @@ struct TcParams {
   int zbufs;             // 1 or 2 z-tile buffers (2 when shared memory allows: next item's rows prefetch)
   const float* ee_half;  // [K] (plane chosen by mode)
   const float* margin;   // [n_rows]
-  uint2* cand;           // [n_rows][ksplit][TC_CAND]
+  uint2* cand;           // [n_rows][ksplit][TC_SLOTS] records {code group << 8 | admit mask, group max}
   int* cnt;              // [n_rows][ksplit]
   float* best;           // [n_rows][ksplit]
 };
+
+// Scan 32 accumulator columns of one row.  Scores s = acc - |e|^2/2.  The whole chunk is skipped with ONE
+// compare unless its maximum reaches the admission threshold thr = best - margin (rare once the running
+// maximum has settled: ~ (1 + margin * best) / j per column j).  The slow path is straight-line,
+// predicated code (no per-element branches, no serial dependency): each group of 8 columns whose maximum
+// passes emits one record {group index << 8 | 8-bit admit mask, group max}.
+__device__ __forceinline__ void epi_scan(const uint32_t (&v)[32], const float* __restrict__ ee, uint32_t code0,
+                                         float margin, float& best, float& thr, int& cnt, uint2* cand_row) {
+  float s[32], gm[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 ea = *reinterpret_cast<const float4*>(ee + g * 8);
+    const float4 eb = *reinterpret_cast<const float4*>(ee + g * 8 + 4);
+    s[g * 8 + 0] = __uint_as_float(v[g * 8 + 0]) - ea.x; s[g * 8 + 1] = __uint_as_float(v[g * 8 + 1]) - ea.y;
+    s[g * 8 + 2] = __uint_as_float(v[g * 8 + 2]) - ea.z; s[g * 8 + 3] = __uint_as_float(v[g * 8 + 3]) - ea.w;
+    s[g * 8 + 4] = __uint_as_float(v[g * 8 + 4]) - eb.x; s[g * 8 + 5] = __uint_as_float(v[g * 8 + 5]) - eb.y;
+    s[g * 8 + 6] = __uint_as_float(v[g * 8 + 6]) - eb.z; s[g * 8 + 7] = __uint_as_float(v[g * 8 + 7]) - eb.w;
+    gm[g] = fmaxf(fmaxf(fmaxf(s[g * 8 + 0], s[g * 8 + 1]), fmaxf(s[g * 8 + 2], s[g * 8 + 3])),
+                  fmaxf(fmaxf(s[g * 8 + 4], s[g * 8 + 5]), fmaxf(s[g * 8 + 6], s[g * 8 + 7])));
+  }
+  const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+  if (cm >= thr) {
+    best = fmaxf(best, cm);
+    thr = best - margin;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint32_t mk = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mk |= (s[g * 8 + i] >= thr) ? (1u << i) : 0u;
+      const bool hit = gm[g] >= thr;
+      // unconditional store: misses land in the row's scratch slot TC_CAND (keeps the path branch-free)
+      const int slot = (hit && cnt < TC_CAND) ? cnt : TC_CAND;
+      cand_row[slot] = make_uint2((((code0 >> 3) + g) << 8) | mk, __float_as_uint(gm[g]));
+      cnt += hit ? 1 : 0;
+    }
+  }
+}
 
 template <int BM>
 __global__ void __launch_bounds__(64 + BM, 1)
@@ -278,8 +317,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
       const int64_t row = static_cast<int64_t>(rt) * BM + half * 128 + quarter * 32 + lane;
       const bool row_ok = row < p.n_rows;
       const float margin = row_ok ? p.margin[row] : __int_as_float(0x7fc00000);
-      uint2* cand_row = p.cand + (row_ok ? (row * p.ksplit + ks) * TC_CAND : 0);
+      uint2* cand_row = p.cand + (row_ok ? (row * p.ksplit + ks) : 0) * TC_SLOTS;   // rows past the end share row 0's scratch... never admitted
       float best = __int_as_float(0xff800000);
+      float thr = margin == margin ? best : margin;     // admission threshold best - margin (NaN: never admits)
       int cnt = 0;
 
       float4 ee_next;
@@ -307,38 +347,25 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * (NHALF * TC_BN) +
                                half * TC_BN;
-#pragma unroll 1
-        for (int c = 0; c < TC_BN / 32; ++c) {
-          uint32_t v[32];
-          TC_LD32(taddr + c * 32, v);
-          tc_wait_ld();
-          float s[32];
-          float m = __int_as_float(0xff800000);
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 e4 = *reinterpret_cast<const float4*>(ee + c * 32 + j);
-            s[j + 0] = __uint_as_float(v[j + 0]) - e4.x;
-            s[j + 1] = __uint_as_float(v[j + 1]) - e4.y;
-            s[j + 2] = __uint_as_float(v[j + 2]) - e4.z;
-            s[j + 3] = __uint_as_float(v[j + 3]) - e4.w;
-            m = fmaxf(m, fmaxf(fmaxf(s[j], s[j + 1]), fmaxf(s[j + 2], s[j + 3])));
-          }
-          if (m >= best - margin) {                    // rare after the first few tiles
-            best = fmaxf(best, m);
-            const float thr = best - margin;
-            const uint32_t code0 = static_cast<uint32_t>(t * TC_BN + c * 32);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (s[j] >= thr) {
-                if (cnt < TC_CAND) cand_row[cnt] = make_uint2(code0 + j, __float_as_uint(s[j]));
-                ++cnt;
-              }
-            }
-          }
-        }
+        // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is scanned, and the
+        // accumulator buffer is handed back to the MMA warp as soon as its last chunk sits in registers.
+        uint32_t va[32], vb[32];
+        const uint32_t code_t = static_cast<uint32_t>(t * TC_BN);
+        TC_LD32(taddr, va);
+        tc_wait_ld();
+        TC_LD32(taddr + 32, vb);
+        epi_scan(va, ee, code_t, margin, best, thr, cnt, cand_row);
+        tc_wait_ld();
+        TC_LD32(taddr + 64, va);
+        epi_scan(vb, ee + 32, code_t + 32, margin, best, thr, cnt, cand_row);
+        tc_wait_ld();
+        TC_LD32(taddr + 96, vb);
+        epi_scan(va, ee + 64, code_t + 64, margin, best, thr, cnt, cand_row);
+        tc_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        epi_scan(vb, ee + 96, code_t + 96, margin, best, thr, cnt, cand_row);
       }
       if (row_ok) {
         p.cnt[row * p.ksplit + ks] = cnt;
@@ -356,9 +383,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------ exact re-rank
-// Stage 1, one THREAD per row: prune the candidate lists against the final maximum.  One survivor
-// = certified by the error bound, written at once.  Several = compacted in place and queued for
-// stage 2.  Overflowed / empty / non-finite rows are queued for the exact SIMT kernel.
+// Stage 1, one THREAD per row: prune the candidate records against the final maximum.  Exactly one
+// surviving code = certified by the error bound, written at once.  Several = compacted in place and
+// queued for stage 2.  Overflowed / empty / non-finite rows are queued for the exact SIMT kernel.
 __global__ void __launch_bounds__(256)
 prune_kernel(int64_t n, int ksplit, const float* __restrict__ margin, uint2* __restrict__ cand,
              int* __restrict__ cnt, const float* __restrict__ best, int64_t idx_offset,
@@ -374,34 +401,31 @@ prune_kernel(int64_t n, int ksplit, const float* __restrict__ margin, uint2* __r
       bmax = fmaxf(bmax, best[row * ksplit + ks]);
     }
     const float mg = margin[row];
-    if (bad || !(mg == mg)) {
-      const int pos = atomicAdd(counters + 0, 1);
-      fb_rows[pos] = static_cast<int>(row);
-      fb_packed[row] = ~0ull;
-      continue;
-    }
-    const float thr = bmax - mg;
-    uint2* out = cand + row * ksplit * TC_CAND;        // survivors are compacted to the front of the row's slots
-    int ns = 0;
+    int ns = 0, ncodes = 0;
     uint32_t first = 0;
-    for (int ks = 0; ks < ksplit; ++ks) {
-      const int c = cnt[row * ksplit + ks];
-      const uint2* src = cand + (row * ksplit + ks) * TC_CAND;
-      for (int j = 0; j < c; ++j) {
-        const uint2 ent = src[j];
-        if (__uint_as_float(ent.y) >= thr) {
-          if (ns == 0) first = ent.x;
-          if (ns < TC_CAND) out[ns] = ent;             // out + ns <= src + j: never overtakes the read cursor
-          ++ns;
+    if (!bad && mg == mg) {
+      const float thr = bmax - mg;
+      uint2* out = cand + row * ksplit * TC_SLOTS;     // survivors are compacted to the front of the row's slots
+      for (int ks = 0; ks < ksplit; ++ks) {
+        const int c = cnt[row * ksplit + ks];
+        const uint2* src = cand + (row * ksplit + ks) * TC_SLOTS;
+        for (int j = 0; j < c; ++j) {
+          const uint2 ent = src[j];
+          if (__uint_as_float(ent.y) >= thr) {         // the group's maximum is still within the margin
+            if (ns == 0) first = ent.x;
+            if (ns < TC_CAND) out[ns] = ent;           // out + ns <= src + j: never overtakes the read cursor
+            ++ns;
+            ncodes += __popc(ent.x & 0xffu);
+          }
         }
       }
     }
-    if (ns == 1) {
-      idx_out[row] = idx_offset + first;
-    } else if (ns <= TC_CAND) {
+    if (ns == 1 && ncodes == 1) {
+      idx_out[row] = idx_offset + ((first >> 8) << 3) + (__ffs(first & 0xffu) - 1);
+    } else if (ns >= 1 && ns <= TC_CAND) {
       cnt[row * ksplit] = ns;
       multi_rows[atomicAdd(counters + 1, 1)] = static_cast<int>(row);
-    } else {
+    } else {                                           // overflow / nothing admitted / non-finite
       const int pos = atomicAdd(counters + 0, 1);
       fb_rows[pos] = static_cast<int>(row);
       fb_packed[row] = ~0ull;
@@ -409,8 +433,9 @@ prune_kernel(int64_t n, int ksplit, const float* __restrict__ margin, uint2* __r
   }
 }
 
-// Stage 2, one WARP per queued row: score the survivors exactly (fp64 accumulation of the fp32 -- or
-// bf16-rounded -- inputs); ascending code order + strict '>' keeps the lowest index on exact ties.
+// Stage 2, one WARP per queued row: score every admitted code of the surviving records exactly (fp64
+// accumulation of the fp32 -- or bf16-rounded -- inputs); ascending code order + strict '>' keeps the
+// lowest index on exact ties.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 exact_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, const float* __restrict__ E,
@@ -424,35 +449,40 @@ exact_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, 
   for (int64_t i = warp; i < n_multi; i += nwarps) {
     const int64_t row = multi_rows[i];
     const int ns = cnt[row * ksplit];
-    const uint32_t my_code = lane < ns ? cand[row * ksplit * TC_CAND + lane].x : 0u;
+    const uint32_t my_rec = lane < ns ? cand[row * ksplit * TC_SLOTS + lane].x : 0u;
     double top = -1e300;
     uint32_t top_idx = 0xffffffffu;
     for (int j = 0; j < ns; ++j) {
-      const uint32_t code = __shfl_sync(0xffffffffu, my_code, j);
-      double dot = 0.0, ee = 0.0;
-      for (int d = lane * 4; d < D; d += 128) {
-        float zv[4], ev[4];
-        if (BF16) {
-          const uint2 a = *reinterpret_cast<const uint2*>(zb + row * D + d);
-          const uint2 b = *reinterpret_cast<const uint2*>(Eb + static_cast<int64_t>(code) * D + d);
-          zv[0] = __uint_as_float(a.x << 16); zv[1] = __uint_as_float(a.x & 0xffff0000u);
-          zv[2] = __uint_as_float(a.y << 16); zv[3] = __uint_as_float(a.y & 0xffff0000u);
-          ev[0] = __uint_as_float(b.x << 16); ev[1] = __uint_as_float(b.x & 0xffff0000u);
-          ev[2] = __uint_as_float(b.y << 16); ev[3] = __uint_as_float(b.y & 0xffff0000u);
-        } else {
-          *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + row * D + d);
-          *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + d));
-        }
+      const uint32_t rec = __shfl_sync(0xffffffffu, my_rec, j);
+      uint32_t mk = rec & 0xffu;
+      while (mk) {
+        const uint32_t code = ((rec >> 8) << 3) + (__ffs(mk) - 1);
+        mk &= mk - 1;
+        double dot = 0.0, ee = 0.0;
+        for (int d = lane * 4; d < D; d += 128) {
+          float zv[4], ev[4];
+          if (BF16) {
+            const uint2 a = *reinterpret_cast<const uint2*>(zb + row * D + d);
+            const uint2 b = *reinterpret_cast<const uint2*>(Eb + static_cast<int64_t>(code) * D + d);
+            zv[0] = __uint_as_float(a.x << 16); zv[1] = __uint_as_float(a.x & 0xffff0000u);
+            zv[2] = __uint_as_float(a.y << 16); zv[3] = __uint_as_float(a.y & 0xffff0000u);
+            ev[0] = __uint_as_float(b.x << 16); ev[1] = __uint_as_float(b.x & 0xffff0000u);
+            ev[2] = __uint_as_float(b.y << 16); ev[3] = __uint_as_float(b.y & 0xffff0000u);
+          } else {
+            *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + row * D + d);
+            *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + d));
+          }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
-          ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+          for (int q = 0; q < 4; ++q) {
+            dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
+            ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+          }
         }
+        dot = warp_sum(dot);
+        ee = warp_sum(ee);
+        const double sc = dot - 0.5 * ee;
+        if (sc > top) { top = sc; top_idx = code; }
       }
-      dot = warp_sum(dot);
-      ee = warp_sum(ee);
-      const double sc = dot - 0.5 * ee;
-      if (sc > top) { top = sc; top_idx = code; }
     }
     if (lane == 0) idx_out[row] = idx_offset + top_idx;
   }
@@ -565,7 +595,7 @@ size_t tc_workspace_bytes(int64_t N, int K, int D) {
   b += align_up(static_cast<size_t>(rows) * D * 2, 256);            // zb
   b += align_up(static_cast<size_t>(rows) * 4, 256);                // margin
   b += align_up(slots * 4, 256) * 2;                                // cnt, best
-  b += align_up(slots * TC_CAND * 8, 256);                          // cand
+  b += align_up(slots * TC_SLOTS * 8, 256);                         // cand
   b += align_up(static_cast<size_t>(rows) * 4, 256) * 2;            // fb_rows, multi_rows
   b += align_up(static_cast<size_t>(rows) * 8, 256);                // fb_packed
   return b;
@@ -595,7 +625,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   float* margin = reinterpret_cast<float*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
   int* cnt = reinterpret_cast<int*>(w); w += align_up(slots * 4, 256);
   float* best = reinterpret_cast<float*>(w); w += align_up(slots * 4, 256);
-  uint2* cand = reinterpret_cast<uint2*>(w); w += align_up(slots * TC_CAND * 8, 256);
+  uint2* cand = reinterpret_cast<uint2*>(w); w += align_up(slots * TC_SLOTS * 8, 256);
   int* fb_rows = reinterpret_cast<int*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
   int* multi_rows = reinterpret_cast<int*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
   uint64_t* fb_packed = reinterpret_cast<uint64_t*>(w);
