@@ -69,6 +69,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -83,11 +88,13 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, 128-byte swizzle, 8-row atoms 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
-  return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(1) << 16) |
-         (static_cast<uint64_t>(1024 >> 4) << 32) | (static_cast<uint64_t>(1) << 46) |
-         (static_cast<uint64_t>(2) << 61);
+// K-major, 128-byte swizzle, 8-row atoms 1024 bytes apart (cute::UMMA::SmemDescriptor, version 1).
+// The high word is constant; the low word is (address >> 4) | LBO, so stepping through a tile is ONE add
+// on the low word (shared memory addresses stay below 2^18, the 14-bit field cannot carry).
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo) {
+  return (static_cast<uint64_t>(kDescHi) << 32) | lo;
 }
 // kind::f16, A = B = bf16, D = fp32, both K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
@@ -198,20 +205,23 @@ __device__ __forceinline__ void epi_scan(const uint32_t (&v)[32], const float* _
   }
 }
 
+constexpr int TC_CS = 2;            // epilogue column split: two warps share a row quarter, 64 columns each
+
 template <int BM>
-__global__ void __launch_bounds__(64 + BM, 1)
+__global__ void __launch_bounds__(64 + BM * TC_CS, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
                  const TcParams p) {
   constexpr int NHALF = BM / 128;
-  constexpr int NEPI = BM / 32;
+  constexpr int NEPI = (BM / 32) * TC_CS;
+  constexpr int WCOLS = TC_BN / TC_CS;           // columns one epilogue warp scans per tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int KBLK = p.D / TC_KB;
   const uint32_t z_bytes = static_cast<uint32_t>(BM) * p.D * 2;
   const uint32_t z_smem = base;                                    // zbufs x KBLK slabs of [BM rows x 128 B]
   const uint32_t e_smem = z_smem + p.zbufs * z_bytes;              // ring of [128 codes x 128 B]
-  const uint32_t ee_smem = e_smem + static_cast<uint32_t>(p.stages) * TC_STAGE_BYTES;   // [NEPI][2][128] fp32
-  const uint32_t bar0 = ee_smem + NEPI * 2 * TC_BN * 4;
+  const uint32_t ee_smem = e_smem + static_cast<uint32_t>(p.stages) * TC_STAGE_BYTES;   // [NEPI][2][WCOLS] fp32
+  const uint32_t bar0 = ee_smem + NEPI * 2 * WCOLS * 4;
   // barrier map (8 bytes each)
   const uint32_t bar_full = bar0;                         // [stages]
   const uint32_t bar_empty = bar0 + 8 * 8;                // [stages]
@@ -245,70 +255,82 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
-        const int t0 = ks * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
-        const uint32_t zb = p.zbufs == 2 ? (it & 1) : 0;
-        const uint32_t zuse = p.zbufs == 2 ? (it >> 1) : it;
-        mbar_wait(bar_zempty + 8 * zb, (zuse & 1) ^ 1);
+    // The whole warp walks the loop (warp-uniform control flow keeps addresses in uniform registers);
+    // one elected lane issues the copies.
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
+      const int t0 = ks * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
+      const uint32_t zb = p.zbufs == 2 ? (it & 1) : 0;
+      const uint32_t zuse = p.zbufs == 2 ? (it >> 1) : it;
+      mbar_wait(bar_zempty + 8 * zb, (zuse & 1) ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(bar_zfull + 8 * zb, z_bytes);
         for (int kb = 0; kb < KBLK; ++kb)
           tma_load_2d(z_smem + zb * z_bytes + kb * (BM * 128), &tmap_z, bar_zfull + 8 * zb, kb * TC_KB, rt * BM);
-        for (int t = t0; t < t1; ++t) {
-          for (int kb = 0; kb < KBLK; ++kb) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+      }
+      __syncwarp();
+      for (int t = t0; t < t1; ++t) {
+        for (int kb = 0; kb < KBLK; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
             tma_load_2d(e_smem + stage * TC_STAGE_BYTES, &tmap_e, bar_full + 8 * stage, kb * TC_KB, t * TC_BN);
-            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, it = 0, tg = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
-        const int t0 = ks * p.tiles_per_split;
-        const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
-        const uint32_t zb = p.zbufs == 2 ? (it & 1) : 0;
-        const uint32_t zuse = p.zbufs == 2 ? (it >> 1) : it;
-        mbar_wait(bar_zfull + 8 * zb, zuse & 1);
-        for (int t = t0; t < t1; ++t, ++tg) {
-          const uint32_t b = tg & 1;
-          mbar_wait(bar_tempty + 8 * b, ((tg >> 1) & 1) ^ 1);
+    // Warp-uniform loop, one elected lane issues.  Descriptors advance by adds on the low word only.
+    uint32_t stage = 0, phase = 0, it = 0, tg = 0;
+    const uint32_t z_lo = umma_desc_lo(z_smem), e_lo = umma_desc_lo(e_smem);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
+      const int t0 = ks * p.tiles_per_split;
+      const int t1 = min(t0 + p.tiles_per_split, p.code_tiles);
+      const uint32_t zb = p.zbufs == 2 ? (it & 1) : 0;
+      const uint32_t zuse = p.zbufs == 2 ? (it >> 1) : it;
+      (void)rt;
+      mbar_wait(bar_zfull + 8 * zb, zuse & 1);
+      for (int t = t0; t < t1; ++t, ++tg) {
+        const uint32_t b = tg & 1;
+        mbar_wait(bar_tempty + 8 * b, ((tg >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < KBLK; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          for (int kb = 0; kb < KBLK; ++kb) {
-            mbar_wait(bar_full + 8 * stage, phase);
-            tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a0 = z_lo + ((zb * z_bytes + kb * (BM * 128)) >> 4);
+            const uint32_t b0 = e_lo + ((stage * TC_STAGE_BYTES) >> 4);
 #pragma unroll
             for (int h = 0; h < NHALF; ++h) {
               const uint32_t d_tmem = tmem_base + b * (NHALF * TC_BN) + h * TC_BN;
 #pragma unroll
-              for (int k = 0; k < TC_KB / 16; ++k) {
-                const uint64_t ad = umma_desc(z_smem + zb * z_bytes + kb * (BM * 128) + h * (128 * 128) + k * 32);
-                const uint64_t bd = umma_desc(e_smem + stage * TC_STAGE_BYTES + k * 32);
-                tc_mma_bf16(d_tmem, ad, bd, kIdesc, (kb | k) ? 1u : 0u);
-              }
+              for (int k = 0; k < TC_KB / 16; ++k)
+                tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), kIdesc,
+                            (kb | k) ? 1u : 0u);
             }
             tc_commit(bar_empty + 8 * stage);          // frees the smem stage when these MMAs retire
-            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+            if (kb == KBLK - 1) tc_commit(bar_tfull + 8 * b);   // accumulator tile complete
           }
-          tc_commit(bar_tfull + 8 * b);                // accumulator tile complete
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         }
-        tc_commit(bar_zempty + 8 * zb);                // z tile may be overwritten
       }
+      if (elect_one()) tc_commit(bar_zempty + 8 * zb);  // z tile may be overwritten
+      __syncwarp();
     }
   } else {
     // ============================== epilogue ==============================
     const int we = warp - 2;                           // 0 .. NEPI-1
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
-    const int half = we >> 2;
-    float* ee_mine = reinterpret_cast<float*>(gen + (ee_smem - base)) + we * 2 * TC_BN;
+    const int half = (we >> 2) % NHALF;                // which 128-row accumulator
+    const int cs = (we >> 2) / NHALF;                  // which column slice of the tile
+    float* ee_mine = reinterpret_cast<float*>(gen + (ee_smem - base)) + we * 2 * WCOLS;
     uint32_t tg = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
@@ -317,59 +339,50 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
       const int64_t row = static_cast<int64_t>(rt) * BM + half * 128 + quarter * 32 + lane;
       const bool row_ok = row < p.n_rows;
       const float margin = row_ok ? p.margin[row] : __int_as_float(0x7fc00000);
-      uint2* cand_row = p.cand + (row_ok ? (row * p.ksplit + ks) : 0) * TC_SLOTS;   // rows past the end share row 0's scratch... never admitted
+      const int64_t sub = row_ok ? (row * p.ksplit + ks) * TC_CS + cs : 0;   // this warp's candidate sub-list
+      uint2* cand_row = p.cand + sub * TC_SLOTS;   // rows past the end share row 0's scratch... never admitted
       float best = __int_as_float(0xff800000);
       float thr = margin == margin ? best : margin;     // admission threshold best - margin (NaN: never admits)
       int cnt = 0;
 
-      float4 ee_next;
+      const float kInf = __int_as_float(0x7f800000);
+      float2 ee_next;
       {
-        const int c = t0 * TC_BN + lane * 4;
-        ee_next.x = c + 0 < p.K ? p.ee_half[c + 0] : __int_as_float(0x7f800000);
-        ee_next.y = c + 1 < p.K ? p.ee_half[c + 1] : __int_as_float(0x7f800000);
-        ee_next.z = c + 2 < p.K ? p.ee_half[c + 2] : __int_as_float(0x7f800000);
-        ee_next.w = c + 3 < p.K ? p.ee_half[c + 3] : __int_as_float(0x7f800000);
+        const int c = t0 * TC_BN + cs * WCOLS + lane * 2;
+        ee_next.x = c + 0 < p.K ? p.ee_half[c + 0] : kInf;
+        ee_next.y = c + 1 < p.K ? p.ee_half[c + 1] : kInf;
       }
       for (int t = t0; t < t1; ++t, ++tg) {
         const uint32_t b = tg & 1;
-        float* ee = ee_mine + b * TC_BN;
+        float* ee = ee_mine + b * WCOLS;
         __syncwarp();
-        reinterpret_cast<float4*>(ee)[lane] = ee_next;
+        reinterpret_cast<float2*>(ee)[lane] = ee_next;
         __syncwarp();
         if (t + 1 < t1) {
-          const int c = (t + 1) * TC_BN + lane * 4;
-          ee_next.x = c + 0 < p.K ? p.ee_half[c + 0] : __int_as_float(0x7f800000);
-          ee_next.y = c + 1 < p.K ? p.ee_half[c + 1] : __int_as_float(0x7f800000);
-          ee_next.z = c + 2 < p.K ? p.ee_half[c + 2] : __int_as_float(0x7f800000);
-          ee_next.w = c + 3 < p.K ? p.ee_half[c + 3] : __int_as_float(0x7f800000);
+          const int c = (t + 1) * TC_BN + cs * WCOLS + lane * 2;
+          ee_next.x = c + 0 < p.K ? p.ee_half[c + 0] : kInf;
+          ee_next.y = c + 1 < p.K ? p.ee_half[c + 1] : kInf;
         }
         mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * (NHALF * TC_BN) +
-                               half * TC_BN;
-        // Two register buffers: the TMEM load of chunk c+1 is in flight while chunk c is scanned, and the
-        // accumulator buffer is handed back to the MMA warp as soon as its last chunk sits in registers.
+                               half * TC_BN + cs * WCOLS;
+        // Both 32-column chunks of this warp's slice are pulled into registers, then the accumulator
+        // buffer is handed back to the MMA warp before the scan starts.
         uint32_t va[32], vb[32];
-        const uint32_t code_t = static_cast<uint32_t>(t * TC_BN);
+        const uint32_t code_t = static_cast<uint32_t>(t * TC_BN + cs * WCOLS);
         TC_LD32(taddr, va);
-        tc_wait_ld();
         TC_LD32(taddr + 32, vb);
-        epi_scan(va, ee, code_t, margin, best, thr, cnt, cand_row);
-        tc_wait_ld();
-        TC_LD32(taddr + 64, va);
-        epi_scan(vb, ee + 32, code_t + 32, margin, best, thr, cnt, cand_row);
-        tc_wait_ld();
-        TC_LD32(taddr + 96, vb);
-        epi_scan(va, ee + 64, code_t + 64, margin, best, thr, cnt, cand_row);
         tc_wait_ld();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
-        epi_scan(vb, ee + 96, code_t + 96, margin, best, thr, cnt, cand_row);
+        epi_scan(va, ee, code_t, margin, best, thr, cnt, cand_row);
+        epi_scan(vb, ee + 32, code_t + 32, margin, best, thr, cnt, cand_row);
       }
       if (row_ok) {
-        p.cnt[row * p.ksplit + ks] = cnt;
-        p.best[row * p.ksplit + ks] = best;
+        p.cnt[sub] = cnt;
+        p.best[sub] = best;
       }
     }
   }
@@ -481,7 +494,7 @@ exact_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, 
         dot = warp_sum(dot);
         ee = warp_sum(ee);
         const double sc = dot - 0.5 * ee;
-        if (sc > top) { top = sc; top_idx = code; }
+        if (sc > top || (sc == top && code < top_idx)) { top = sc; top_idx = code; }   // lowest index on exact ties
       }
     }
     if (lane == 0) idx_out[row] = idx_offset + top_idx;
@@ -535,10 +548,10 @@ struct TcPlan {
 static bool tc_plan(int64_t N, int K, int D, TcPlan* pl) {
   if (D % TC_KB != 0 || D < 64 || D > 512 || K < TC_BN || N < 64) return false;
   pl->BM = (D <= 256) ? 256 : 128;
-  const int nepi = pl->BM / 32;
+  const int nepi = (pl->BM / 32) * TC_CS;
   const int ztile = pl->BM * D * 2;
-  pl->zbufs = (2 * ztile + 4 * TC_STAGE_BYTES + nepi * 2 * TC_BN * 4 + 2048 <= TC_SMEM_LIMIT) ? 2 : 1;
-  const int fixed = 1024 + pl->zbufs * ztile + nepi * 2 * TC_BN * 4 + 256;
+  pl->zbufs = (2 * ztile + 4 * TC_STAGE_BYTES + nepi * 2 * (TC_BN / TC_CS) * 4 + 2048 <= TC_SMEM_LIMIT) ? 2 : 1;
+  const int fixed = 1024 + pl->zbufs * ztile + nepi * 2 * (TC_BN / TC_CS) * 4 + 256;
   int st = (TC_SMEM_LIMIT - fixed) / TC_STAGE_BYTES;
   if (st > 8) st = 8;
   if (st < 2) return false;
@@ -583,7 +596,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // (row, split) slots: code splits are only used while row_tiles * ksplit <= #SMs
 static size_t tc_slots(int64_t rows, int BM) {
   const size_t few = static_cast<size_t>(kNumSMs) * BM;
-  return static_cast<size_t>(rows) > few ? static_cast<size_t>(rows) : few;
+  return (static_cast<size_t>(rows) > few ? static_cast<size_t>(rows) : few) * TC_CS;   // x column slices
 }
 
 size_t tc_workspace_bytes(int64_t N, int K, int D) {
@@ -668,15 +681,15 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     const int items = p.row_tiles * p.ksplit;
     const int grid = items < kNumSMs ? items : kNumSMs;
     if (pl.BM == 256)
-      search_tc_kernel<256><<<grid, 64 + 256, pl.smem_bytes, s>>>(map_z, map_e, p);
+      search_tc_kernel<256><<<grid, 64 + 256 * TC_CS, pl.smem_bytes, s>>>(map_z, map_e, p);
     else
-      search_tc_kernel<128><<<grid, 64 + 128, pl.smem_bytes, s>>>(map_z, map_e, p);
+      search_tc_kernel<128><<<grid, 64 + 128 * TC_CS, pl.smem_bytes, s>>>(map_z, map_e, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
 
     blocks = (rows + 255) / 256;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    prune_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(rows, p.ksplit, margin, cand, cnt, best, idx_offset,
+    prune_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(rows, p.ksplit * TC_CS, margin, cand, cnt, best, idx_offset,
                                                               idx_out + r0, multi_rows, fb_rows, fb_packed, counters);
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
@@ -684,10 +697,10 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
     if (bf)
-      exact_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, D, p.ksplit, cand, cnt, multi_rows,
+      exact_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, D, p.ksplit * TC_CS, cand, cnt, multi_rows,
                                                                       counters, idx_offset, idx_out + r0);
     else
-      exact_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, D, p.ksplit, cand, cnt, multi_rows,
+      exact_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, D, p.ksplit * TC_CS, cand, cnt, multi_rows,
                                                                        counters, idx_offset, idx_out + r0);
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
