@@ -112,12 +112,19 @@ __device__ __forceinline__ void block_add_double(double v, double* dst) {
 
 constexpr int GATHER_ILP = 4;   // independent 128-bit items per thread kept in flight (HBM latency x bandwidth)
 
-template <bool ACC>
+constexpr int HIST_SMEM_BINS = 2048;   // small codebooks: all counts land on a few L2 lines, privatise per CTA
+
+template <bool ACC, bool SMEM_HIST>
 __global__ void __launch_bounds__(ROW_THREADS, 3)
 gather_kernel(const float4* __restrict__ z, const float4* __restrict__ E, const int64_t* __restrict__ idx,
               int64_t N, int D4, int d4_shift, int K_total, float4* zq_out, float4* __restrict__ zq_st_out,
               float4* __restrict__ residual_out, double* sqerr_sum, int32_t* __restrict__ hist,
               const uint8_t* __restrict__ row_mask) {
+  __shared__ int sh_hist[SMEM_HIST ? HIST_SMEM_BINS : 1];
+  if (SMEM_HIST) {
+    for (int k = threadIdx.x; k < K_total; k += blockDim.x) sh_hist[k] = 0;
+    __syncthreads();
+  }
   const int64_t total = N * D4;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   float err = 0.f;
@@ -167,7 +174,17 @@ gather_kernel(const float4* __restrict__ z, const float4* __restrict__ E, const 
         st_stream(residual_out + i, make_float4(-df.x, -df.y, -df.z, -df.w));
       err = fmaf(df.x, df.x, err); err = fmaf(df.y, df.y, err);
       err = fmaf(df.z, df.z, err); err = fmaf(df.w, df.w, err);
-      if (hist && c[u] == 0 && (!row_mask || row_mask[row[u]])) atomicAdd(hist + k[u], 1);
+      if (hist && c[u] == 0 && (!row_mask || row_mask[row[u]])) {
+        if (SMEM_HIST) atomicAdd(sh_hist + k[u], 1);
+        else atomicAdd(hist + k[u], 1);
+      }
+    }
+  }
+  if (SMEM_HIST) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < K_total; k += blockDim.x) {
+      const int v = sh_hist[k];
+      if (v) atomicAdd(hist + k, v);
     }
   }
   if (sqerr_sum) block_add_double(static_cast<double>(err), sqerr_sum);
@@ -188,14 +205,17 @@ int launch_gather(const float* z, const float* E, const int64_t* idx, int64_t N,
   if (blocks > cap) blocks = cap;
   auto Z = reinterpret_cast<const float4*>(z);
   auto Ev = reinterpret_cast<const float4*>(E);
-  if (zq_accumulate)
-    gather_kernel<true><<<static_cast<unsigned>(blocks), ROW_THREADS, 0, s>>>(
-        Z, Ev, idx, N, D4, shift, K_total, reinterpret_cast<float4*>(zq_out), reinterpret_cast<float4*>(zq_st_out),
-        reinterpret_cast<float4*>(residual_out), sqerr_sum, hist, row_mask);
-  else
-    gather_kernel<false><<<static_cast<unsigned>(blocks), ROW_THREADS, 0, s>>>(
-        Z, Ev, idx, N, D4, shift, K_total, reinterpret_cast<float4*>(zq_out), reinterpret_cast<float4*>(zq_st_out),
-        reinterpret_cast<float4*>(residual_out), sqerr_sum, hist, row_mask);
+  const bool sh = hist != nullptr && K_total <= HIST_SMEM_BINS;
+  if (sh && blocks > static_cast<int64_t>(kNumSMs) * 3) blocks = static_cast<int64_t>(kNumSMs) * 3;   // one wave: fewer flushes
+  const unsigned g = static_cast<unsigned>(blocks);
+  auto ZQ = reinterpret_cast<float4*>(zq_out);
+  auto ST = reinterpret_cast<float4*>(zq_st_out);
+  auto RS = reinterpret_cast<float4*>(residual_out);
+#define VQ_GATHER(ACC_, SH_) \
+  gather_kernel<ACC_, SH_><<<g, ROW_THREADS, 0, s>>>(Z, Ev, idx, N, D4, shift, K_total, ZQ, ST, RS, sqerr_sum, hist, row_mask)
+  if (zq_accumulate) { if (sh) VQ_GATHER(true, true); else VQ_GATHER(true, false); }
+  else { if (sh) VQ_GATHER(false, true); else VQ_GATHER(false, false); }
+#undef VQ_GATHER
   return status_of(cudaGetLastError());
 }
 

@@ -29,9 +29,10 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * BM;
   if (n_rows_dev) n_rows = *n_rows_dev;      // row-list length produced on the device (no host sync)
-  if (row0 >= n_rows) return;
+  // grid.x may be smaller than the number of row tiles (the hand-back path launches a bounded grid)
+  for (int64_t row0 = static_cast<int64_t>(blockIdx.x) * BM; row0 < n_rows; row0 += static_cast<int64_t>(gridDim.x) * BM) {
+  __syncthreads();
 
   // rows this thread stages into shared memory (2 float4 per tile step)
   const int ld_r = tid >> 2, ld_c = (tid & 3) * 4;
@@ -124,13 +125,17 @@ search_simt_kernel(const float* __restrict__ z, const int32_t* __restrict__ row_
       if (idx_out) idx_out[dst] = static_cast<int64_t>(best[i] & 0xffffffffull) + idx_offset;
     }
   }
+  }  // row-tile loop
 }
 
 static int launch_impl(const float* z, const int32_t* row_list, const int* n_rows_dev, int64_t n_rows, int D,
                        const float* E, const float* ee_half, int K, int codes_per_cta, int round_bf16,
                        int64_t idx_offset, int64_t* idx_out, uint64_t* packed_out, cudaStream_t s) {
   if (n_rows == 0) return VQB200_OK;
-  const int64_t blocks = (n_rows + BM - 1) / BM;
+  int64_t blocks = (n_rows + BM - 1) / BM;
+  // device-side row lists are short (hand-back rows): a bounded grid avoids scheduling thousands of CTAs
+  // that would exit at once; CTAs loop over row tiles.
+  if (n_rows_dev && blocks > 64) blocks = 64;
   if (blocks > 0x7fffffff) return VQB200_ESHAPE;
   dim3 grid(static_cast<unsigned>(blocks), codes_per_cta > 0 ? (K + codes_per_cta - 1) / codes_per_cta : 1);
   if (round_bf16)

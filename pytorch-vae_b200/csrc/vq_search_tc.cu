@@ -396,108 +396,106 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------ exact re-rank
-// Stage 1, one THREAD per row: prune the candidate records against the final maximum.  Exactly one
-// surviving code = certified by the error bound, written at once.  Several = compacted in place and
-// queued for stage 2.  Overflowed / empty / non-finite rows are queued for the exact SIMT kernel.
-__global__ void __launch_bounds__(256)
-prune_kernel(int64_t n, int ksplit, const float* __restrict__ margin, uint2* __restrict__ cand,
-             int* __restrict__ cnt, const float* __restrict__ best, int64_t idx_offset,
-             int64_t* __restrict__ idx_out, int* __restrict__ multi_rows, int* __restrict__ fb_rows,
-             uint64_t* __restrict__ fb_packed, int* __restrict__ counters) {
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < n; row += stride) {
-    float bmax = __int_as_float(0xff800000);
-    bool bad = false;
-    for (int ks = 0; ks < ksplit; ++ks) {
-      const int c = cnt[row * ksplit + ks];
-      bad |= (c <= 0 || c > TC_CAND);
-      bmax = fmaxf(bmax, best[row * ksplit + ks]);
-    }
-    const float mg = margin[row];
-    int ns = 0, ncodes = 0;
-    uint32_t first = 0;
-    if (!bad && mg == mg) {
-      const float thr = bmax - mg;
-      uint2* out = cand + row * ksplit * TC_SLOTS;     // survivors are compacted to the front of the row's slots
-      for (int ks = 0; ks < ksplit; ++ks) {
-        const int c = cnt[row * ksplit + ks];
-        const uint2* src = cand + (row * ksplit + ks) * TC_SLOTS;
-        for (int j = 0; j < c; ++j) {
-          const uint2 ent = src[j];
-          if (__uint_as_float(ent.y) >= thr) {         // the group's maximum is still within the margin
-            if (ns == 0) first = ent.x;
-            if (ns < TC_CAND) out[ns] = ent;           // out + ns <= src + j: never overtakes the read cursor
-            ++ns;
-            ncodes += __popc(ent.x & 0xffu);
-          }
-        }
-      }
-    }
-    if (ns == 1 && ncodes == 1) {
-      idx_out[row] = idx_offset + ((first >> 8) << 3) + (__ffs(first & 0xffu) - 1);
-    } else if (ns >= 1 && ns <= TC_CAND) {
-      cnt[row * ksplit] = ns;
-      multi_rows[atomicAdd(counters + 1, 1)] = static_cast<int>(row);
-    } else {                                           // overflow / nothing admitted / non-finite
-      const int pos = atomicAdd(counters + 0, 1);
-      fb_rows[pos] = static_cast<int>(row);
-      fb_packed[row] = ~0ull;
-    }
-  }
-}
-
-// Stage 2, one WARP per queued row: score every admitted code of the surviving records exactly (fp64
-// accumulation of the fp32 -- or bf16-rounded -- inputs); ascending code order + strict '>' keeps the
-// lowest index on exact ties.
+// One kernel, two granularities.  Each warp takes 32 rows: first every THREAD prunes its row's candidate
+// records against the final maximum (one surviving code = certified by the error bound, written at once;
+// overflow / nothing admitted / non-finite = queued for the exact SIMT kernel).  Rows with several
+// survivors are then scored one at a time by the whole WARP: fp64 accumulation of the fp32 (or
+// bf16-rounded) inputs, lowest index on exact ties.
 template <bool BF16>
 __global__ void __launch_bounds__(256)
-exact_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, const float* __restrict__ E,
-             const __nv_bfloat16* __restrict__ Eb, int D, int ksplit, const uint2* __restrict__ cand,
-             const int* __restrict__ cnt, const int* __restrict__ multi_rows, const int* __restrict__ counters,
-             int64_t idx_offset, int64_t* __restrict__ idx_out) {
+rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, const float* __restrict__ E,
+              const __nv_bfloat16* __restrict__ Eb, int64_t n, int D, int nsub, const float* __restrict__ margin,
+              uint2* __restrict__ cand, const int* __restrict__ cnt, const float* __restrict__ best,
+              int64_t idx_offset, int64_t* __restrict__ idx_out, int* __restrict__ fb_rows,
+              uint64_t* __restrict__ fb_packed, int* __restrict__ counters) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  const int n_multi = counters[1];
-  for (int64_t i = warp; i < n_multi; i += nwarps) {
-    const int64_t row = multi_rows[i];
-    const int ns = cnt[row * ksplit];
-    const uint32_t my_rec = lane < ns ? cand[row * ksplit * TC_SLOTS + lane].x : 0u;
-    double top = -1e300;
-    uint32_t top_idx = 0xffffffffu;
-    for (int j = 0; j < ns; ++j) {
-      const uint32_t rec = __shfl_sync(0xffffffffu, my_rec, j);
-      uint32_t mk = rec & 0xffu;
-      while (mk) {
-        const uint32_t code = ((rec >> 8) << 3) + (__ffs(mk) - 1);
-        mk &= mk - 1;
-        double dot = 0.0, ee = 0.0;
-        for (int d = lane * 4; d < D; d += 128) {
-          float zv[4], ev[4];
-          if (BF16) {
-            const uint2 a = *reinterpret_cast<const uint2*>(zb + row * D + d);
-            const uint2 b = *reinterpret_cast<const uint2*>(Eb + static_cast<int64_t>(code) * D + d);
-            zv[0] = __uint_as_float(a.x << 16); zv[1] = __uint_as_float(a.x & 0xffff0000u);
-            zv[2] = __uint_as_float(a.y << 16); zv[3] = __uint_as_float(a.y & 0xffff0000u);
-            ev[0] = __uint_as_float(b.x << 16); ev[1] = __uint_as_float(b.x & 0xffff0000u);
-            ev[2] = __uint_as_float(b.y << 16); ev[3] = __uint_as_float(b.y & 0xffff0000u);
-          } else {
-            *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + row * D + d);
-            *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + d));
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
-            ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+  for (int64_t base = warp * 32; base < n; base += nwarps * 32) {
+    const int64_t row = base + lane;
+    int ns = 0, ncodes = 0;
+    uint32_t first = 0;
+    bool fallback = false;
+    if (row < n) {
+      float bmax = __int_as_float(0xff800000);
+      bool bad = false;
+      for (int sb = 0; sb < nsub; ++sb) {
+        const int c = cnt[row * nsub + sb];
+        bad |= (c <= 0 || c > TC_CAND);
+        bmax = fmaxf(bmax, best[row * nsub + sb]);
+      }
+      const float mg = margin[row];
+      if (!bad && mg == mg) {
+        const float thr = bmax - mg;
+        uint2* out = cand + row * nsub * TC_SLOTS;     // survivors are compacted to the front of the row's slots
+        for (int sb = 0; sb < nsub; ++sb) {
+          const int c = cnt[row * nsub + sb];
+          const uint2* src = cand + (row * nsub + sb) * TC_SLOTS;
+          for (int j = 0; j < c; ++j) {
+            const uint2 ent = src[j];
+            if (__uint_as_float(ent.y) >= thr) {       // the group's maximum is still within the margin
+              if (ns == 0) first = ent.x;
+              if (ns < TC_CAND) out[ns] = ent;         // out + ns <= src + j: never overtakes the read cursor
+              ++ns;
+              ncodes += __popc(ent.x & 0xffu);
+            }
           }
         }
-        dot = warp_sum(dot);
-        ee = warp_sum(ee);
-        const double sc = dot - 0.5 * ee;
-        if (sc > top || (sc == top && code < top_idx)) { top = sc; top_idx = code; }   // lowest index on exact ties
+      }
+      if (ns == 1 && ncodes == 1) {
+        idx_out[row] = idx_offset + ((first >> 8) << 3) + (__ffs(first & 0xffu) - 1);
+      } else if (ns < 1 || ns > TC_CAND) {
+        fallback = true;
+        const int pos = atomicAdd(counters + 0, 1);
+        fb_rows[pos] = static_cast<int>(row);
+        fb_packed[row] = ~0ull;
       }
     }
-    if (lane == 0) idx_out[row] = idx_offset + top_idx;
+    const bool multi = row < n && !fallback && !(ns == 1 && ncodes == 1);
+    __syncwarp();                                      // compacted records become visible to the whole warp
+    unsigned todo = __ballot_sync(0xffffffffu, multi);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t r = base + src;
+      const int ns_r = __shfl_sync(0xffffffffu, ns, src);
+      const uint32_t my_rec = lane < ns_r ? cand[r * nsub * TC_SLOTS + lane].x : 0u;
+      double top = -1e300;
+      uint32_t top_idx = 0xffffffffu;
+      for (int j = 0; j < ns_r; ++j) {
+        const uint32_t rec = __shfl_sync(0xffffffffu, my_rec, j);
+        uint32_t mk = rec & 0xffu;
+        while (mk) {
+          const uint32_t code = ((rec >> 8) << 3) + (__ffs(mk) - 1);
+          mk &= mk - 1;
+          double dot = 0.0, ee = 0.0;
+          for (int d = lane * 4; d < D; d += 128) {
+            float zv[4], ev[4];
+            if (BF16) {
+              const uint2 a = *reinterpret_cast<const uint2*>(zb + r * D + d);
+              const uint2 b = *reinterpret_cast<const uint2*>(Eb + static_cast<int64_t>(code) * D + d);
+              zv[0] = __uint_as_float(a.x << 16); zv[1] = __uint_as_float(a.x & 0xffff0000u);
+              zv[2] = __uint_as_float(a.y << 16); zv[3] = __uint_as_float(a.y & 0xffff0000u);
+              ev[0] = __uint_as_float(b.x << 16); ev[1] = __uint_as_float(b.x & 0xffff0000u);
+              ev[2] = __uint_as_float(b.y << 16); ev[3] = __uint_as_float(b.y & 0xffff0000u);
+            } else {
+              *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + r * D + d);
+              *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + d));
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
+              ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+            }
+          }
+          dot = warp_sum(dot);
+          ee = warp_sum(ee);
+          const double sc = dot - 0.5 * ee;
+          if (sc > top || (sc == top && code < top_idx)) { top = sc; top_idx = code; }   // lowest index on exact ties
+        }
+      }
+      if (lane == 0) idx_out[r] = idx_offset + top_idx;
+    }
   }
 }
 
@@ -609,7 +607,7 @@ size_t tc_workspace_bytes(int64_t N, int K, int D) {
   b += align_up(static_cast<size_t>(rows) * 4, 256);                // margin
   b += align_up(slots * 4, 256) * 2;                                // cnt, best
   b += align_up(slots * TC_SLOTS * 8, 256);                         // cand
-  b += align_up(static_cast<size_t>(rows) * 4, 256) * 2;            // fb_rows, multi_rows
+  b += align_up(static_cast<size_t>(rows) * 4, 256);                // fb_rows
   b += align_up(static_cast<size_t>(rows) * 8, 256);                // fb_packed
   return b;
 }
@@ -618,7 +616,7 @@ int tc_launches(int64_t N, int K, int D) {
   TcPlan pl;
   if (!tc_plan(N, K, D, &pl)) return 0;
   const int64_t chunks = (N + pl.chunk_rows - 1) / pl.chunk_rows;
-  return static_cast<int>(chunks) * 6;   // zprep, tcgen05 search, prune, exact, SIMT hand-back, unpack
+  return static_cast<int>(chunks) * 5;   // zprep, tcgen05 search, re-rank, SIMT hand-back, unpack
 }
 
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
@@ -633,14 +631,13 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   const size_t slots = tc_slots(cap, pl.BM);
 
   uint8_t* w = static_cast<uint8_t*>(workspace);
-  int* counters = reinterpret_cast<int*>(w); w += 256;   // [0] rows handed to the SIMT kernel, [1] multi-survivor rows
+  int* counters = reinterpret_cast<int*>(w); w += 256;   // [0] rows handed to the SIMT kernel
   __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(w); w += align_up(static_cast<size_t>(cap) * D * 2, 256);
   float* margin = reinterpret_cast<float*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
   int* cnt = reinterpret_cast<int*>(w); w += align_up(slots * 4, 256);
   float* best = reinterpret_cast<float*>(w); w += align_up(slots * 4, 256);
   uint2* cand = reinterpret_cast<uint2*>(w); w += align_up(slots * TC_SLOTS * 8, 256);
   int* fb_rows = reinterpret_cast<int*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
-  int* multi_rows = reinterpret_cast<int*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
   uint64_t* fb_packed = reinterpret_cast<uint64_t*>(w);
 
   CUtensorMap map_e;
@@ -687,21 +684,17 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
 
-    blocks = (rows + 255) / 256;
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    prune_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(rows, p.ksplit * TC_CS, margin, cand, cnt, best, idx_offset,
-                                                              idx_out + r0, multi_rows, fb_rows, fb_packed, counters);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return status_of(e);
-    blocks = (rows + 7) / 8;                           // one warp per queued row; surplus warps exit at once
+    blocks = (rows + 255) / 256;                       // one warp per 32 rows
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
     if (bf)
-      exact_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, D, p.ksplit * TC_CS, cand, cnt, multi_rows,
-                                                                      counters, idx_offset, idx_out + r0);
+      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit * TC_CS, margin,
+                                                                       cand, cnt, best, idx_offset, idx_out + r0, fb_rows,
+                                                                       fb_packed, counters);
     else
-      exact_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, D, p.ksplit * TC_CS, cand, cnt, multi_rows,
-                                                                       counters, idx_offset, idx_out + r0);
+      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit * TC_CS, margin,
+                                                                        cand, cnt, best, idx_offset, idx_out + r0, fb_rows,
+                                                                        fb_packed, counters);
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
     // rows handed back (overflow / non-finite): exact SIMT scan over the device-side row list, K split over CTAs
