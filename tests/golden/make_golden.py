@@ -19,7 +19,7 @@ import torch
 
 sys.path.insert(0, "/root/reference")
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from models.vq_vae import VectorQuantizerEMA  # noqa: E402  (the oracle's authority)
+from models.vq_vae import VQVAE, VectorQuantizerEMA  # noqa: E402  (the oracle's authority)
 from synth import large_case_inputs, rs_inputs  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "vq_golden.npz")
@@ -191,8 +191,41 @@ def case_survey_kat(name, seed, K_per, D, L, B, M):
     print(name, sha(q.embedding), sha(z), sha(idx), int(idx.sum()), float(stats[0]), float(stats[1]))
 
 
+VQVAE_CFG = dict(input_dim=6, hidden_dim=32, num_layers=1, num_heads=2, max_seq_len=40, codebook_size=32, code_dim=16,
+                 beta=0.25, use_vq=True, num_quantizers=2, label_smoothing=0.01, ss_tv_lambda=0.002, xyz_align_alpha=0.0,
+                 latent_tokens=8, tokenizer_heads=2, tokenizer_layers=1, tokenizer_dropout=0.1, reinit_dead_codes=True,
+                 print_init=False, name="tiny")
+
+
+def case_vqvae():
+    """Whole-model call contract on a tiny configuration, eval mode, CPU."""
+    torch.manual_seed(77)
+    m = VQVAE(**VQVAE_CFG).eval()
+    rs = np.random.RandomState(78)
+    B, L = 3, 24
+    x = np.zeros((B, L, 6), dtype=np.float32)
+    x[..., :3] = rs.standard_normal((B, L, 3))
+    x[np.arange(B)[:, None], np.arange(L)[None, :], 3 + rs.randint(0, 3, (B, L))] = 1.0
+    mask = np.ones((B, L), dtype=bool)
+    mask[1, 17:] = False
+    mask[2, 9:] = False
+    xt, mt = torch.from_numpy(x), torch.from_numpy(mask)
+    with torch.no_grad():
+        recons, target, vq_pack, _ = m(xt, mt)
+        out = m.loss_function(recons, target, vq_pack, mt, ss_weight=0.7, rmsd_weight=1.3)
+    zq, ze, idx, ppl, dead = vq_pack
+    for k, v in m.state_dict().items():
+        G[f"vqvae/sd/{k}"] = v.detach().cpu().numpy().copy()
+    put("vqvae", x=x, mask=mask, recons=recons, zq=zq, ze=ze, idx=idx, ppl=ppl, dead=dead)
+    for k in ("loss", "Reconstruction_Loss_XYZ", "XYZ_MSE_Raw", "Reconstruction_Loss_SS", "SS_Accuracy", "VQ_Loss",
+              "SS_TV", "VQ_Perplexity", "VQ_DeadRatio", "RMSD_Raw"):
+        G[f"vqvae/loss/{k}"] = np.asarray(float(out[k]))
+    G["vqvae/loss_keys"] = np.array(sorted(out.keys()))
+
+
 def main():
     torch.set_num_threads(8)
+    case_vqvae()
     case_small_single()
     case_small_rvq()
     case_semantics()
