@@ -233,36 +233,44 @@ def run_b200(args, w):
         e2e_ms = float(t)
     e2e_val = world * N / (e2e_ms / args.steps * 1e-3)
 
-    # ---- roofline of the dominant kernel (the fused distance+argmin search), timed alone with CUDA
-    # events on the stream it is launched on (torch's current stream)
-    cache = q._codebook_cache()
-    flat = z.view(-1, D)
-    idx_tmp = torch.empty(N, dtype=torch.int64, device=dev)
+    # ---- roofline of the dominant kernel: the library brackets every launch of the fused distance+argmin
+    # kernel (tcgen05 path; the SIMT kernel on shapes that take it) with CUDA events on the launching stream
+    # while full steps run, so the duration is the kernel's own, measured inside a live step.
+    import ctypes
+    lib = vq._cabi.lib
     mode = vq.quantizer._MODES[args.mode]
-    for _ in range(3):
-        vq.ops.search(flat, q.embedding, cache, 0, mode, idx_tmp)
+    lib.vqb200_timing_enable(1)
+    for _ in range(max(3, min(args.steps, 10))):
+        step()
     torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = max(3, args.steps)
-    k0.record()
-    for _ in range(reps):
-        vq.ops.search(flat, q.embedding, cache, 0, mode, idx_tmp)
-    k1.record()
-    torch.cuda.synchronize()
-    search_ms = k0.elapsed_time(k1) / reps
+    lib.vqb200_timing_enable(0)
+    tot, nl = ctypes.c_float(0), ctypes.c_int(0)
+    lib.vqb200_timing_collect(ctypes.byref(tot), ctypes.byref(nl))
+    n_steps_t = max(3, min(args.steps, 10))
+    launches_per_step = max(1, nl.value // n_steps_t)
+    kern_ms = tot.value / max(1, nl.value)                       # average duration of ONE launch
+    rows_per_launch = N * L / launches_per_step                  # rows one launch scans (chunks x levels per step)
     hbm, tf, peak_src = peaks()
-    flops = 2.0 * N * K * D
-    bytes_alg = N * (4.0 * D + 8.0)                      # read z (fp32), write idx (int64); codebook negligible
+    flops = 2.0 * rows_per_launch * K * D
+    bytes_alg = rows_per_launch * (4.0 * D + 8.0)                # SURVEY 8(d) codes-only: read z (fp32), write idx
     tensor_bound = flops / (tf * 1e12) > bytes_alg / (hbm * 1e9)
+    on_tc = bool(lib.vqb200_search_path(N, K, D, mode))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath)).get(args.workload if args.mode == "fp32" else "", None)
+        if t:                                                    # dram bytes of one launch from one ncu --set full capture
+            traffic = t["dram_bytes_per_row"] * rows_per_launch
     if tensor_bound:
-        ach = flops / (search_ms * 1e-3) / 1e12
+        ach = flops / (kern_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf}
     else:
-        ach = bytes_alg / (search_ms * 1e-3) / 1e9
+        ach = bytes_alg / (kern_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
-    roof.update({"traffic": None, "kernel": "vqb200_search (level 0)", "kernel_ms": search_ms,
-                 "kernel_share_of_step": search_ms * L / ms_step, "peak_source": peak_src,
-                 "path": "tcgen05" if vq._cabi.lib.vqb200_search_path(N, K, D, mode) else "simt-fp32"})
+    roof.update({"traffic": traffic, "kernel": "search_tc_kernel (tcgen05 distance+argmin)" if on_tc else "search_simt_kernel",
+                 "kernel_ms": kern_ms, "launches_per_step": launches_per_step, "rows_per_launch": rows_per_launch,
+                 "kernel_share_of_step": kern_ms * launches_per_step / ms_step, "peak_source": peak_src,
+                 "algorithmic_unit": "2*K*D flop per row" if tensor_bound else "4*D+8 bytes per row"})
 
     if rank == 0:
         cpu_rows = cpu_sample_rows(w)

@@ -82,6 +82,13 @@ VQB200_API int vqb200_search(const float* z, int64_t N, int D, const float* E, c
                   int mode, int64_t idx_offset, int64_t* idx_out, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Measurement hook (bench.py): while enabled, vqb200_search brackets every launch of its dominant kernel (the
+ * tcgen05 search kernel; the SIMT kernel on shapes that take the SIMT path) with CUDA events on the launching
+ * stream.  vqb200_timing_collect synchronises those events, returns their summed duration and launch count and
+ * clears the list.  Not thread-safe; off by default (no events are created). */
+VQB200_API int vqb200_timing_enable(int on);
+VQB200_API int vqb200_timing_collect(float* total_ms, int* n_launches);
+
 /* Gather + everything elementwise that follows it, in one pass over the rows.
  * Replaces F.embedding (:189,248), the straight-through expression (:199,263), the RVQ
  * residual update (:258) and level sum (:261), F.mse_loss partial sums (:1293) and

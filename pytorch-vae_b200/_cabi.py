@@ -29,6 +29,8 @@ _sz = C.c_size_t
 SIGNATURES = {
     "vqb200_abi_version": (_i, []),
     "vqb200_status_string": (C.c_char_p, [_i]),
+    "vqb200_timing_enable": (_i, [_i]),
+    "vqb200_timing_collect": (_i, [_p, _p]),
     "vqb200_search_path": (_i, [_i64, _i, _i, _i]),
     "vqb200_codebook_prepare": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "vqb200_search_workspace_bytes": (_sz, [_i64, _i, _i, _i]),

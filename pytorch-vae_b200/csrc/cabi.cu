@@ -1,7 +1,26 @@
 // extern "C" entry points of libvqb200.so: argument validation + dispatch.  See include/vq_b200.h.
 #include "common.cuh"
 
+#include <utility>
+#include <vector>
+
 using namespace vqb;
+
+namespace vqb {
+static bool g_timing = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+void timing_mark_begin(cudaStream_t s) {
+  if (!g_timing) return;
+  cudaEvent_t a, b;
+  if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+  g_events.emplace_back(a, b);
+  cudaEventRecord(a, s);
+}
+void timing_mark_end(cudaStream_t s) {
+  if (!g_timing || g_events.empty()) return;
+  cudaEventRecord(g_events.back().second, s);
+}
+}  // namespace vqb
 
 #define VQ_REQUIRE(cond, code) \
   do {                         \
@@ -24,6 +43,30 @@ const char* vqb200_status_string(int status) {
     case VQB200_EDRIVER: return "CUDA driver entry point / tensor-map failure";
     default: return status > 0 ? cudaGetErrorString(static_cast<cudaError_t>(status)) : "unknown status";
   }
+}
+
+int vqb200_timing_enable(int on) {
+  g_timing = on != 0;
+  return VQB200_OK;
+}
+
+int vqb200_timing_collect(float* total_ms, int* n_launches) {
+  VQ_REQUIRE(total_ms && n_launches, VQB200_EINVAL);
+  float total = 0.f;
+  int n = 0;
+  for (auto& ev : g_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.second) == cudaSuccess && cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) {
+      total += ms;
+      ++n;
+    }
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  g_events.clear();
+  *total_ms = total;
+  *n_launches = n;
+  return VQB200_OK;
 }
 
 int vqb200_search_path(int64_t N, int K, int D, int mode) {
@@ -71,8 +114,11 @@ int vqb200_search(const float* z, int64_t N, int D, const float* E, const uint16
     return launch_search_tc(z, N, D, E, E_bf16, ee_half, ee_half_bf16, level_meta, K, mode, idx_offset, idx_out,
                             workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
   }
-  return launch_search_simt(z, nullptr, N, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0, idx_offset, idx_out,
-                            nullptr, static_cast<cudaStream_t>(stream));
+  timing_mark_begin(static_cast<cudaStream_t>(stream));
+  const int st = launch_search_simt(z, nullptr, N, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0, idx_offset, idx_out,
+                                    nullptr, static_cast<cudaStream_t>(stream));
+  timing_mark_end(static_cast<cudaStream_t>(stream));
+  return st;
 }
 
 int vqb200_gather(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int K_total, float* zq_out,

@@ -62,6 +62,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // Internal launchers (defined in the .cu files, called from cabi.cu).
 namespace vqb {
+// measurement hook, see vqb200_timing_enable
+void timing_mark_begin(cudaStream_t s);
+void timing_mark_end(cudaStream_t s);
 int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, int D, const float* E,
                        const float* ee_half, int K, int round_bf16, int64_t idx_offset, int64_t* idx_out,
                        uint64_t* packed_out, cudaStream_t s);

@@ -677,10 +677,12 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     p.margin = margin; p.cand = cand; p.cnt = cnt; p.best = best;
     const int items = p.row_tiles * p.ksplit;
     const int grid = items < kNumSMs ? items : kNumSMs;
+    timing_mark_begin(s);
     if (pl.BM == 256)
       search_tc_kernel<256><<<grid, 64 + 256 * TC_CS, pl.smem_bytes, s>>>(map_z, map_e, p);
     else
       search_tc_kernel<128><<<grid, 64 + 128 * TC_CS, pl.smem_bytes, s>>>(map_z, map_e, p);
+    timing_mark_end(s);
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
 

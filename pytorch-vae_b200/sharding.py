@@ -40,8 +40,9 @@ def allreduce_stats(sqerr_sum: torch.Tensor, n_elems: int, hist: torch.Tensor, g
 
     Returns (global mean sq err as float64[1], global histogram as int32[K]).
     """
+    # torch.full is a device-side fill: no pageable host->device copy, hence no host sync on the step path
     pack = torch.cat([sqerr_sum.reshape(1).to(torch.float64),
-                      torch.tensor([float(n_elems)], dtype=torch.float64, device=hist.device),
+                      torch.full((1,), float(n_elems), dtype=torch.float64, device=hist.device),
                       hist.to(torch.float64)])
     dist.all_reduce(pack, op=dist.ReduceOp.SUM, group=group)
     mean = (pack[:1] / pack[1:2].clamp_min(1.0)).contiguous()
