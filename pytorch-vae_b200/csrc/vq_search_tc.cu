@@ -110,6 +110,13 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) <
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])    \
       : "r"(taddr)                                                                                                 \
       : "memory")
+#define TC_ST16(taddr, v)                                                                                          \
+  asm volatile(                                                                                                    \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};"     \
+      ::"r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),          \
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(taddr)               \
+      : "memory")
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------ z pre-pass
@@ -168,24 +175,18 @@ struct TcParams {
   float* best;           // [n_rows][ksplit]
 };
 
-// Scan 32 accumulator columns of one row.  Scores s = acc - |e|^2/2.  The whole chunk is skipped with ONE
-// compare unless its maximum reaches the admission threshold thr = best - margin (rare once the running
-// maximum has settled: ~ (1 + margin * best) / j per column j).  The slow path is straight-line,
-// predicated code (no per-element branches, no serial dependency): each group of 8 columns whose maximum
-// passes emits one record {group index << 8 | 8-bit admit mask, group max}.
-__device__ __forceinline__ void epi_scan(const uint32_t (&v)[32], const float* __restrict__ ee, uint32_t code0,
-                                         float margin, float& best, float& thr, int& cnt, uint2* cand_row) {
-  float s[32], gm[4];
+// Scan 32 accumulator columns of one row.  The accumulator was pre-loaded with -|e|^2/2, so the TMEM words ARE
+// the scores s = z.e - |e|^2/2: no shared-memory read and no subtract per column.  The whole chunk is skipped
+// with ONE compare unless its maximum reaches the admission threshold thr = best - margin (rare once the
+// running maximum has settled: ~ (1 + margin * best) / j per column j).  In the slow path each group of 8
+// columns whose maximum passes emits one record {group index << 8 | 8-bit admit mask, group max}.
+__device__ __forceinline__ void epi_scan(const uint32_t (&v)[32], uint32_t code0, float margin, float& best,
+                                         float& thr, int& cnt, uint2* cand_row) {
+  float gm[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float4 ea = *reinterpret_cast<const float4*>(ee + g * 8);
-    const float4 eb = *reinterpret_cast<const float4*>(ee + g * 8 + 4);
-    s[g * 8 + 0] = __uint_as_float(v[g * 8 + 0]) - ea.x; s[g * 8 + 1] = __uint_as_float(v[g * 8 + 1]) - ea.y;
-    s[g * 8 + 2] = __uint_as_float(v[g * 8 + 2]) - ea.z; s[g * 8 + 3] = __uint_as_float(v[g * 8 + 3]) - ea.w;
-    s[g * 8 + 4] = __uint_as_float(v[g * 8 + 4]) - eb.x; s[g * 8 + 5] = __uint_as_float(v[g * 8 + 5]) - eb.y;
-    s[g * 8 + 6] = __uint_as_float(v[g * 8 + 6]) - eb.z; s[g * 8 + 7] = __uint_as_float(v[g * 8 + 7]) - eb.w;
-    gm[g] = fmaxf(fmaxf(fmaxf(s[g * 8 + 0], s[g * 8 + 1]), fmaxf(s[g * 8 + 2], s[g * 8 + 3])),
-                  fmaxf(fmaxf(s[g * 8 + 4], s[g * 8 + 5]), fmaxf(s[g * 8 + 6], s[g * 8 + 7])));
+    const float* s = reinterpret_cast<const float*>(&v[g * 8]);
+    gm[g] = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), fmaxf(fmaxf(s[4], s[5]), fmaxf(s[6], s[7])));
   }
   const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
   if (cm >= thr) {
@@ -193,25 +194,27 @@ __device__ __forceinline__ void epi_scan(const uint32_t (&v)[32], const float* _
     thr = best - margin;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      uint32_t mk = 0;
+      if (gm[g] >= thr) {                              // ~1 of the 4 groups: the mask is built only where needed
+        uint32_t mk = 0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mk |= (s[g * 8 + i] >= thr) ? (1u << i) : 0u;
-      const bool hit = gm[g] >= thr;
-      // unconditional store: misses land in the row's scratch slot TC_CAND (keeps the path branch-free)
-      const int slot = (hit && cnt < TC_CAND) ? cnt : TC_CAND;
-      cand_row[slot] = make_uint2((((code0 >> 3) + g) << 8) | mk, __float_as_uint(gm[g]));
-      cnt += hit ? 1 : 0;
+        for (int i = 0; i < 8; ++i) mk |= (__uint_as_float(v[g * 8 + i]) >= thr) ? (1u << i) : 0u;
+        if (cnt < TC_CAND) cand_row[cnt] = make_uint2((((code0 >> 3) + g) << 8) | mk, __float_as_uint(gm[g]));
+        ++cnt;
+      }
     }
   }
 }
 
-constexpr int TC_CS = 2;            // epilogue column split: two warps share a row quarter, 64 columns each
+// Epilogue column split CS: CS warps share a row quarter and scan TC_BN/CS columns each.  BM=256 runs 8
+// epilogue warps (CS=1: a 10-warp CTA keeps the full register budget, no spills); BM=128 (D=512) runs CS=2.
+constexpr int tc_cs(int BM) { return BM == 128 ? 2 : 1; }
 
 template <int BM>
-__global__ void __launch_bounds__(64 + BM * TC_CS, 1)
+__global__ void __launch_bounds__(64 + BM * tc_cs(BM), 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
                  const TcParams p) {
   constexpr int NHALF = BM / 128;
+  constexpr int TC_CS = tc_cs(BM);
   constexpr int NEPI = (BM / 32) * TC_CS;
   constexpr int WCOLS = TC_BN / TC_CS;           // columns one epilogue warp scans per tile
   extern __shared__ uint8_t smem_raw[];
@@ -298,7 +301,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
       mbar_wait(bar_zfull + 8 * zb, zuse & 1);
       for (int t = t0; t < t1; ++t, ++tg) {
         const uint32_t b = tg & 1;
-        mbar_wait(bar_tempty + 8 * b, ((tg >> 1) & 1) ^ 1);
+        mbar_wait(bar_tempty + 8 * b, (tg >> 1) & 1);   // buffer drained AND pre-loaded with -|e|^2/2
         tc_fence_after();
         for (int kb = 0; kb < KBLK; ++kb) {
           mbar_wait(bar_full + 8 * stage, phase);
@@ -311,8 +314,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
               const uint32_t d_tmem = tmem_base + b * (NHALF * TC_BN) + h * TC_BN;
 #pragma unroll
               for (int k = 0; k < TC_KB / 16; ++k)
-                tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), kIdesc,
-                            (kb | k) ? 1u : 0u);
+                tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), kIdesc, 1u);
             }
             tc_commit(bar_empty + 8 * stage);          // frees the smem stage when these MMAs retire
             if (kb == KBLK - 1) tc_commit(bar_tfull + 8 * b);   // accumulator tile complete
@@ -330,7 +332,67 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may touch
     const int half = (we >> 2) % NHALF;                // which 128-row accumulator
     const int cs = (we >> 2) / NHALF;                  // which column slice of the tile
-    float* ee_mine = reinterpret_cast<float*>(gen + (ee_smem - base)) + we * 2 * WCOLS;
+    float* ee_slot = reinterpret_cast<float*>(gen + (ee_smem - base)) + we * 2 * WCOLS;   // [WCOLS] staging, per warp
+    const float kNegInf = __int_as_float(0xff800000);
+    const uint32_t tcol = (static_cast<uint32_t>(quarter * 32) << 16) + half * TC_BN + cs * WCOLS;
+
+    // -|e|^2/2 of this warp's column slice of code tile t: WCOLS/32 values per lane (padding codes get -inf)
+    constexpr int BPL = WCOLS / 32;
+    struct Bias { float v[BPL]; };
+    auto load_bias = [&](int t) -> Bias {
+      Bias r;
+#pragma unroll
+      for (int j = 0; j < BPL; ++j) {
+        const int c = t * TC_BN + cs * WCOLS + lane * BPL + j;
+        r.v[j] = (t >= 0 && c < p.K) ? -p.ee_half[c] : kNegInf;
+      }
+      return r;
+    };
+    // write the bias of one code tile into this warp's lanes/columns of accumulator buffer b
+    auto preload = [&](const Bias& bias, uint32_t b) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < BPL; ++j) ee_slot[lane * BPL + j] = bias.v[j];
+      __syncwarp();
+#pragma unroll
+      for (int hh = 0; hh < WCOLS / 16; ++hh) {          // 16 columns per store keeps register pressure low
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(ee_slot + hh * 16 + j);   // broadcast read
+          w[j + 0] = __float_as_uint(q4.x); w[j + 1] = __float_as_uint(q4.y);
+          w[j + 2] = __float_as_uint(q4.z); w[j + 3] = __float_as_uint(q4.w);
+        }
+        TC_ST16(tmem_base + tcol + b * (NHALF * TC_BN) + hh * 16, w);
+      }
+      tc_wait_st();
+    };
+    // walk the CTA's tile sequence two steps ahead of the tile being scanned (the next user of a buffer)
+    int la_item = blockIdx.x, la_t = 0, la_t1 = 0;
+    auto la_open = [&]() {
+      if (la_item < n_items) {
+        const int ks = la_item % p.ksplit;
+        la_t = ks * p.tiles_per_split;
+        la_t1 = min(la_t + p.tiles_per_split, p.code_tiles);
+      }
+    };
+    auto la_next = [&]() -> int {                       // code tile index of the next tile in sequence, -1 at the end
+      while (la_item < n_items && la_t >= la_t1) { la_item += gridDim.x; la_open(); }
+      if (la_item >= n_items) return -1;
+      return la_t++;
+    };
+    la_open();
+    // prologue: both buffers receive the bias of the first two tiles, then are handed to the MMA warp
+    for (uint32_t b = 0; b < 2; ++b) {
+      const int tt = la_next();
+      if (tt >= 0) preload(load_bias(tt), b);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+    }
+    int t_ahead = la_next();                            // tile that will reuse the buffer of the first scanned tile
+    Bias bias_next = load_bias(t_ahead);
+
     uint32_t tg = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int rt = item / p.ksplit, ks = item - rt * p.ksplit;
@@ -340,45 +402,37 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
       const bool row_ok = row < p.n_rows;
       const float margin = row_ok ? p.margin[row] : __int_as_float(0x7fc00000);
       const int64_t sub = row_ok ? (row * p.ksplit + ks) * TC_CS + cs : 0;   // this warp's candidate sub-list
-      uint2* cand_row = p.cand + sub * TC_SLOTS;   // rows past the end share row 0's scratch... never admitted
-      float best = __int_as_float(0xff800000);
+      uint2* cand_row = p.cand + sub * TC_SLOTS;
+      float best = kNegInf;
       float thr = margin == margin ? best : margin;     // admission threshold best - margin (NaN: never admits)
       int cnt = 0;
 
-      const float kInf = __int_as_float(0x7f800000);
-      float2 ee_next;
-      {
-        const int c = t0 * TC_BN + cs * WCOLS + lane * 2;
-        ee_next.x = c + 0 < p.K ? p.ee_half[c + 0] : kInf;
-        ee_next.y = c + 1 < p.K ? p.ee_half[c + 1] : kInf;
-      }
       for (int t = t0; t < t1; ++t, ++tg) {
         const uint32_t b = tg & 1;
-        float* ee = ee_mine + b * WCOLS;
-        __syncwarp();
-        reinterpret_cast<float2*>(ee)[lane] = ee_next;
-        __syncwarp();
-        if (t + 1 < t1) {
-          const int c = (t + 1) * TC_BN + cs * WCOLS + lane * 2;
-          ee_next.x = c + 0 < p.K ? p.ee_half[c + 0] : kInf;
-          ee_next.y = c + 1 < p.K ? p.ee_half[c + 1] : kInf;
-        }
+        const Bias bias = bias_next;                    // for tile t_ahead (fetched one iteration ago)
+        const int t_cur_ahead = t_ahead;
+        t_ahead = la_next();
+        bias_next = load_bias(t_ahead);                 // global loads in flight across the wait below
         mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * (NHALF * TC_BN) +
-                               half * TC_BN + cs * WCOLS;
-        // Both 32-column chunks of this warp's slice are pulled into registers, then the accumulator
-        // buffer is handed back to the MMA warp before the scan starts.
-        uint32_t va[32], vb[32];
+        const uint32_t taddr = tmem_base + tcol + b * (NHALF * TC_BN);
+        // One 32-column chunk in registers at a time (the 18-warp CTA is capped at 96 registers per thread).
+        // After the LAST chunk is out of TMEM the buffer is re-armed with the bias of its next tile and
+        // handed back to the MMA warp; only then is that chunk scanned.
+        uint32_t v[32];
         const uint32_t code_t = static_cast<uint32_t>(t * TC_BN + cs * WCOLS);
-        TC_LD32(taddr, va);
-        TC_LD32(taddr + 32, vb);
-        tc_wait_ld();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
-        epi_scan(va, ee, code_t, margin, best, thr, cnt, cand_row);
-        epi_scan(vb, ee + 32, code_t + 32, margin, best, thr, cnt, cand_row);
+#pragma unroll
+        for (int ch = 0; ch < WCOLS / 32; ++ch) {
+          TC_LD32(taddr + ch * 32, v);
+          tc_wait_ld();
+          if (ch == WCOLS / 32 - 1) {
+            if (t_cur_ahead >= 0) preload(bias, b);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+          }
+          epi_scan(v, code_t + ch * 32, margin, best, thr, cnt, cand_row);
+        }
       }
       if (row_ok) {
         p.cnt[sub] = cnt;
@@ -396,27 +450,43 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------ exact re-rank
-// One kernel, two granularities.  Each warp takes 32 rows: first every THREAD prunes its row's candidate
-// records against the final maximum (one surviving code = certified by the error bound, written at once;
-// overflow / nothing admitted / non-finite = queued for the exact SIMT kernel).  Rows with several
-// survivors are then scored one at a time by the whole WARP: fp64 accumulation of the fp32 (or
-// bf16-rounded) inputs, lowest index on exact ties.
+// One kernel, two granularities.  Each warp takes 32 rows.
+//  (1) every THREAD prunes its row's candidate records against the final maximum -- loads only, no
+//      stores, so they pipeline.  One surviving code = certified by the error bound, written at once;
+//      overflow / nothing admitted / non-finite = queued for the exact SIMT kernel.
+//  (2) rows with several survivors are scored by the whole WARP, one row at a time: the surviving codes are
+//      expanded into a small shared list, then 32/(D/4) codes are scored concurrently by lane groups
+//      (fp64 accumulation of the fp32 -- or bf16-rounded -- inputs); (score, index) is reduced
+//      lexicographically so the lowest index wins exact ties.
+constexpr int RR_LIST = 64;   // surviving codes per row handled in-kernel; more -> exact SIMT kernel
+
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, const float* __restrict__ E,
-              const __nv_bfloat16* __restrict__ Eb, int64_t n, int D, int nsub, const float* __restrict__ margin,
-              uint2* __restrict__ cand, const int* __restrict__ cnt, const float* __restrict__ best,
-              int64_t idx_offset, int64_t* __restrict__ idx_out, int* __restrict__ fb_rows,
-              uint64_t* __restrict__ fb_packed, int* __restrict__ counters) {
-  const int lane = threadIdx.x & 31;
+              const __nv_bfloat16* __restrict__ Eb, int64_t n, int D, int nsub, int rpw,
+              const float* __restrict__ margin, const uint2* __restrict__ cand, const int* __restrict__ cnt,
+              const float* __restrict__ best, int64_t idx_offset, int64_t* __restrict__ idx_out,
+              int* __restrict__ fb_rows, uint64_t* __restrict__ fb_packed, int* __restrict__ counters) {
+  // rpw = rows per warp step (32 for large n; fewer when n is small so that enough warps are in flight to
+  // hide the dependent-load latency of the prune / score chains)
+  __shared__ uint32_t s_list[8][RR_LIST];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t base = warp * 32; base < n; base += nwarps * 32) {
+  // lane groups for the exact scores: lpv lanes cover one row with float4 slices
+  int lpv = D >> 2;
+  if (lpv > 32) lpv = 32;
+  while (lpv & (lpv - 1)) lpv &= lpv - 1;               // largest power of two <= D/4 (D % 4 == 0)
+  const int groups = 32 / lpv, gl = lane % lpv, gi = lane / lpv;
+
+  for (int64_t base = warp * rpw; base < n; base += nwarps * rpw) {
     const int64_t row = base + lane;
+    const bool mine = lane < rpw && row < n;
     int ns = 0, ncodes = 0;
     uint32_t first = 0;
+    float thr = __int_as_float(0x7fc00000);
     bool fallback = false;
-    if (row < n) {
+    if (mine) {
       float bmax = __int_as_float(0xff800000);
       bool bad = false;
       for (int sb = 0; sb < nsub; ++sb) {
@@ -426,16 +496,15 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
       }
       const float mg = margin[row];
       if (!bad && mg == mg) {
-        const float thr = bmax - mg;
-        uint2* out = cand + row * nsub * TC_SLOTS;     // survivors are compacted to the front of the row's slots
+        thr = bmax - mg;
         for (int sb = 0; sb < nsub; ++sb) {
           const int c = cnt[row * nsub + sb];
           const uint2* src = cand + (row * nsub + sb) * TC_SLOTS;
+#pragma unroll 4
           for (int j = 0; j < c; ++j) {
             const uint2 ent = src[j];
             if (__uint_as_float(ent.y) >= thr) {       // the group's maximum is still within the margin
               if (ns == 0) first = ent.x;
-              if (ns < TC_CAND) out[ns] = ent;         // out + ns <= src + j: never overtakes the read cursor
               ++ns;
               ncodes += __popc(ent.x & 0xffu);
             }
@@ -444,32 +513,53 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
       }
       if (ns == 1 && ncodes == 1) {
         idx_out[row] = idx_offset + ((first >> 8) << 3) + (__ffs(first & 0xffu) - 1);
-      } else if (ns < 1 || ns > TC_CAND) {
+      } else if (ns < 1 || ncodes > RR_LIST) {
         fallback = true;
         const int pos = atomicAdd(counters + 0, 1);
         fb_rows[pos] = static_cast<int>(row);
         fb_packed[row] = ~0ull;
       }
     }
-    const bool multi = row < n && !fallback && !(ns == 1 && ncodes == 1);
-    __syncwarp();                                      // compacted records become visible to the whole warp
+    const bool multi = mine && !fallback && !(ns == 1 && ncodes == 1);
     unsigned todo = __ballot_sync(0xffffffffu, multi);
     while (todo) {
-      const int src = __ffs(todo) - 1;
+      const int src_lane = __ffs(todo) - 1;
       todo &= todo - 1;
-      const int64_t r = base + src;
-      const int ns_r = __shfl_sync(0xffffffffu, ns, src);
-      const uint32_t my_rec = lane < ns_r ? cand[r * nsub * TC_SLOTS + lane].x : 0u;
+      const int64_t r = base + src_lane;
+      const float thr_r = __shfl_sync(0xffffffffu, thr, src_lane);
+      // expand the surviving records of row r into the shared code list
+      int n_c = 0;
+      for (int sb = 0; sb < nsub; ++sb) {
+        const int c = cnt[r * nsub + sb];
+        uint2 ent = make_uint2(0u, 0xff800000u);
+        if (lane < c) ent = cand[(r * nsub + sb) * TC_SLOTS + lane];
+        const uint32_t mk = (lane < c && __uint_as_float(ent.y) >= thr_r) ? (ent.x & 0xffu) : 0u;
+        int pre = __popc(mk);                          // exclusive prefix sum of the per-lane code counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, pre, o);
+          if (lane >= o) pre += v;
+        }
+        const int tot = __shfl_sync(0xffffffffu, pre, 31);
+        int at = n_c + pre - __popc(mk);
+        uint32_t m = mk;
+        while (m) {
+          s_list[wib][at++] = ((ent.x >> 8) << 3) + (__ffs(m) - 1);
+          m &= m - 1;
+        }
+        n_c += tot;
+      }
+      __syncwarp();
+      // this lane's slice of the row (reused for every candidate)
       double top = -1e300;
       uint32_t top_idx = 0xffffffffu;
-      for (int j = 0; j < ns_r; ++j) {
-        const uint32_t rec = __shfl_sync(0xffffffffu, my_rec, j);
-        uint32_t mk = rec & 0xffu;
-        while (mk) {
-          const uint32_t code = ((rec >> 8) << 3) + (__ffs(mk) - 1);
-          mk &= mk - 1;
-          double dot = 0.0, ee = 0.0;
-          for (int d = lane * 4; d < D; d += 128) {
+      for (int c0 = 0; c0 < n_c; c0 += groups) {
+        const int ci = c0 + gi;
+        const bool ok = ci < n_c;
+        const uint32_t code = ok ? s_list[wib][ci] : 0u;
+        double dot = 0.0, ee = 0.0;
+        if (ok) {
+          for (int d = gl * 4; d < D; d += lpv * 4) {
             float zv[4], ev[4];
             if (BF16) {
               const uint2 a = *reinterpret_cast<const uint2*>(zb + r * D + d);
@@ -488,13 +578,22 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
               ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
             }
           }
-          dot = warp_sum(dot);
-          ee = warp_sum(ee);
-          const double sc = dot - 0.5 * ee;
-          if (sc > top || (sc == top && code < top_idx)) { top = sc; top_idx = code; }   // lowest index on exact ties
         }
+        for (int o = lpv >> 1; o > 0; o >>= 1) {       // reduce inside the lane group
+          dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          ee += __shfl_xor_sync(0xffffffffu, ee, o);
+        }
+        double sc = ok ? dot - 0.5 * ee : -1e300;
+        uint32_t cd = ok ? code : 0xffffffffu;
+        for (int o = lpv; o < 32; o <<= 1) {           // lexicographic (score, lowest index) across groups
+          const double so = __shfl_xor_sync(0xffffffffu, sc, o);
+          const uint32_t co = __shfl_xor_sync(0xffffffffu, cd, o);
+          if (so > sc || (so == sc && co < cd)) { sc = so; cd = co; }
+        }
+        if (sc > top || (sc == top && cd < top_idx)) { top = sc; top_idx = cd; }
       }
       if (lane == 0) idx_out[r] = idx_offset + top_idx;
+      __syncwarp();
     }
   }
 }
@@ -546,6 +645,7 @@ struct TcPlan {
 static bool tc_plan(int64_t N, int K, int D, TcPlan* pl) {
   if (D % TC_KB != 0 || D < 64 || D > 512 || K < TC_BN || N < 64) return false;
   pl->BM = (D <= 256) ? 256 : 128;
+  const int TC_CS = tc_cs(pl->BM);
   const int nepi = (pl->BM / 32) * TC_CS;
   const int ztile = pl->BM * D * 2;
   pl->zbufs = (2 * ztile + 4 * TC_STAGE_BYTES + nepi * 2 * (TC_BN / TC_CS) * 4 + 2048 <= TC_SMEM_LIMIT) ? 2 : 1;
@@ -594,7 +694,7 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // (row, split) slots: code splits are only used while row_tiles * ksplit <= #SMs
 static size_t tc_slots(int64_t rows, int BM) {
   const size_t few = static_cast<size_t>(kNumSMs) * BM;
-  return (static_cast<size_t>(rows) > few ? static_cast<size_t>(rows) : few) * TC_CS;   // x column slices
+  return (static_cast<size_t>(rows) > few ? static_cast<size_t>(rows) : few) * tc_cs(BM);   // x column slices
 }
 
 size_t tc_workspace_bytes(int64_t N, int K, int D) {
@@ -679,24 +779,26 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     const int grid = items < kNumSMs ? items : kNumSMs;
     timing_mark_begin(s);
     if (pl.BM == 256)
-      search_tc_kernel<256><<<grid, 64 + 256 * TC_CS, pl.smem_bytes, s>>>(map_z, map_e, p);
+      search_tc_kernel<256><<<grid, 64 + 256 * tc_cs(256), pl.smem_bytes, s>>>(map_z, map_e, p);
     else
-      search_tc_kernel<128><<<grid, 64 + 128 * TC_CS, pl.smem_bytes, s>>>(map_z, map_e, p);
+      search_tc_kernel<128><<<grid, 64 + 128 * tc_cs(128), pl.smem_bytes, s>>>(map_z, map_e, p);
     timing_mark_end(s);
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
 
-    blocks = (rows + 255) / 256;                       // one warp per 32 rows
+    int rpw = 32;                                      // rows per warp step: keep >= ~8K warps in flight
+    while (rpw > 1 && rows / rpw < 8192) rpw >>= 1;
+    blocks = (rows + 8 * rpw - 1) / (8 * rpw);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
     if (bf)
-      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit * TC_CS, margin,
-                                                                       cand, cnt, best, idx_offset, idx_out + r0, fb_rows,
-                                                                       fb_packed, counters);
+      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit * tc_cs(pl.BM), rpw,
+                                                                       margin, cand, cnt, best, idx_offset, idx_out + r0,
+                                                                       fb_rows, fb_packed, counters);
     else
-      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit * TC_CS, margin,
-                                                                        cand, cnt, best, idx_offset, idx_out + r0, fb_rows,
-                                                                        fb_packed, counters);
+      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit * tc_cs(pl.BM), rpw,
+                                                                        margin, cand, cnt, best, idx_offset, idx_out + r0,
+                                                                        fb_rows, fb_packed, counters);
     e = cudaGetLastError();
     if (e != cudaSuccess) return status_of(e);
     // rows handed back (overflow / non-finite): exact SIMT scan over the device-side row list, K split over CTAs
