@@ -697,12 +697,10 @@ static size_t tc_slots(int64_t rows, int BM) {
   return (static_cast<size_t>(rows) > few ? static_cast<size_t>(rows) : few) * tc_cs(BM);   // x column slices
 }
 
-size_t tc_workspace_bytes(int64_t N, int K, int D) {
-  TcPlan pl;
-  if (!tc_plan(N, K, D, &pl)) return 0;
-  const int64_t rows = N < pl.chunk_rows ? N : pl.chunk_rows;
-  const size_t slots = tc_slots(rows, pl.BM);
-  size_t b = 256;
+// Workspace of ONE chunk; two chunks' worth is laid out when the rows span several chunks (software pipeline).
+static size_t tc_set_bytes(int64_t rows, int D, int BM) {
+  const size_t slots = tc_slots(rows, BM);
+  size_t b = 256;                                                   // counters
   b += align_up(static_cast<size_t>(rows) * D * 2, 256);            // zb
   b += align_up(static_cast<size_t>(rows) * 4, 256);                // margin
   b += align_up(slots * 4, 256) * 2;                                // cnt, best
@@ -712,6 +710,13 @@ size_t tc_workspace_bytes(int64_t N, int K, int D) {
   return b;
 }
 
+size_t tc_workspace_bytes(int64_t N, int K, int D) {
+  TcPlan pl;
+  if (!tc_plan(N, K, D, &pl)) return 0;
+  const int64_t rows = N < pl.chunk_rows ? N : pl.chunk_rows;
+  return tc_set_bytes(rows, D, pl.BM) * (N > pl.chunk_rows ? 2 : 1);
+}
+
 int tc_launches(int64_t N, int K, int D) {
   TcPlan pl;
   if (!tc_plan(N, K, D, &pl)) return 0;
@@ -719,6 +724,58 @@ int tc_launches(int64_t N, int K, int D) {
   return static_cast<int>(chunks) * 5;   // zprep, tcgen05 search, re-rank, SIMT hand-back, unpack
 }
 
+// Helper streams for the chunk pipeline (created once per device, never destroyed).
+struct TcPipe {
+  bool ready = false;
+  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaEvent_t fork = nullptr, prep[2] = {nullptr, nullptr}, tc[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+};
+static TcPipe* tc_pipe() {
+  static TcPipe pipes[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  TcPipe& p = pipes[dev];
+  if (!p.ready) {
+    bool ok = cudaStreamCreateWithFlags(&p.s1, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&p.s2, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i)
+      ok = cudaEventCreateWithFlags(&p.prep[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p.tc[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&p.done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) return nullptr;
+    p.ready = true;
+  }
+  return &p;
+}
+
+struct TcSet {
+  int* counters; __nv_bfloat16* zb; float* margin; int* cnt; float* best; uint2* cand; int* fb_rows; uint64_t* fb_packed;
+};
+static TcSet carve(uint8_t* w, int64_t cap, int D, int BM) {
+  const size_t slots = tc_slots(cap, BM);
+  TcSet t;
+  t.counters = reinterpret_cast<int*>(w); w += 256;      // [0] rows handed to the SIMT kernel
+  t.zb = reinterpret_cast<__nv_bfloat16*>(w); w += align_up(static_cast<size_t>(cap) * D * 2, 256);
+  t.margin = reinterpret_cast<float*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
+  t.cnt = reinterpret_cast<int*>(w); w += align_up(slots * 4, 256);
+  t.best = reinterpret_cast<float*>(w); w += align_up(slots * 4, 256);
+  t.cand = reinterpret_cast<uint2*>(w); w += align_up(slots * TC_SLOTS * 8, 256);
+  t.fb_rows = reinterpret_cast<int*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
+  t.fb_packed = reinterpret_cast<uint64_t*>(w);
+  return t;
+}
+
+#define VQ_CUDA(call)                         \
+  do {                                        \
+    cudaError_t e_ = (call);                  \
+    if (e_ != cudaSuccess) return status_of(e_); \
+  } while (0)
+
+// The search over N rows runs chunk by chunk through three stages -- pre-pass, tcgen05 kernel, re-rank (+ exact
+// hand-back) -- and, with more than one chunk, the stages of neighbouring chunks overlap on three streams:
+// the pre-pass and re-rank kernels are short and latency-bound, the tensor kernel is persistent with one CTA per
+// SM, so they co-reside.  Everything is joined back into the caller's stream before returning.
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                      int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s) {
@@ -727,18 +784,15 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   if (workspace_bytes < tc_workspace_bytes(N, K, D)) return VQB200_EWORKSPACE;
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
   const int64_t cap = N < pl.chunk_rows ? N : pl.chunk_rows;
-  const int ksm = pl.ksplit_max;
-  const size_t slots = tc_slots(cap, pl.BM);
+  const int n_chunks = static_cast<int>((N + pl.chunk_rows - 1) / pl.chunk_rows);
+  TcPipe* pipe = n_chunks > 1 ? tc_pipe() : nullptr;
+  const bool piped = pipe != nullptr;
+  cudaStream_t s_prep = piped ? pipe->s1 : s, s_rr = piped ? pipe->s2 : s;
 
-  uint8_t* w = static_cast<uint8_t*>(workspace);
-  int* counters = reinterpret_cast<int*>(w); w += 256;   // [0] rows handed to the SIMT kernel
-  __nv_bfloat16* zb = reinterpret_cast<__nv_bfloat16*>(w); w += align_up(static_cast<size_t>(cap) * D * 2, 256);
-  float* margin = reinterpret_cast<float*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
-  int* cnt = reinterpret_cast<int*>(w); w += align_up(slots * 4, 256);
-  float* best = reinterpret_cast<float*>(w); w += align_up(slots * 4, 256);
-  uint2* cand = reinterpret_cast<uint2*>(w); w += align_up(slots * TC_SLOTS * 8, 256);
-  int* fb_rows = reinterpret_cast<int*>(w); w += align_up(static_cast<size_t>(cap) * 4, 256);
-  uint64_t* fb_packed = reinterpret_cast<uint64_t*>(w);
+  const size_t set_bytes = tc_set_bytes(cap, D, pl.BM);
+  TcSet sets[2];
+  sets[0] = carve(static_cast<uint8_t*>(workspace), cap, D, pl.BM);
+  sets[1] = n_chunks > 1 ? carve(static_cast<uint8_t*>(workspace) + set_bytes, cap, D, pl.BM) : sets[0];
 
   CUtensorMap map_e;
   if (!make_map(&map_e, E_bf16, K, D, TC_BN)) return VQB200_EDRIVER;
@@ -746,35 +800,48 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
 
   static bool attr_done[2] = {false, false};
   if (!attr_done[pl.BM == 256]) {
-    cudaError_t e = pl.BM == 256
+    VQ_CUDA(pl.BM == 256
         ? cudaFuncSetAttribute(search_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT)
-        : cudaFuncSetAttribute(search_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
-    if (e != cudaSuccess) return status_of(e);
+        : cudaFuncSetAttribute(search_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_done[pl.BM == 256] = true;
   }
+  if (piped) {
+    VQ_CUDA(cudaEventRecord(pipe->fork, s));
+    VQ_CUDA(cudaStreamWaitEvent(s_prep, pipe->fork, 0));
+    VQ_CUDA(cudaStreamWaitEvent(s_rr, pipe->fork, 0));
+  }
 
-  for (int64_t r0 = 0; r0 < N; r0 += pl.chunk_rows) {
+  int ci = 0;
+  for (int64_t r0 = 0; r0 < N; r0 += pl.chunk_rows, ++ci) {
     const int64_t rows = (N - r0) < pl.chunk_rows ? (N - r0) : pl.chunk_rows;
     const float* zc = z + r0 * D;
-    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(int), s);
-    if (e != cudaSuccess) return status_of(e);
+    const int b = piped ? (ci & 1) : 0;
+    const TcSet& w = sets[b];
 
-    int64_t warps = rows;
-    int64_t blocks = (warps + 7) / 8;
+    // ---- stage 1: pre-pass (needs the set free: the re-rank of chunk ci-2 has finished with it)
+    if (piped && ci >= 2) VQ_CUDA(cudaStreamWaitEvent(s_prep, pipe->done[b], 0));
+    VQ_CUDA(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int), s_prep));
+    int64_t blocks = (rows + 7) / 8;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    zprep_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, rows, D, mode, level_meta, zb, margin);
+    zprep_kernel<<<static_cast<unsigned>(blocks), 256, 0, s_prep>>>(zc, rows, D, mode, level_meta, w.zb, w.margin);
+    VQ_CUDA(cudaGetLastError());
+    if (piped) {
+      VQ_CUDA(cudaEventRecord(pipe->prep[b], s_prep));
+      VQ_CUDA(cudaStreamWaitEvent(s, pipe->prep[b], 0));
+    }
 
+    // ---- stage 2: tensor-core candidates (caller's stream)
     CUtensorMap map_z;
-    if (!make_map(&map_z, zb, rows, D, pl.BM)) return VQB200_EDRIVER;
+    if (!make_map(&map_z, w.zb, rows, D, pl.BM)) return VQB200_EDRIVER;
     TcParams p;
     p.n_rows = rows; p.D = D; p.K = K;
     p.row_tiles = static_cast<int>((rows + pl.BM - 1) / pl.BM);
-    p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, ksm, &p.tiles_per_split);
+    p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, pl.ksplit_max, &p.tiles_per_split);
     p.code_tiles = code_tiles;
     p.stages = pl.stages;
     p.zbufs = pl.zbufs;
     p.ee_half = bf ? ee_half_bf16 : ee_half;
-    p.margin = margin; p.cand = cand; p.cnt = cnt; p.best = best;
+    p.margin = w.margin; p.cand = w.cand; p.cnt = w.cnt; p.best = w.best;
     const int items = p.row_tiles * p.ksplit;
     const int grid = items < kNumSMs ? items : kNumSMs;
     timing_mark_begin(s);
@@ -783,31 +850,38 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     else
       search_tc_kernel<128><<<grid, 64 + 128 * tc_cs(128), pl.smem_bytes, s>>>(map_z, map_e, p);
     timing_mark_end(s);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return status_of(e);
+    VQ_CUDA(cudaGetLastError());
+    if (piped) {
+      VQ_CUDA(cudaEventRecord(pipe->tc[b], s));
+      VQ_CUDA(cudaStreamWaitEvent(s_rr, pipe->tc[b], 0));
+    }
 
+    // ---- stage 3: prune + exact re-rank, then the rows handed back to the exact SIMT kernel
     int rpw = 32;                                      // rows per warp step: keep >= ~8K warps in flight
     while (rpw > 1 && rows / rpw < 8192) rpw >>= 1;
     blocks = (rows + 8 * rpw - 1) / (8 * rpw);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
+    const int nsub = p.ksplit * tc_cs(pl.BM);
     if (bf)
-      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit * tc_cs(pl.BM), rpw,
-                                                                       margin, cand, cnt, best, idx_offset, idx_out + r0,
-                                                                       fb_rows, fb_packed, counters);
+      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s_rr>>>(zc, w.zb, E, Eb, rows, D, nsub, rpw, w.margin,
+                                                                          w.cand, w.cnt, w.best, idx_offset, idx_out + r0,
+                                                                          w.fb_rows, w.fb_packed, w.counters);
     else
-      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s>>>(zc, zb, E, Eb, rows, D, p.ksplit * tc_cs(pl.BM), rpw,
-                                                                        margin, cand, cnt, best, idx_offset, idx_out + r0,
-                                                                        fb_rows, fb_packed, counters);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return status_of(e);
-    // rows handed back (overflow / non-finite): exact SIMT scan over the device-side row list, K split over CTAs
-    int st = launch_search_simt_list(zc, fb_rows, counters, rows, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0,
-                                     idx_offset, fb_packed, s);
+      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s_rr>>>(zc, w.zb, E, Eb, rows, D, nsub, rpw, w.margin,
+                                                                           w.cand, w.cnt, w.best, idx_offset, idx_out + r0,
+                                                                           w.fb_rows, w.fb_packed, w.counters);
+    VQ_CUDA(cudaGetLastError());
+    const int st = launch_search_simt_list(zc, w.fb_rows, w.counters, rows, D, E, bf ? ee_half_bf16 : ee_half, K,
+                                           bf ? 1 : 0, idx_offset, w.fb_packed, s_rr);
     if (st != VQB200_OK) return st;
-    fb_unpack_kernel<<<64, 256, 0, s>>>(fb_rows, fb_packed, counters, idx_out + r0);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return status_of(e);
+    fb_unpack_kernel<<<64, 256, 0, s_rr>>>(w.fb_rows, w.fb_packed, w.counters, idx_out + r0);
+    VQ_CUDA(cudaGetLastError());
+    if (piped) VQ_CUDA(cudaEventRecord(pipe->done[b], s_rr));
+  }
+  if (piped) {                                         // join: the caller's stream sees every chunk finished
+    VQ_CUDA(cudaStreamWaitEvent(s, pipe->done[0], 0));
+    if (n_chunks > 1) VQ_CUDA(cudaStreamWaitEvent(s, pipe->done[1], 0));
   }
   return VQB200_OK;
 }
