@@ -104,6 +104,18 @@ VQB200_API int vqb200_gather(const float* z, const float* E, const int64_t* idx,
                   float* zq_out, int zq_accumulate, float* zq_st_out, float* residual_out,
                   double* sqerr_sum, int32_t* hist, const uint8_t* row_mask, void* stream);
 
+/* The whole single-level forward in ONE kernel (small code dimensions, currently D = 64): search, exact re-rank,
+ * gather, straight-through, commitment partial sum and histogram, reading the fp32 latents once.  Same
+ * outputs, bit for bit, as vqb200_search followed by vqb200_gather.  Every output except idx_out is optional.
+ * vqb200_quantize_fused_supported returns 1 when the shape takes this path. */
+VQB200_API int vqb200_quantize_fused_supported(int64_t N, int K, int D, int mode);
+VQB200_API size_t vqb200_quantize_fused_workspace_bytes(int64_t N, int K, int D, int mode);
+VQB200_API int vqb200_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16,
+                          const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K,
+                          int mode, int64_t idx_offset, int64_t* idx_out, float* zq_out, float* zq_st_out,
+                          double* sqerr_sum, int32_t* hist, const uint8_t* row_mask, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* Straight-through value and commitment partial sum from z and an already-summed z_q
  * (the RVQ tail, models/vq_vae.py:263 and :1293). */
 VQB200_API int vqb200_st_loss(const float* z, const float* zq, int64_t n_elems, float* zq_st_out,

@@ -133,6 +133,32 @@ int vqb200_gather(const float* z, const float* E, const int64_t* idx, int64_t N,
                        row_mask, static_cast<cudaStream_t>(stream));
 }
 
+int vqb200_quantize_fused_supported(int64_t N, int K, int D, int mode) {
+  (void)mode;
+  return fused_supported(N, K, D) ? 1 : 0;
+}
+
+size_t vqb200_quantize_fused_workspace_bytes(int64_t N, int K, int D, int mode) {
+  (void)mode;
+  return fused_supported(N, K, D) ? fused_workspace_bytes(N) : 0;
+}
+
+int vqb200_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16,
+                          const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K, int mode,
+                          int64_t idx_offset, int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum,
+                          int32_t* hist, const uint8_t* row_mask, void* workspace, size_t workspace_bytes, void* stream) {
+  VQ_REQUIRE(N > 0 && K > 0 && z && idx_out && workspace, VQB200_EINVAL);
+  VQ_REQUIRE(E && E_bf16 && ee_half && ee_half_bf16 && level_meta, VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(fused_supported(N, K, D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(E_bf16) && aligned16(zq_out) && aligned16(zq_st_out) &&
+                 (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+             VQB200_EALIGN);
+  return launch_quantize_fused(z, N, D, E, E_bf16, ee_half, ee_half_bf16, level_meta, K, mode, idx_offset, idx_out,
+                               zq_out, zq_st_out, sqerr_sum, hist, row_mask, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_st_loss(const float* z, const float* zq, int64_t n_elems, float* zq_st_out, double* sqerr_sum,
                    void* stream) {
   VQ_REQUIRE(n_elems >= 0, VQB200_EINVAL);

@@ -77,6 +77,12 @@ int tc_launches(int64_t N, int K, int D);
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                      int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s);
+bool fused_supported(int64_t N, int K, int D);
+size_t fused_workspace_bytes(int64_t N);
+int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
+                          const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
+                          int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                          const uint8_t* row_mask, void* workspace, size_t workspace_bytes, cudaStream_t s);
 int launch_codebook_refresh(bool ema, const float* seg_sum, const float* seg_cnt, float decay, float omd,
                             float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb, float* E,
                             uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s);

@@ -1,0 +1,619 @@
+// Fully fused quantizer forward for small code dimensions (D = 64): ONE persistent kernel reads the fp32
+// latents once and writes indices, z_q, z_q_st, the commitment partial sum and the usage histogram -- the
+// algorithmic HBM traffic of the path (12 D + 8 bytes per latent) and nothing else.  The multi-kernel
+// pipeline of vq_search_tc.cu + gather crosses HBM/L2 four times per latent; at D = 64 that, not the tensor
+// work, bounds the step.
+//
+// Per CTA (one per SM, persistent over 256-row tiles), 12 warps:
+//   warp 0      TMA producer: fp32 latent tile [256 x D] (prefetched one tile ahead) + bf16 codebook blocks
+//   warp 1      MMA issuer:   tcgen05.mma M=128 N=128 K=16, two row halves, accumulators double-buffered in TMEM,
+//                             pre-loaded with -|e|^2/2 so the accumulator IS the score
+//   warps 2-9   epilogue:     scan scores out of TMEM, keep <= 4 live candidate records per row IN REGISTERS
+//                             (a record dies as soon as the running threshold passes it), then per tile of rows:
+//                             prune, score survivors exactly (fp64, lane groups, inputs from L2), write idx,
+//                             z_q = E[idx], z_q_st = fl(z + fl(z_q - z)), sum (z_q - z)^2, histogram
+//   warps 10-11 converters:   fp32 tile (swizzled TMA layout) -> bf16 UMMA operand tile (128-byte swizzle),
+//                             row norms -> admission margins
+// Exactness argument, margin and hand-back rules are those of vq_search_tc.cu.
+#include <cstdlib>
+
+#include "tc_ptx.cuh"
+
+namespace vqb {
+
+constexpr int FZ_BM = 256;
+constexpr int FZ_NEPI = 8;
+constexpr int FZ_NCONV = 2;          // 12 warps = 3 per scheduler: 170 registers per thread, no spills
+constexpr int FZ_THREADS = 64 + FZ_NEPI * 32 + FZ_NCONV * 32;   // 384
+constexpr int FZ_PAIRS = 64;          // (row, code) pairs scored per warp pass
+constexpr int FZ_HIST = 2048;         // codebooks up to this size get a shared-memory histogram
+constexpr uint32_t FZ_EMPTY = 0xffffffffu;
+
+struct FusedParams {
+  int64_t n_rows;
+  int K, row_tiles, code_tiles, stages, mode;
+  const float* z;               // [n_rows, D] fp32
+  const float* E;               // [K, D] fp32
+  const __nv_bfloat16* Eb;      // [K, D] bf16
+  const float* ee_half;         // [K] plane chosen by mode
+  const float* level_meta;
+  int64_t idx_offset;
+  int64_t* idx_out;
+  float* zq_out;
+  float* zq_st_out;
+  double* sqerr_sum;
+  int* hist;                    // [K_total] (+ idx_offset applied)
+  const uint8_t* row_mask;
+  int* fb_rows;
+  uint64_t* fb_packed;
+  int* counters;
+};
+
+// 32 score columns of one row -> candidate records in register slots.  A slot is reusable once its group
+// maximum falls below the running threshold (it can never be the argmax any more).
+__device__ __forceinline__ void fz_scan(const uint32_t (&v)[32], uint32_t code0, float margin, float& best, float& thr,
+                                        uint32_t (&sx)[4], float (&sg)[4], bool& overflow) {
+  float gm[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float* s = reinterpret_cast<const float*>(&v[g * 8]);
+    gm[g] = fmaxf(fmaxf(fmaxf(s[0], s[1]), fmaxf(s[2], s[3])), fmaxf(fmaxf(s[4], s[5]), fmaxf(s[6], s[7])));
+  }
+  const float cm = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+  if (cm >= thr) {
+    best = fmaxf(best, cm);
+    thr = best - margin;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (gm[g] >= thr) {
+        uint32_t mk = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mk |= (__uint_as_float(v[g * 8 + i]) >= thr) ? (1u << i) : 0u;
+        const uint32_t rec = (((code0 >> 3) + g) << 8) | mk;
+        bool placed = false;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const bool dead = sx[s] == FZ_EMPTY || sg[s] < thr;
+          if (!placed && dead) { sx[s] = rec; sg[s] = gm[g]; placed = true; }
+        }
+        overflow |= !placed;
+      }
+    }
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(FZ_THREADS, 1)
+quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_constant__ CUtensorMap tmap_e,
+                      const FusedParams p) {
+  constexpr int KBLK = D / TC_KB;                  // bf16 operand blocks along D
+  constexpr int KB32 = D / 32;                     // fp32 staging slabs along D (32 floats = 128 bytes)
+  constexpr uint32_t ZF_BYTES = FZ_BM * D * 4;
+  constexpr uint32_t ZB_BYTES = FZ_BM * D * 2;
+  constexpr int LPV = (D / 4) < 32 ? (D / 4) : 32; // lanes that cover one row with float4 slices
+  constexpr int GROUPS = 32 / LPV;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t zf_smem = base;
+  const uint32_t zb_smem = zf_smem + ZF_BYTES;
+  const uint32_t e_smem = zb_smem + 2 * ZB_BYTES;
+  const uint32_t misc = e_smem + static_cast<uint32_t>(p.stages) * TC_STAGE_BYTES;
+  float* margin_s = reinterpret_cast<float*>(gen + (misc - base));                       // [2][256]
+  float* ee_slots = margin_s + 2 * FZ_BM;                                                 // [8][128]
+  uint32_t* pair_list = reinterpret_cast<uint32_t*>(ee_slots + FZ_NEPI * TC_BN);          // [8][64]
+  double* pair_score = reinterpret_cast<double*>(pair_list + FZ_NEPI * FZ_PAIRS);         // [8][64]
+  int* hist_s = reinterpret_cast<int*>(pair_score + FZ_NEPI * FZ_PAIRS);                  // [FZ_HIST]
+  double* red_s = reinterpret_cast<double*>(hist_s + FZ_HIST);                            // [16]
+  const uint32_t bar0 = misc + 2 * FZ_BM * 4 + FZ_NEPI * TC_BN * 4 + FZ_NEPI * FZ_PAIRS * 4 + FZ_NEPI * FZ_PAIRS * 8 +
+                        FZ_HIST * 4 + 16 * 8;
+  const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * 8, bar_tfull = bar0 + 16 * 8, bar_tempty = bar0 + 18 * 8;
+  const uint32_t bar_zffull = bar0 + 20 * 8, bar_zfempty = bar0 + 21 * 8;
+  const uint32_t bar_zbfull = bar0 + 22 * 8, bar_zbempty = bar0 + 24 * 8;    // [2] each
+  const uint32_t tmem_slot = bar0 + 26 * 8;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool smem_hist = p.hist != nullptr && p.K <= FZ_HIST;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, FZ_NEPI);
+      mbar_init(bar_zbfull + 8 * b, FZ_NCONV); mbar_init(bar_zbempty + 8 * b, 1);
+    }
+    mbar_init(bar_zffull, 1);
+    mbar_init(bar_zfempty, FZ_NCONV);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (smem_hist)
+    for (int k = threadIdx.x; k < p.K; k += FZ_THREADS) hist_s[k] = 0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int n_items = p.row_tiles;
+  float err_acc = 0.f;                              // sum (z_q - z)^2 over the rows this thread finalises
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    uint32_t stage = 0, phase = 0, it = 0;
+    auto load_z = [&](int item, uint32_t seq) {
+      mbar_wait(bar_zfempty, (seq & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(bar_zffull, ZF_BYTES);
+        for (int kb = 0; kb < KB32; ++kb)
+          tma_load_2d(zf_smem + kb * (FZ_BM * 128), &tmap_zf, bar_zffull, kb * 32, item * FZ_BM);
+      }
+      __syncwarp();
+    };
+    if (static_cast<int>(blockIdx.x) < n_items) load_z(blockIdx.x, 0);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int nxt = item + gridDim.x;
+      if (nxt < n_items) load_z(nxt, it + 1);       // the next tile's latents ride ahead of this tile's codebook blocks
+      for (int t = 0; t < p.code_tiles; ++t) {
+        for (int kb = 0; kb < KBLK; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+            tma_load_2d(e_smem + stage * TC_STAGE_BYTES, &tmap_e, bar_full + 8 * stage, kb * TC_KB, t * TC_BN);
+          }
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    uint32_t stage = 0, phase = 0, it = 0, tg = 0;
+    const uint32_t zb_lo = umma_desc_lo(zb_smem), e_lo = umma_desc_lo(e_smem);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t zb = it & 1;
+      mbar_wait(bar_zbfull + 8 * zb, (it >> 1) & 1);
+      for (int t = 0; t < p.code_tiles; ++t, ++tg) {
+        const uint32_t b = tg & 1;
+        mbar_wait(bar_tempty + 8 * b, (tg >> 1) & 1);       // drained AND pre-loaded with -|e|^2/2
+        tc_fence_after();
+        for (int kb = 0; kb < KBLK; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a0 = zb_lo + ((zb * ZB_BYTES + kb * (FZ_BM * 128)) >> 4);
+            const uint32_t b0 = e_lo + ((stage * TC_STAGE_BYTES) >> 4);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const uint32_t d_tmem = tmem_base + b * (2 * TC_BN) + h * TC_BN;
+#pragma unroll
+              for (int k = 0; k < TC_KB / 16; ++k)
+                tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), kIdesc, 1u);
+            }
+            tc_commit(bar_empty + 8 * stage);
+            if (kb == KBLK - 1) tc_commit(bar_tfull + 8 * b);
+          }
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (elect_one()) tc_commit(bar_zbempty + 8 * zb);
+      __syncwarp();
+    }
+  } else if (warp >= 2 + FZ_NEPI) {
+    // ============================== converters: fp32 tile -> bf16 operand tile + margins ==============================
+    const int ct = (warp - 2 - FZ_NEPI) * 32 + lane;     // 0..63: rows ct, ct+64, ct+128, ct+192 of the tile
+    const float emax = p.mode == VQB200_MODE_BF16_INPUT ? p.level_meta[2] : p.level_meta[0];
+    const bool code_bad = p.level_meta[1] != 0.f;
+    const float coef = p.mode == VQB200_MODE_BF16_INPUT ? 2.f * static_cast<float>(D + 32) * 1.1920929e-7f
+                                                        : 2.f * 0.00391007f * 1.02f;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t zb = it & 1;
+      mbar_wait(bar_zffull, it & 1);
+      mbar_wait(bar_zbempty + 8 * zb, ((it >> 1) & 1) ^ 1);
+#pragma unroll 1
+      for (int rr = 0; rr < FZ_BM / (FZ_NCONV * 32); ++rr) {
+        const int r = ct + rr * (FZ_NCONV * 32);
+        const uint32_t sw = static_cast<uint32_t>(r & 7);
+        float ss = 0.f;
+#pragma unroll
+        for (int q = 0; q < D / 8; ++q) {             // one 16-byte bf16 chunk (8 elements) per step
+          const int c = q * 8;                        // first column of the chunk
+          float4 lo, hi;
+          {
+            const int slab = c / 32, j = (c % 32) / 4;
+            const uint8_t* src = gen + (zf_smem - base) + slab * (FZ_BM * 128) + r * 128;
+            lo = *reinterpret_cast<const float4*>(src + ((static_cast<uint32_t>(j) ^ sw) << 4));
+            hi = *reinterpret_cast<const float4*>(src + ((static_cast<uint32_t>(j + 1) ^ sw) << 4));
+          }
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w),
+                               p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
+          uint4 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&p0); pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+          pk.z = *reinterpret_cast<const uint32_t*>(&p2); pk.w = *reinterpret_cast<const uint32_t*>(&p3);
+          const int bslab = c / TC_KB, bj = (c % TC_KB) / 8;
+          uint8_t* dst = gen + (zb_smem - base) + zb * ZB_BYTES + bslab * (FZ_BM * 128) + r * 128;
+          *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(bj) ^ sw) << 4)) = pk;
+          if (p.mode == VQB200_MODE_BF16_INPUT) {
+            const float2 a = __bfloat1622float2(p0), b2 = __bfloat1622float2(p1), c2 = __bfloat1622float2(p2),
+                         d2 = __bfloat1622float2(p3);
+            ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y + c2.x * c2.x + c2.y * c2.y + d2.x * d2.x + d2.y * d2.y;
+          } else {
+            ss += lo.x * lo.x + lo.y * lo.y + lo.z * lo.z + lo.w * lo.w + hi.x * hi.x + hi.y * hi.y + hi.z * hi.z + hi.w * hi.w;
+          }
+        }
+        float m = coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f;
+        if (code_bad || !(ss < __int_as_float(0x7f800000))) m = __int_as_float(0x7fc00000);   // NaN: exact path
+        margin_s[zb * FZ_BM + r] = m;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bar_zbfull + 8 * zb); mbar_arrive(bar_zfempty); }
+    }
+  } else {
+    // ============================== epilogue + finalise ==============================
+    const int we = warp - 2;
+    const int quarter = warp & 3, half = we >> 2;
+    const int row_in_tile = half * 128 + quarter * 32;
+    float* ee_slot = ee_slots + we * TC_BN;
+    uint32_t* plist = pair_list + we * FZ_PAIRS;
+    double* pscore = pair_score + we * FZ_PAIRS;
+    const float kNegInf = __int_as_float(0xff800000);
+    const uint32_t tcol = (static_cast<uint32_t>(quarter * 32) << 16) + half * TC_BN;
+    const int gl = lane % LPV, gi = lane / LPV;
+
+    struct Bias { float v[4]; };
+    auto load_bias = [&](int t) -> Bias {
+      Bias r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = t * TC_BN + lane * 4 + j;
+        r.v[j] = (t >= 0 && c < p.K) ? -p.ee_half[c] : kNegInf;
+      }
+      return r;
+    };
+    auto preload = [&](const Bias& bias, uint32_t b) {
+      __syncwarp();
+      *reinterpret_cast<float4*>(ee_slot + lane * 4) = make_float4(bias.v[0], bias.v[1], bias.v[2], bias.v[3]);
+      __syncwarp();
+#pragma unroll
+      for (int hh = 0; hh < TC_BN / 16; ++hh) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(ee_slot + hh * 16 + j);
+          w[j + 0] = __float_as_uint(q4.x); w[j + 1] = __float_as_uint(q4.y);
+          w[j + 2] = __float_as_uint(q4.z); w[j + 3] = __float_as_uint(q4.w);
+        }
+        TC_ST16(tmem_base + tcol + b * (2 * TC_BN) + hh * 16, w);
+      }
+      tc_wait_st();
+    };
+    // the CTA's tile sequence is item-major, code tiles 0..code_tiles-1 inside; walk it two tiles ahead
+    const int64_t total_tiles = static_cast<int64_t>((n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                                     static_cast<int>(gridDim.x)) * p.code_tiles;
+    int64_t la = 0;                                   // index into the sequence of the next tile to fetch
+    auto la_next = [&]() -> int { return la < total_tiles ? static_cast<int>((la++) % p.code_tiles) : (la++, -1); };
+    for (uint32_t b = 0; b < 2; ++b) {
+      const int tt = la_next();
+      if (tt >= 0) preload(load_bias(tt), b);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+    }
+    int t_ahead = la_next();
+    Bias bias_next = load_bias(t_ahead);
+
+    uint32_t tg = 0, it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t zb = it & 1;
+      const int64_t row0w = static_cast<int64_t>(item) * FZ_BM + row_in_tile;
+      const int64_t row = row0w + lane;
+      const bool row_ok = row < p.n_rows;
+      mbar_wait(bar_zbfull + 8 * zb, (it >> 1) & 1);          // margins of this tile are in shared memory
+      const float margin = row_ok ? margin_s[zb * FZ_BM + row_in_tile + lane] : __int_as_float(0x7fc00000);
+      float best = kNegInf;
+      float thr = margin == margin ? best : margin;
+      uint32_t sx[4] = {FZ_EMPTY, FZ_EMPTY, FZ_EMPTY, FZ_EMPTY};
+      float sg[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
+      bool overflow = false;
+
+      for (int t = 0; t < p.code_tiles; ++t, ++tg) {
+        const uint32_t b = tg & 1;
+        const Bias bias = bias_next;
+        const int t_cur_ahead = t_ahead;
+        t_ahead = la_next();
+        bias_next = load_bias(t_ahead);
+        mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + tcol + b * (2 * TC_BN);
+        uint32_t v[32];
+#pragma unroll
+        for (int ch = 0; ch < TC_BN / 32; ++ch) {
+          TC_LD32(taddr + ch * 32, v);
+          tc_wait_ld();
+          if (ch == TC_BN / 32 - 1) {
+            if (t_cur_ahead >= 0) preload(bias, b);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+          }
+          fz_scan(v, static_cast<uint32_t>(t * TC_BN + ch * 32), margin, best, thr, sx, sg, overflow);
+        }
+      }
+
+      // ---------------- finalise the 32 rows of this warp ----------------
+      int ns = 0, ncodes = 0;
+      uint32_t first = 0;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const bool alive = sx[s] != FZ_EMPTY && sg[s] >= thr;
+        if (!alive) sx[s] = FZ_EMPTY;
+        else { if (ns == 0) first = sx[s]; ++ns; ncodes += __popc(sx[s] & 0xffu); }
+      }
+      bool resolved = false, multi = false;
+      uint32_t my_idx = 0;
+      if (row_ok) {
+        if (overflow || ns == 0 || !(margin == margin)) {       // exact SIMT kernel takes the row
+          const int pos = atomicAdd(p.counters, 1);
+          p.fb_rows[pos] = static_cast<int>(row);
+          p.fb_packed[row] = ~0ull;
+        } else if (ns == 1 && ncodes == 1) {                    // certified by the error bound
+          my_idx = ((first >> 8) << 3) + (__ffs(first & 0xffu) - 1);
+          resolved = true;
+        } else {
+          multi = true;
+        }
+      }
+      bool pending = multi;
+      while (__any_sync(0xffffffffu, pending)) {
+        const int c = pending ? ncodes : 0;
+        int pre = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(0xffffffffu, pre, o);
+          if (lane >= o) pre += u;
+        }
+        const bool take = pending && pre <= FZ_PAIRS;
+        const int off0 = pre - c;
+        if (take) {
+          int at = off0;
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            if (sx[s] != FZ_EMPTY) {
+              uint32_t m = sx[s] & 0xffu;
+              while (m) {
+                plist[at++] = (static_cast<uint32_t>(lane) << 24) | (((sx[s] >> 8) << 3) + (__ffs(m) - 1));
+                m &= m - 1;
+              }
+            }
+          }
+        }
+        const unsigned tk = __ballot_sync(0xffffffffu, take);
+        const int T = __shfl_sync(0xffffffffu, pre, 31 - __clz(tk));
+        __syncwarp();
+        for (int pb = 0; pb < T; pb += GROUPS) {                // GROUPS pairs scored concurrently by lane groups
+          const int pi = pb + gi;
+          const bool ok = pi < T;
+          const uint32_t pr = ok ? plist[pi] : 0u;
+          const uint32_t code = pr & 0xffffffu;
+          const int64_t grow = row0w + (pr >> 24);
+          double dot = 0.0, ee = 0.0;
+          if (ok) {
+#pragma unroll
+            for (int d = gl * 4; d < D; d += LPV * 4) {
+              float zv[4], ev[4];
+              *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(p.z + grow * D + d);
+              if (p.mode == VQB200_MODE_BF16_INPUT) {
+                const uint2 eb = *reinterpret_cast<const uint2*>(p.Eb + static_cast<int64_t>(code) * D + d);
+                ev[0] = __uint_as_float(eb.x << 16); ev[1] = __uint_as_float(eb.x & 0xffff0000u);
+                ev[2] = __uint_as_float(eb.y << 16); ev[3] = __uint_as_float(eb.y & 0xffff0000u);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) zv[q] = bf16_round(zv[q]);
+              } else {
+                *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(code) * D + d));
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
+                ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+              }
+            }
+          }
+#pragma unroll
+          for (int o = LPV >> 1; o > 0; o >>= 1) {
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            ee += __shfl_xor_sync(0xffffffffu, ee, o);
+          }
+          if (ok && gl == 0) pscore[pi] = dot - 0.5 * ee;
+        }
+        __syncwarp();
+        if (take) {                                             // lexicographic (score, lowest index)
+          double top = -1e300;
+          uint32_t top_idx = 0xffffffffu;
+          for (int j = off0; j < off0 + c; ++j) {
+            const double sc = pscore[j];
+            const uint32_t cd = plist[j] & 0xffffffu;
+            if (sc > top || (sc == top && cd < top_idx)) { top = sc; top_idx = cd; }
+          }
+          my_idx = top_idx;
+          resolved = true;
+        }
+        pending = pending && !take;
+        __syncwarp();
+      }
+
+      // ---------------- outputs ----------------
+      if (resolved) {
+        p.idx_out[row] = p.idx_offset + my_idx;
+        if (p.hist && (!p.row_mask || p.row_mask[row])) {
+          if (smem_hist) atomicAdd(hist_s + my_idx, 1);
+          else atomicAdd(p.hist + p.idx_offset + my_idx, 1);
+        }
+      }
+      if (p.zq_out || p.zq_st_out || p.sqerr_sum) {
+#pragma unroll 2
+        for (int rb = 0; rb < 32; rb += GROUPS) {
+          const int rl = rb + gi;
+          const bool res = __shfl_sync(0xffffffffu, static_cast<int>(resolved), rl) != 0;
+          const uint32_t code = __shfl_sync(0xffffffffu, my_idx, rl);
+          const int64_t grow = row0w + rl;
+          if (res) {
+#pragma unroll
+            for (int d = gl * 4; d < D; d += LPV * 4) {
+              const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(code) * D + d));
+              const float4 z4 = ld_stream(reinterpret_cast<const float4*>(p.z + grow * D + d));
+              float4 df;
+              df.x = __fsub_rn(e4.x, z4.x); df.y = __fsub_rn(e4.y, z4.y);
+              df.z = __fsub_rn(e4.z, z4.z); df.w = __fsub_rn(e4.w, z4.w);
+              if (p.zq_out) st_stream(reinterpret_cast<float4*>(p.zq_out + grow * D + d), e4);
+              if (p.zq_st_out) {
+                float4 o;
+                o.x = __fadd_rn(z4.x, df.x); o.y = __fadd_rn(z4.y, df.y);
+                o.z = __fadd_rn(z4.z, df.z); o.w = __fadd_rn(z4.w, df.w);
+                st_stream(reinterpret_cast<float4*>(p.zq_st_out + grow * D + d), o);
+              }
+              err_acc = fmaf(df.x, df.x, err_acc); err_acc = fmaf(df.y, df.y, err_acc);
+              err_acc = fmaf(df.z, df.z, err_acc); err_acc = fmaf(df.w, df.w, err_acc);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (smem_hist)
+    for (int k = threadIdx.x; k < p.K; k += FZ_THREADS) {
+      const int v = hist_s[k];
+      if (v) atomicAdd(p.hist + p.idx_offset + k, v);
+    }
+  if (p.sqerr_sum) {
+    const double e = warp_sum(static_cast<double>(err_acc));
+    if (lane == 0) red_s[warp] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < FZ_THREADS / 32; ++w) t += red_s[w];
+      atomicAdd(p.sqerr_sum, t);
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Rows handed back to the exact SIMT kernel: write their index and outputs once it has decided.
+__global__ void __launch_bounds__(256)
+fused_fixup_kernel(const int* __restrict__ fb_rows, const uint64_t* __restrict__ fb_packed,
+                   const int* __restrict__ counters, const float* __restrict__ z, const float* __restrict__ E, int D,
+                   int64_t* __restrict__ idx_out, float* __restrict__ zq_out, float* __restrict__ zq_st_out,
+                   double* sqerr_sum, int* __restrict__ hist, const uint8_t* __restrict__ row_mask) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n = counters[0];
+  float err = 0.f;
+  for (int i = warp; i < n; i += nwarps) {
+    const int64_t row = fb_rows[i];
+    const int64_t code = static_cast<int64_t>(fb_packed[row] & 0xffffffffull);   // idx_offset already applied
+    if (lane == 0) {
+      idx_out[row] = code;
+      if (hist && (!row_mask || row_mask[row])) atomicAdd(hist + code, 1);
+    }
+    for (int d = lane * 4; d < D; d += 128) {
+      const float4 e4 = __ldg(reinterpret_cast<const float4*>(E + code * D + d));
+      const float4 z4 = *reinterpret_cast<const float4*>(z + row * D + d);
+      float4 df;
+      df.x = __fsub_rn(e4.x, z4.x); df.y = __fsub_rn(e4.y, z4.y); df.z = __fsub_rn(e4.z, z4.z); df.w = __fsub_rn(e4.w, z4.w);
+      if (zq_out) *reinterpret_cast<float4*>(zq_out + row * D + d) = e4;
+      if (zq_st_out)
+        *reinterpret_cast<float4*>(zq_st_out + row * D + d) =
+            make_float4(__fadd_rn(z4.x, df.x), __fadd_rn(z4.y, df.y), __fadd_rn(z4.z, df.z), __fadd_rn(z4.w, df.w));
+      err = fmaf(df.x, df.x, err); err = fmaf(df.y, df.y, err); err = fmaf(df.z, df.z, err); err = fmaf(df.w, df.w, err);
+    }
+  }
+  if (sqerr_sum) {
+    const double e = warp_sum(static_cast<double>(err));
+    if (lane == 0 && e != 0.0) atomicAdd(sqerr_sum, e);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static size_t fz_align(size_t v) { return (v + 255) / 256 * 256; }
+
+bool fused_supported(int64_t N, int K, int D) {
+  const char* f = std::getenv("VQB200_FORCE_SIMT");
+  if (f && f[0] == '1') return false;
+  const char* g = std::getenv("VQB200_NO_FUSED");
+  if (g && g[0] == '1') return false;
+  return D == 64 && K >= TC_BN && K < (1 << 24) && N >= 4096 && N <= 0x7fffffff;
+}
+
+size_t fused_workspace_bytes(int64_t N) { return 256 + fz_align(static_cast<size_t>(N) * 4) + fz_align(static_cast<size_t>(N) * 8); }
+
+static int fused_smem_bytes(int D, int stages) {
+  return 1024 + FZ_BM * D * 4 + 2 * FZ_BM * D * 2 + stages * TC_STAGE_BYTES + 2 * FZ_BM * 4 + FZ_NEPI * TC_BN * 4 +
+         FZ_NEPI * FZ_PAIRS * 4 + FZ_NEPI * FZ_PAIRS * 8 + FZ_HIST * 4 + 16 * 8 + 256;
+}
+
+int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
+                          const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
+                          int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                          const uint8_t* row_mask, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  if (!fused_supported(N, K, D)) return VQB200_ESHAPE;
+  if (workspace_bytes < fused_workspace_bytes(N)) return VQB200_EWORKSPACE;
+  const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  int stages = 8;
+  while (stages > 2 && fused_smem_bytes(D, stages) > TC_SMEM_LIMIT) --stages;
+  if (fused_smem_bytes(D, stages) > TC_SMEM_LIMIT) return VQB200_ESHAPE;
+
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  int* counters = reinterpret_cast<int*>(w); w += 256;
+  int* fb_rows = reinterpret_cast<int*>(w); w += fz_align(static_cast<size_t>(N) * 4);
+  uint64_t* fb_packed = reinterpret_cast<uint64_t*>(w);
+
+  CUtensorMap map_zf, map_e;
+  if (!make_tensor_map_2d(&map_zf, z, N, D, FZ_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4)) return VQB200_EDRIVER;
+  if (!make_tensor_map_2d(&map_e, E_bf16, K, D, TC_BN, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2)) return VQB200_EDRIVER;
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(quantize_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    if (e != cudaSuccess) return status_of(e);
+    attr_done = true;
+  }
+  cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(int), s);
+  if (e != cudaSuccess) return status_of(e);
+
+  FusedParams p;
+  p.n_rows = N; p.K = K;
+  p.row_tiles = static_cast<int>((N + FZ_BM - 1) / FZ_BM);
+  p.code_tiles = (K + TC_BN - 1) / TC_BN;
+  p.stages = stages; p.mode = mode;
+  p.z = z; p.E = E; p.Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
+  p.ee_half = bf ? ee_half_bf16 : ee_half; p.level_meta = level_meta;
+  p.idx_offset = idx_offset; p.idx_out = idx_out; p.zq_out = zq_out; p.zq_st_out = zq_st_out;
+  p.sqerr_sum = sqerr_sum; p.hist = hist; p.row_mask = row_mask;
+  p.fb_rows = fb_rows; p.fb_packed = fb_packed; p.counters = counters;
+  const int grid = p.row_tiles < kNumSMs ? p.row_tiles : kNumSMs;
+  timing_mark_begin(s);
+  quantize_fused_kernel<64><<<grid, FZ_THREADS, fused_smem_bytes(D, stages), s>>>(map_zf, map_e, p);
+  timing_mark_end(s);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return status_of(e);
+
+  const int st = launch_search_simt_list(z, fb_rows, counters, N, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0,
+                                         idx_offset, fb_packed, s);
+  if (st != VQB200_OK) return st;
+  fused_fixup_kernel<<<64, 256, 0, s>>>(fb_rows, fb_packed, counters, z, E, D, idx_out, zq_out, zq_st_out, sqerr_sum, hist,
+                                        row_mask);
+  return status_of(cudaGetLastError());
+}
+
+}  // namespace vqb

@@ -80,6 +80,26 @@ def search_launches(N, K, D, mode) -> int:
     return lib.vqb200_search_launches(N, K, D, mode)
 
 
+def fused_supported(N, K, D, mode) -> bool:
+    return bool(lib.vqb200_quantize_fused_supported(N, K, D, mode))
+
+
+def quantize_fused(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st_out=None, sqerr_sum=None,
+                   hist=None, row_mask=None):
+    """Single-level forward in one kernel: idx, z_q, z_q_st, sum (z_q - z)^2 and histogram from one read of z."""
+    _need_cuda(z, E, idx_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    K = cache.K_per
+    ws_bytes = lib.vqb200_quantize_fused_workspace_bytes(N, K, D, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    check(lib.vqb200_quantize_fused(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), cache.ee_half.data_ptr(),
+                                    cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, mode, 0,
+                                    ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist),
+                                    ptr(row_mask), ptr(ws), ws_bytes, stream_ptr()), "vqb200_quantize_fused")
+    _count(3)     # fused kernel, exact hand-back kernel, fix-up kernel
+
+
 def gather(z, E, idx, zq_out=None, accumulate=False, zq_st_out=None, residual_out=None, sqerr_sum=None,
            hist=None, row_mask=None):
     _need_cuda(z, E, idx)

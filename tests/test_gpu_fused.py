@@ -1,0 +1,84 @@
+"""The fully fused small-D forward (one kernel) against the multi-kernel path (VQB200_NO_FUSED=1) and the
+oracle: identical indices, bit-identical z_q / z_q_st, identical histogram, loss within 1e-6."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from synth import large_case_inputs
+
+from oracle import vq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vq():
+    import pytorch_vae_b200 as m
+    return m
+
+
+def forward(vq, z, E, K, mode="fp32", fused=True, mask=None):
+    dev = torch.device("cuda:0")
+    D = z.shape[-1]
+    q = vq.VectorQuantizerEMA(K, D, print_init=False, search_mode=mode).to(dev).eval()
+    q.embedding.copy_(torch.from_numpy(E).to(dev))
+    old = os.environ.get("VQB200_NO_FUSED")
+    os.environ["VQB200_NO_FUSED"] = "0" if fused else "1"
+    try:
+        used = vq.ops.fused_supported(z.shape[0] * z.shape[1], K, D, 0)
+        st, zq, idx, stats = q(torch.from_numpy(z).to(dev), do_ema_update=False,
+                               mask=None if mask is None else torch.from_numpy(mask).to(dev))
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("VQB200_NO_FUSED", None)
+        else:
+            os.environ["VQB200_NO_FUSED"] = old
+    return used, st, zq, idx, stats, q
+
+
+@pytest.mark.parametrize("K,N,mode", [(512, 8192, "fp32"), (128, 4096, "fp32"), (1000, 300 * 64, "fp32"),
+                                      (2048, 16384, "fp32"), (4096, 8192, "fp32"), (512, 1 << 18, "fp32"),
+                                      (512, 8192, "bf16_input")])
+def test_fused_equals_multikernel(vq, K, N, mode):
+    D = 64
+    E, z = large_case_inputs(300 + K + N % 977, K, D, 1, N // 64, 64)
+    uf, st_f, zq_f, idx_f, stats_f, qf = forward(vq, z, E, K, mode, fused=True)
+    um, st_m, zq_m, idx_m, stats_m, qm = forward(vq, z, E, K, mode, fused=False)
+    assert uf and not um
+    assert torch.equal(idx_f, idx_m)
+    assert torch.equal(zq_f, zq_m) and torch.equal(st_f, st_m)
+    assert torch.equal(qf._ep_usage, qm._ep_usage) and float(qf._ep_usage.sum()) == N
+    np.testing.assert_allclose(stats_f.cpu().numpy(), stats_m.cpu().numpy(), rtol=1e-6)
+    np.testing.assert_allclose(float(qf.last_commit), float(qm.last_commit), rtol=1e-6)
+    if mode == "fp32":
+        ref = O.nearest_code64(z.reshape(-1, D), E)
+        mm, outside = O.near_tie_rows(z.reshape(-1, D), E, idx_f.cpu().numpy().reshape(-1), ref)
+        assert outside.size == 0 and mm.size <= 2
+
+
+def test_fused_hard_rows_and_mask(vq):
+    K, D, N = 256, 64, 8192
+    E, z = large_case_inputs(41, K, D, 1, N // 64, 64)
+    z = z.copy()
+    z[0, 3, 5] = np.nan
+    z[1, 7, 0] = np.inf
+    z[2, 1, 2] = -np.inf
+    z[3, 0] = 0.0
+    z[5, :, :] *= 40.0                                     # large norms: wide margins, many survivors
+    E[40:200] = 0.0                                        # collapsed codebook: candidate slots overflow
+    E[210] = E[17]
+    z[4, :] = E[17] * 1.01                                 # duplicate of a winning code: lowest index
+    mask = np.random.RandomState(3).rand(N // 64, 64) > 0.3
+    uf, st_f, zq_f, idx_f, stats_f, qf = forward(vq, z, E, K, fused=True, mask=mask)
+    um, st_m, zq_m, idx_m, stats_m, qm = forward(vq, z, E, K, fused=False, mask=mask)
+    assert uf and not um
+    assert torch.equal(idx_f, idx_m)
+    fin = torch.isfinite(st_m).all(-1) & torch.isfinite(st_f).all(-1)
+    assert torch.equal(zq_f, zq_m) and torch.equal(st_f[fin], st_m[fin])
+    assert torch.equal(qf._ep_usage, qm._ep_usage)
+    assert (idx_f[4] == 17).all()
+    flat = z.reshape(-1, D)
+    ok = np.isfinite(flat).all(1)
+    assert np.array_equal(idx_f.cpu().numpy().reshape(-1)[ok], O.nearest_code64(flat[ok], E))
