@@ -252,13 +252,17 @@ def run_b200(args, w):
     rows_per_launch = N * L / launches_per_step                  # rows one launch scans (chunks x levels per step)
     hbm, tf, peak_src = peaks()
     flops = 2.0 * rows_per_launch * K * D
-    bytes_alg = rows_per_launch * (4.0 * D + 8.0)                # SURVEY 8(d) codes-only: read z (fp32), write idx
+    fused = L == 1 and bool(lib.vqb200_quantize_fused_supported(N, K, D, mode))
+    # the fused kernel does the full forward (read z, write z_q, z_q_st, idx = 12 D + 8 bytes per
+    # row); the stand-alone search kernel is "codes-only" (read z, write idx = 4 D + 8)
+    bytes_alg = rows_per_launch * ((12.0 * D + 8.0) if fused else (4.0 * D + 8.0))
     tensor_bound = flops / (tf * 1e12) > bytes_alg / (hbm * 1e9)
     on_tc = bool(lib.vqb200_search_path(N, K, D, mode))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        t = json.load(open(tpath)).get(args.workload if args.mode == "fp32" else "", None)
+        key = (args.workload + ("_fused" if fused else "")) if args.mode == "fp32" else ""
+        t = json.load(open(tpath)).get(key, None)
         if t:                                                    # dram bytes of one launch from one ncu --set full capture
             traffic = t["dram_bytes_per_row"] * rows_per_launch
     if tensor_bound:
@@ -267,10 +271,13 @@ def run_b200(args, w):
     else:
         ach = bytes_alg / (kern_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
-    roof.update({"traffic": traffic, "kernel": "search_tc_kernel (tcgen05 distance+argmin)" if on_tc else "search_simt_kernel",
+    kname = ("quantize_fused_kernel (tcgen05 distance+argmin+gather, one pass)" if fused else
+             "search_tc_kernel (tcgen05 distance+argmin)" if on_tc else "search_simt_kernel")
+    roof.update({"traffic": traffic, "kernel": kname,
                  "kernel_ms": kern_ms, "launches_per_step": launches_per_step, "rows_per_launch": rows_per_launch,
                  "kernel_share_of_step": kern_ms * launches_per_step / ms_step, "peak_source": peak_src,
-                 "algorithmic_unit": "2*K*D flop per row" if tensor_bound else "4*D+8 bytes per row"})
+                 "algorithmic_unit": "2*K*D flop per row" if tensor_bound else
+                 ("12*D+8 bytes per row" if fused else "4*D+8 bytes per row")})
 
     if rank == 0:
         cpu_rows = cpu_sample_rows(w)

@@ -49,10 +49,14 @@ struct FusedParams {
   int* counters;
 };
 
-// 32 score columns of one row -> candidate records in register slots.  A slot is reusable once its group
-// maximum falls below the running threshold (it can never be the argmax any more).
+// 32 score columns of one row.  Fast path: one compare against the admission threshold.  Slow path: every group
+// of 8 columns whose maximum reaches the threshold is appended, raw scores and all, to the lane's ring of
+// FZ_RING entries in shared memory (lane-interleaved 16-byte fields: conflict-free for any per-lane ring
+// position).  No mask is built here -- at the end of the row tile the survivors are re-tested against the FINAL
+// threshold.  Overwriting an entry remembers its maximum: if that could still matter the row is handed back.
+constexpr int FZ_RING = 4;
 __device__ __forceinline__ void fz_scan(const uint32_t (&v)[32], uint32_t code0, float margin, float& best, float& thr,
-                                        uint32_t (&sx)[4], float (&sg)[4], bool& overflow) {
+                                        uint4* ring, int lane, int& cnt, float& lost) {
   float gm[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -66,23 +70,18 @@ __device__ __forceinline__ void fz_scan(const uint32_t (&v)[32], uint32_t code0,
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       if (gm[g] >= thr) {
-        uint32_t mk = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mk |= (__uint_as_float(v[g * 8 + i]) >= thr) ? (1u << i) : 0u;
-        const uint32_t rec = (((code0 >> 3) + g) << 8) | mk;
-        bool placed = false;
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          const bool dead = sx[s] == FZ_EMPTY || sg[s] < thr;
-          if (!placed && dead) { sx[s] = rec; sg[s] = gm[g]; placed = true; }
-        }
-        overflow |= !placed;
+        uint4* e = ring + ((cnt & (FZ_RING - 1)) * 3) * 32 + lane;     // fields at e[0], e[32], e[64]
+        if (cnt >= FZ_RING) lost = fmaxf(lost, __uint_as_float(e[64].x));
+        e[0] = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
+        e[32] = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+        e[64] = make_uint4(__float_as_uint(gm[g]), (code0 >> 3) + g, 0u, 0u);
+        ++cnt;
       }
     }
   }
 }
 
-template <int D>
+template <int D, bool BF16>
 __global__ void __launch_bounds__(FZ_THREADS, 1)
 quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_constant__ CUtensorMap tmap_e,
                       const FusedParams p) {
@@ -98,7 +97,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t zf_smem = base;
   const uint32_t zb_smem = zf_smem + ZF_BYTES;
-  const uint32_t e_smem = zb_smem + 2 * ZB_BYTES;
+  const uint32_t e_smem = zb_smem + ZB_BYTES;               // ONE bf16 operand tile: shared memory goes to the rings
   const uint32_t misc = e_smem + static_cast<uint32_t>(p.stages) * TC_STAGE_BYTES;
   float* margin_s = reinterpret_cast<float*>(gen + (misc - base));                       // [2][256]
   float* ee_slots = margin_s + 2 * FZ_BM;                                                 // [8][128]
@@ -106,8 +105,9 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
   double* pair_score = reinterpret_cast<double*>(pair_list + FZ_NEPI * FZ_PAIRS);         // [8][64]
   int* hist_s = reinterpret_cast<int*>(pair_score + FZ_NEPI * FZ_PAIRS);                  // [FZ_HIST]
   double* red_s = reinterpret_cast<double*>(hist_s + FZ_HIST);                            // [16]
+  uint4* rings = reinterpret_cast<uint4*>(red_s + 16);                                    // [8][FZ_RING*3][32] x 16 B
   const uint32_t bar0 = misc + 2 * FZ_BM * 4 + FZ_NEPI * TC_BN * 4 + FZ_NEPI * FZ_PAIRS * 4 + FZ_NEPI * FZ_PAIRS * 8 +
-                        FZ_HIST * 4 + 16 * 8;
+                        FZ_HIST * 4 + 16 * 8 + FZ_NEPI * FZ_RING * 3 * 32 * 16;
   const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * 8, bar_tfull = bar0 + 16 * 8, bar_tempty = bar0 + 18 * 8;
   const uint32_t bar_zffull = bar0 + 20 * 8, bar_zfempty = bar0 + 21 * 8;
   const uint32_t bar_zbfull = bar0 + 22 * 8, bar_zbempty = bar0 + 24 * 8;    // [2] each
@@ -174,8 +174,8 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     uint32_t stage = 0, phase = 0, it = 0, tg = 0;
     const uint32_t zb_lo = umma_desc_lo(zb_smem), e_lo = umma_desc_lo(e_smem);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const uint32_t zb = it & 1;
-      mbar_wait(bar_zbfull + 8 * zb, (it >> 1) & 1);
+      const uint32_t zb = 0;
+      mbar_wait(bar_zbfull, it & 1);
       for (int t = 0; t < p.code_tiles; ++t, ++tg) {
         const uint32_t b = tg & 1;
         mbar_wait(bar_tempty + 8 * b, (tg >> 1) & 1);       // drained AND pre-loaded with -|e|^2/2
@@ -200,21 +200,21 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
           if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
         }
       }
-      if (elect_one()) tc_commit(bar_zbempty + 8 * zb);
+      if (elect_one()) tc_commit(bar_zbempty);
       __syncwarp();
     }
   } else if (warp >= 2 + FZ_NEPI) {
     // ============================== converters: fp32 tile -> bf16 operand tile + margins ==============================
     const int ct = (warp - 2 - FZ_NEPI) * 32 + lane;     // 0..63: rows ct, ct+64, ct+128, ct+192 of the tile
-    const float emax = p.mode == VQB200_MODE_BF16_INPUT ? p.level_meta[2] : p.level_meta[0];
+    const float emax = BF16 ? p.level_meta[2] : p.level_meta[0];
     const bool code_bad = p.level_meta[1] != 0.f;
-    const float coef = p.mode == VQB200_MODE_BF16_INPUT ? 2.f * static_cast<float>(D + 32) * 1.1920929e-7f
+    const float coef = BF16 ? 2.f * static_cast<float>(D + 32) * 1.1920929e-7f
                                                         : 2.f * 0.00391007f * 1.02f;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const uint32_t zb = it & 1;
+      const uint32_t zb = 0, mb = it & 1;
       mbar_wait(bar_zffull, it & 1);
-      mbar_wait(bar_zbempty + 8 * zb, ((it >> 1) & 1) ^ 1);
+      mbar_wait(bar_zbempty, (it & 1) ^ 1);             // the MMAs of the previous tile have retired
 #pragma unroll 1
       for (int rr = 0; rr < FZ_BM / (FZ_NCONV * 32); ++rr) {
         const int r = ct + rr * (FZ_NCONV * 32);
@@ -238,7 +238,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
           const int bslab = c / TC_KB, bj = (c % TC_KB) / 8;
           uint8_t* dst = gen + (zb_smem - base) + zb * ZB_BYTES + bslab * (FZ_BM * 128) + r * 128;
           *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(bj) ^ sw) << 4)) = pk;
-          if (p.mode == VQB200_MODE_BF16_INPUT) {
+          if (BF16) {
             const float2 a = __bfloat1622float2(p0), b2 = __bfloat1622float2(p1), c2 = __bfloat1622float2(p2),
                          d2 = __bfloat1622float2(p3);
             ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y + c2.x * c2.x + c2.y * c2.y + d2.x * d2.x + d2.y * d2.y;
@@ -248,11 +248,11 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
         }
         float m = coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f;
         if (code_bad || !(ss < __int_as_float(0x7f800000))) m = __int_as_float(0x7fc00000);   // NaN: exact path
-        margin_s[zb * FZ_BM + r] = m;
+        margin_s[mb * FZ_BM + r] = m;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
       __syncwarp();
-      if (lane == 0) { mbar_arrive(bar_zbfull + 8 * zb); mbar_arrive(bar_zfempty); }
+      if (lane == 0) { mbar_arrive(bar_zbfull); mbar_arrive(bar_zfempty); }
     }
   } else {
     // ============================== epilogue + finalise ==============================
@@ -260,6 +260,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     const int quarter = warp & 3, half = we >> 2;
     const int row_in_tile = half * 128 + quarter * 32;
     float* ee_slot = ee_slots + we * TC_BN;
+    uint4* ring = rings + we * (FZ_RING * 3 * 32);
     uint32_t* plist = pair_list + we * FZ_PAIRS;
     double* pscore = pair_score + we * FZ_PAIRS;
     const float kNegInf = __int_as_float(0xff800000);
@@ -280,7 +281,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       __syncwarp();
       *reinterpret_cast<float4*>(ee_slot + lane * 4) = make_float4(bias.v[0], bias.v[1], bias.v[2], bias.v[3]);
       __syncwarp();
-#pragma unroll
+#pragma unroll 2
       for (int hh = 0; hh < TC_BN / 16; ++hh) {
         uint32_t w[16];
 #pragma unroll
@@ -310,17 +311,15 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
 
     uint32_t tg = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const uint32_t zb = it & 1;
       const int64_t row0w = static_cast<int64_t>(item) * FZ_BM + row_in_tile;
       const int64_t row = row0w + lane;
       const bool row_ok = row < p.n_rows;
-      mbar_wait(bar_zbfull + 8 * zb, (it >> 1) & 1);          // margins of this tile are in shared memory
-      const float margin = row_ok ? margin_s[zb * FZ_BM + row_in_tile + lane] : __int_as_float(0x7fc00000);
+      mbar_wait(bar_zbfull, it & 1);                          // margins of this tile are in shared memory
+      const float margin = row_ok ? margin_s[(it & 1) * FZ_BM + row_in_tile + lane] : __int_as_float(0x7fc00000);
       float best = kNegInf;
       float thr = margin == margin ? best : margin;
-      uint32_t sx[4] = {FZ_EMPTY, FZ_EMPTY, FZ_EMPTY, FZ_EMPTY};
-      float sg[4] = {kNegInf, kNegInf, kNegInf, kNegInf};
-      bool overflow = false;
+      int rcnt = 0;
+      float lost = kNegInf;
 
       for (int t = 0; t < p.code_tiles; ++t, ++tg) {
         const uint32_t b = tg & 1;
@@ -331,6 +330,9 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
         mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + tcol + b * (2 * TC_BN);
+        // One 32-column chunk in registers at a time (measured: double-buffering the TMEM loads buys nothing
+        // here, the scan is bound by its own dependency chains).  After the LAST chunk is out of TMEM the
+        // buffer is re-armed with the bias of its next tile and handed back; only then is that chunk scanned.
         uint32_t v[32];
 #pragma unroll
         for (int ch = 0; ch < TC_BN / 32; ++ch) {
@@ -342,18 +344,36 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
           }
-          fz_scan(v, static_cast<uint32_t>(t * TC_BN + ch * 32), margin, best, thr, sx, sg, overflow);
+          fz_scan(v, static_cast<uint32_t>(t * TC_BN + ch * 32), margin, best, thr, ring, lane, rcnt, lost);
         }
       }
 
       // ---------------- finalise the 32 rows of this warp ----------------
+      // survivors: ring entries whose maximum reaches the FINAL threshold; their admit masks are built now,
+      // against that threshold, from the stored raw scores
       int ns = 0, ncodes = 0;
       uint32_t first = 0;
+      uint32_t sx[FZ_RING];
+      const bool overflow = lost >= thr;                        // an overwritten entry could still matter
 #pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const bool alive = sx[s] != FZ_EMPTY && sg[s] >= thr;
-        if (!alive) sx[s] = FZ_EMPTY;
-        else { if (ns == 0) first = sx[s]; ++ns; ncodes += __popc(sx[s] & 0xffu); }
+      for (int s = 0; s < FZ_RING; ++s) {
+        sx[s] = FZ_EMPTY;
+        if (s < rcnt) {
+          const uint4* e = ring + (s * 3) * 32 + lane;
+          const uint4 meta = e[64];
+          if (__uint_as_float(meta.x) >= thr) {
+            const uint4 a = e[0], b4 = e[32];
+            uint32_t mk = 0;
+            mk |= (__uint_as_float(a.x) >= thr) ? 1u : 0u;   mk |= (__uint_as_float(a.y) >= thr) ? 2u : 0u;
+            mk |= (__uint_as_float(a.z) >= thr) ? 4u : 0u;   mk |= (__uint_as_float(a.w) >= thr) ? 8u : 0u;
+            mk |= (__uint_as_float(b4.x) >= thr) ? 16u : 0u; mk |= (__uint_as_float(b4.y) >= thr) ? 32u : 0u;
+            mk |= (__uint_as_float(b4.z) >= thr) ? 64u : 0u; mk |= (__uint_as_float(b4.w) >= thr) ? 128u : 0u;
+            sx[s] = (meta.y << 8) | mk;
+            if (ns == 0) first = sx[s];
+            ++ns;
+            ncodes += __popc(mk);
+          }
+        }
       }
       bool resolved = false, multi = false;
       uint32_t my_idx = 0;
@@ -383,7 +403,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
         if (take) {
           int at = off0;
 #pragma unroll
-          for (int s = 0; s < 4; ++s) {
+          for (int s = 0; s < FZ_RING; ++s) {
             if (sx[s] != FZ_EMPTY) {
               uint32_t m = sx[s] & 0xffu;
               while (m) {
@@ -396,40 +416,63 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
         const unsigned tk = __ballot_sync(0xffffffffu, take);
         const int T = __shfl_sync(0xffffffffu, pre, 31 - __clz(tk));
         __syncwarp();
-        for (int pb = 0; pb < T; pb += GROUPS) {                // GROUPS pairs scored concurrently by lane groups
-          const int pi = pb + gi;
-          const bool ok = pi < T;
-          const uint32_t pr = ok ? plist[pi] : 0u;
-          const uint32_t code = pr & 0xffffffu;
-          const int64_t grow = row0w + (pr >> 24);
-          double dot = 0.0, ee = 0.0;
-          if (ok) {
+        // GROUPS pairs are scored concurrently by lane groups, SB such steps are batched so that their
+        // L2 loads are all in flight before the first FMA (the chain is latency-, not bandwidth-bound)
+        constexpr int SB = 4;
+        constexpr int SL = D / (LPV * 4);                     // float4 slices per lane per row
+        for (int pb = 0; pb < T; pb += GROUPS * SB) {
+          float4 zq4[SB][SL], eq4[SB][SL];
+          uint2 eb2[SB][SL];
+          bool okb[SB];
 #pragma unroll
-            for (int d = gl * 4; d < D; d += LPV * 4) {
-              float zv[4], ev[4];
-              *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(p.z + grow * D + d);
-              if (p.mode == VQB200_MODE_BF16_INPUT) {
-                const uint2 eb = *reinterpret_cast<const uint2*>(p.Eb + static_cast<int64_t>(code) * D + d);
-                ev[0] = __uint_as_float(eb.x << 16); ev[1] = __uint_as_float(eb.x & 0xffff0000u);
-                ev[2] = __uint_as_float(eb.y << 16); ev[3] = __uint_as_float(eb.y & 0xffff0000u);
+          for (int u = 0; u < SB; ++u) {
+            const int pi = pb + u * GROUPS + gi;
+            okb[u] = pi < T;
+            const uint32_t pr = okb[u] ? plist[pi] : 0u;
+            const uint32_t code = pr & 0xffffffu;
+            const int64_t grow = row0w + (pr >> 24);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) zv[q] = bf16_round(zv[q]);
-              } else {
-                *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(code) * D + d));
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
-                ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+            for (int sl = 0; sl < SL; ++sl) {
+              const int d = gl * 4 + sl * LPV * 4;
+              if (okb[u]) {
+                zq4[u][sl] = *reinterpret_cast<const float4*>(p.z + grow * D + d);
+                if (BF16)
+                  eb2[u][sl] = *reinterpret_cast<const uint2*>(p.Eb + static_cast<int64_t>(code) * D + d);
+                else
+                  eq4[u][sl] = __ldg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(code) * D + d));
               }
             }
           }
 #pragma unroll
-          for (int o = LPV >> 1; o > 0; o >>= 1) {
-            dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            ee += __shfl_xor_sync(0xffffffffu, ee, o);
+          for (int u = 0; u < SB; ++u) {
+            double dot = 0.0, ee = 0.0;
+            if (okb[u]) {
+#pragma unroll
+              for (int sl = 0; sl < SL; ++sl) {
+                float zv[4] = {zq4[u][sl].x, zq4[u][sl].y, zq4[u][sl].z, zq4[u][sl].w};
+                float ev[4];
+                if (BF16) {
+                  ev[0] = __uint_as_float(eb2[u][sl].x << 16); ev[1] = __uint_as_float(eb2[u][sl].x & 0xffff0000u);
+                  ev[2] = __uint_as_float(eb2[u][sl].y << 16); ev[3] = __uint_as_float(eb2[u][sl].y & 0xffff0000u);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) zv[q] = bf16_round(zv[q]);
+                } else {
+                  ev[0] = eq4[u][sl].x; ev[1] = eq4[u][sl].y; ev[2] = eq4[u][sl].z; ev[3] = eq4[u][sl].w;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
+                  ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+                }
+              }
+            }
+#pragma unroll
+            for (int o = LPV >> 1; o > 0; o >>= 1) {
+              dot += __shfl_xor_sync(0xffffffffu, dot, o);
+              ee += __shfl_xor_sync(0xffffffffu, ee, o);
+            }
+            if (okb[u] && gl == 0) pscore[pb + u * GROUPS + gi] = dot - 0.5 * ee;
           }
-          if (ok && gl == 0) pscore[pi] = dot - 0.5 * ee;
         }
         __syncwarp();
         if (take) {                                             // lexicographic (score, lowest index)
@@ -456,25 +499,43 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
         }
       }
       if (p.zq_out || p.zq_st_out || p.sqerr_sum) {
-#pragma unroll 2
-        for (int rb = 0; rb < 32; rb += GROUPS) {
-          const int rl = rb + gi;
-          const bool res = __shfl_sync(0xffffffffu, static_cast<int>(resolved), rl) != 0;
-          const uint32_t code = __shfl_sync(0xffffffffu, my_idx, rl);
-          const int64_t grow = row0w + rl;
-          if (res) {
+        constexpr int OB = 4;                                   // row-steps whose loads are issued together
+        constexpr int SL = D / (LPV * 4);
+#pragma unroll 1
+        for (int rb = 0; rb < 32; rb += GROUPS * OB) {
+          float4 e4[OB][SL], z4[OB][SL];
+          bool res[OB];
 #pragma unroll
-            for (int d = gl * 4; d < D; d += LPV * 4) {
-              const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(code) * D + d));
-              const float4 z4 = ld_stream(reinterpret_cast<const float4*>(p.z + grow * D + d));
+          for (int u = 0; u < OB; ++u) {
+            const int rl = rb + u * GROUPS + gi;
+            res[u] = rl < 32 && __shfl_sync(0xffffffffu, static_cast<int>(resolved), rl & 31) != 0;
+            const uint32_t code = __shfl_sync(0xffffffffu, my_idx, rl & 31);
+            const int64_t grow = row0w + rl;
+#pragma unroll
+            for (int sl = 0; sl < SL; ++sl) {
+              const int d = gl * 4 + sl * LPV * 4;
+              if (res[u]) {
+                e4[u][sl] = __ldg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(code) * D + d));
+                z4[u][sl] = ld_stream(reinterpret_cast<const float4*>(p.z + grow * D + d));
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < OB; ++u) {
+            if (!res[u]) continue;
+            const int64_t grow = row0w + rb + u * GROUPS + gi;
+#pragma unroll
+            for (int sl = 0; sl < SL; ++sl) {
+              const int d = gl * 4 + sl * LPV * 4;
+              const float4 e = e4[u][sl], zz = z4[u][sl];
               float4 df;
-              df.x = __fsub_rn(e4.x, z4.x); df.y = __fsub_rn(e4.y, z4.y);
-              df.z = __fsub_rn(e4.z, z4.z); df.w = __fsub_rn(e4.w, z4.w);
-              if (p.zq_out) st_stream(reinterpret_cast<float4*>(p.zq_out + grow * D + d), e4);
+              df.x = __fsub_rn(e.x, zz.x); df.y = __fsub_rn(e.y, zz.y);
+              df.z = __fsub_rn(e.z, zz.z); df.w = __fsub_rn(e.w, zz.w);
+              if (p.zq_out) st_stream(reinterpret_cast<float4*>(p.zq_out + grow * D + d), e);
               if (p.zq_st_out) {
                 float4 o;
-                o.x = __fadd_rn(z4.x, df.x); o.y = __fadd_rn(z4.y, df.y);
-                o.z = __fadd_rn(z4.z, df.z); o.w = __fadd_rn(z4.w, df.w);
+                o.x = __fadd_rn(zz.x, df.x); o.y = __fadd_rn(zz.y, df.y);
+                o.z = __fadd_rn(zz.z, df.z); o.w = __fadd_rn(zz.w, df.w);
                 st_stream(reinterpret_cast<float4*>(p.zq_st_out + grow * D + d), o);
               }
               err_acc = fmaf(df.x, df.x, err_acc); err_acc = fmaf(df.y, df.y, err_acc);
@@ -558,8 +619,8 @@ bool fused_supported(int64_t N, int K, int D) {
 size_t fused_workspace_bytes(int64_t N) { return 256 + fz_align(static_cast<size_t>(N) * 4) + fz_align(static_cast<size_t>(N) * 8); }
 
 static int fused_smem_bytes(int D, int stages) {
-  return 1024 + FZ_BM * D * 4 + 2 * FZ_BM * D * 2 + stages * TC_STAGE_BYTES + 2 * FZ_BM * 4 + FZ_NEPI * TC_BN * 4 +
-         FZ_NEPI * FZ_PAIRS * 4 + FZ_NEPI * FZ_PAIRS * 8 + FZ_HIST * 4 + 16 * 8 + 256;
+  return 1024 + FZ_BM * D * 4 + FZ_BM * D * 2 + stages * TC_STAGE_BYTES + 2 * FZ_BM * 4 + FZ_NEPI * TC_BN * 4 +
+         FZ_NEPI * FZ_PAIRS * 4 + FZ_NEPI * FZ_PAIRS * 8 + FZ_HIST * 4 + 16 * 8 + FZ_NEPI * FZ_RING * 3 * 32 * 16 + 256;
 }
 
 int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
@@ -584,7 +645,9 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
 
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(quantize_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(quantize_fused_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(quantize_fused_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return status_of(e);
     attr_done = true;
   }
@@ -603,7 +666,8 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
   p.fb_rows = fb_rows; p.fb_packed = fb_packed; p.counters = counters;
   const int grid = p.row_tiles < kNumSMs ? p.row_tiles : kNumSMs;
   timing_mark_begin(s);
-  quantize_fused_kernel<64><<<grid, FZ_THREADS, fused_smem_bytes(D, stages), s>>>(map_zf, map_e, p);
+  if (bf) quantize_fused_kernel<64, true><<<grid, FZ_THREADS, fused_smem_bytes(D, stages), s>>>(map_zf, map_e, p);
+  else quantize_fused_kernel<64, false><<<grid, FZ_THREADS, fused_smem_bytes(D, stages), s>>>(map_zf, map_e, p);
   timing_mark_end(s);
   e = cudaGetLastError();
   if (e != cudaSuccess) return status_of(e);

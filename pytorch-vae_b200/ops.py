@@ -12,6 +12,7 @@ from ._cabi import check, lib, ptr, stream_ptr
 
 # kernels launched by this process through the library (bench.py reports the delta per step)
 _launches = 0
+last_fused_workspace = None
 
 
 def launch_count() -> int:
@@ -97,6 +98,8 @@ def quantize_fused(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st
                                     cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, mode, 0,
                                     ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist),
                                     ptr(row_mask), ptr(ws), ws_bytes, stream_ptr()), "vqb200_quantize_fused")
+    global last_fused_workspace
+    last_fused_workspace = ws          # counters[0] = rows handed to the exact kernel (read lazily: no sync here)
     _count(3)     # fused kernel, exact hand-back kernel, fix-up kernel
 
 
