@@ -264,8 +264,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
 #pragma unroll
       for (int j = 0; j < BPL; ++j) ee_slot[lane * BPL + j] = bias.v[j];
       __syncwarp();
-#pragma unroll 2
-      for (int hh = 0; hh < WCOLS / 16; ++hh) {          // 16 columns per store keeps register pressure low
+#pragma unroll
+      for (int hh = 0; hh < WCOLS / 16; ++hh) {
         uint32_t w[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
