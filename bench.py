@@ -170,7 +170,11 @@ def run_b200(args, w):
     z_pin = torch.from_numpy(z_host).pin_memory()
     z = z_pin.to(dev)
 
+    graphed = vq.GraphedForward(q, z) if args.graph else None
+
     def step():
+        if graphed is not None:
+            return graphed(z)
         with torch.no_grad():
             return q(z, do_ema_update=False)
 
@@ -289,7 +293,7 @@ def run_b200(args, w):
             "config": {"workload": w["desc"], "K": K, "D": D, "levels": L, "rows_per_gpu": N,
                        "search_mode": args.mode, "l2": "inputs+outputs per step exceed the 126 MB L2"
                        if N * D * 12 > 126e6 else "L2-resident working set (no flush)",
-                       "parallelism": f"rows sharded x{world}, codebook replicated"},
+                       "parallelism": f"rows sharded x{world}, codebook replicated", "cuda_graph": bool(args.graph)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": N * D * 4,
                     "d2h_bytes_per_step": out[2].numel() * 8 + 8, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "clocks": clk, "roofline": roof,
@@ -309,6 +313,7 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
     ap.add_argument("--mode", choices=["fp32", "bf16_input"], default="fp32")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--graph", action="store_true", help="replay the forward as one CUDA graph (launch-bound shapes)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

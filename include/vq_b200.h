@@ -116,6 +116,15 @@ VQB200_API int vqb200_quantize_fused(const float* z, int64_t N, int D, const flo
                           double* sqerr_sum, int32_t* hist, const uint8_t* row_mask, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* vqb200_search + vqb200_gather for one single-level codebook in ONE call: on the tensor path the gather of each
+ * chunk of rows is queued behind that chunk's re-rank, so it overlaps the tensor kernel of the next chunk.
+ * Workspace as vqb200_search_workspace_bytes.  E_full / K_total: the whole codebook (idx are global ids). */
+VQB200_API int vqb200_quantize(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16,
+                    const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K, int mode,
+                    int64_t idx_offset, int64_t* idx_out, const float* E_full, int K_total, float* zq_out,
+                    float* zq_st_out, double* sqerr_sum, int32_t* hist, const uint8_t* row_mask, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 /* Straight-through value and commitment partial sum from z and an already-summed z_q
  * (the RVQ tail, models/vq_vae.py:263 and :1293). */
 VQB200_API int vqb200_st_loss(const float* z, const float* zq, int64_t n_elems, float* zq_st_out,

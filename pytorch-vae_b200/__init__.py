@@ -7,5 +7,6 @@ there is no fallback implementation.
 from . import _cabi, ops  # noqa: F401  (loads the shared library; ImportError if absent)
 from .quantizer import VectorQuantizer, VectorQuantizerEMA  # noqa: F401
 from .integration import install, uninstall  # noqa: F401
+from .graphs import GraphedForward  # noqa: F401
 
-__all__ = ["VectorQuantizerEMA", "VectorQuantizer", "install", "uninstall", "ops"]
+__all__ = ["VectorQuantizerEMA", "VectorQuantizer", "GraphedForward", "install", "uninstall", "ops"]

@@ -39,6 +39,7 @@ SIGNATURES = {
     "vqb200_quantize_fused_supported": (_i, [_i64, _i, _i, _i]),
     "vqb200_quantize_fused_workspace_bytes": (_sz, [_i64, _i, _i, _i]),
     "vqb200_quantize_fused": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _i, _i, _i64, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "vqb200_quantize": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _i, _i, _i64, _p, _p, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "vqb200_gather": (_i, [_p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p]),
     "vqb200_st_loss": (_i, [_p, _p, _i64, _p, _p, _p]),
     "vqb200_stats_finalize": (_i, [_p, _i, _f, _p, _d, _p, _p, _p, _p]),

@@ -159,6 +159,33 @@ int vqb200_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
                                static_cast<cudaStream_t>(stream));
 }
 
+int vqb200_quantize(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
+                    const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
+                    int64_t* idx_out, const float* E_full, int K_total, float* zq_out, float* zq_st_out,
+                    double* sqerr_sum, int32_t* hist, const uint8_t* row_mask, void* workspace, size_t workspace_bytes,
+                    void* stream) {
+  VQ_REQUIRE(N >= 0 && K > 0 && K_total > 0, VQB200_EINVAL);
+  if (N == 0) return VQB200_OK;
+  VQ_REQUIRE(z && idx_out && E && E_bf16 && ee_half && ee_half_bf16 && level_meta && E_full, VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(E_full) && aligned16(zq_out) && aligned16(zq_st_out), VQB200_EALIGN);
+  VQ_REQUIRE(workspace_bytes >= vqb200_search_workspace_bytes(N, K, D, mode) && workspace, VQB200_EWORKSPACE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  if (tc_supported(N, K, D)) {
+    VQ_REQUIRE(aligned16(E_bf16) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, VQB200_EALIGN);
+    GatherArgs ga{E_full, K_total, zq_out, zq_st_out, sqerr_sum, hist, row_mask};
+    return launch_search_tc(z, N, D, E, E_bf16, ee_half, ee_half_bf16, level_meta, K, mode, idx_offset, idx_out, workspace,
+                            workspace_bytes, s, &ga);
+  }
+  timing_mark_begin(s);
+  int st = launch_search_simt(z, nullptr, N, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0, idx_offset, idx_out, nullptr, s);
+  timing_mark_end(s);
+  if (st != VQB200_OK) return st;
+  return launch_gather(z, E_full, idx_out, N, D, K_total, zq_out, 0, zq_st_out, nullptr, sqerr_sum, hist, row_mask, s);
+}
+
 int vqb200_st_loss(const float* z, const float* zq, int64_t n_elems, float* zq_st_out, double* sqerr_sum,
                    void* stream) {
   VQ_REQUIRE(n_elems >= 0, VQB200_EINVAL);

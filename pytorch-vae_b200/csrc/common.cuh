@@ -74,9 +74,20 @@ int launch_search_simt_list(const float* z, const int32_t* row_list, const int* 
 bool tc_supported(int64_t N, int K, int D);
 size_t tc_workspace_bytes(int64_t N, int K, int D);
 int tc_launches(int64_t N, int K, int D);
+// optional gather stage appended to each chunk of the tensor-core search pipeline
+struct GatherArgs {
+  const float* E_full;      // [K_total, D] (idx_out holds GLOBAL ids)
+  int K_total;
+  float* zq_out;
+  float* zq_st_out;
+  double* sqerr_sum;
+  int32_t* hist;
+  const uint8_t* row_mask;
+};
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
-                     int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s);
+                     int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                     const GatherArgs* ga = nullptr);
 bool fused_supported(int64_t N, int K, int D);
 size_t fused_workspace_bytes(int64_t N);
 int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,

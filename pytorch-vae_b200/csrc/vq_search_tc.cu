@@ -664,7 +664,7 @@ static TcSet carve(uint8_t* w, int64_t cap, int D, int BM) {
 // SM, so they co-reside.  Everything is joined back into the caller's stream before returning.
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
-                     int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                     int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s, const GatherArgs* ga) {
   TcPlan pl;
   if (!tc_plan(N, K, D, &pl)) return VQB200_ESHAPE;
   if (workspace_bytes < tc_workspace_bytes(N, K, D)) return VQB200_EWORKSPACE;
@@ -763,6 +763,13 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     if (st != VQB200_OK) return st;
     fb_unpack_kernel<<<64, 256, 0, s_rr>>>(w.fb_rows, w.fb_packed, w.counters, idx_out + r0);
     VQ_CUDA(cudaGetLastError());
+    if (ga) {   // stage 4 (optional): gather / straight-through / loss / histogram of this chunk, behind its re-rank
+      const int gs = launch_gather(zc, ga->E_full, idx_out + r0, rows, D, ga->K_total,
+                                   ga->zq_out ? ga->zq_out + r0 * D : nullptr, 0,
+                                   ga->zq_st_out ? ga->zq_st_out + r0 * D : nullptr, nullptr, ga->sqerr_sum, ga->hist,
+                                   ga->row_mask ? ga->row_mask + r0 : nullptr, s_rr);
+      if (gs != VQB200_OK) return gs;
+    }
     if (piped) VQ_CUDA(cudaEventRecord(pipe->done[b], s_rr));
   }
   if (piped) {                                         // join: the caller's stream sees every chunk finished

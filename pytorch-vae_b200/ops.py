@@ -103,6 +103,25 @@ def quantize_fused(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st
     _count(3)     # fused kernel, exact hand-back kernel, fix-up kernel
 
 
+def quantize(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st_out=None, sqerr_sum=None, hist=None,
+             row_mask=None):
+    """Single-level search + gather in one call; on the tensor path the gather of each chunk of rows overlaps the
+    tensor kernel of the next chunk (three-stream pipeline inside the library)."""
+    _need_cuda(z, E, idx_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    K = cache.K_per
+    ws_bytes = lib.vqb200_search_workspace_bytes(N, K, D, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    check(lib.vqb200_quantize(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), cache.ee_half.data_ptr(),
+                              cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, mode, 0,
+                              ptr(idx_out), ptr(E), E.shape[0], ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist),
+                              ptr(row_mask), ptr(ws), ws_bytes, stream_ptr()), "vqb200_quantize")
+    n_search = search_launches(N, K, D, mode)
+    chunks = max(1, n_search // 5) if lib.vqb200_search_path(N, K, D, mode) else 1
+    _count(n_search + chunks)
+
+
 def gather(z, E, idx, zq_out=None, accumulate=False, zq_st_out=None, residual_out=None, sqerr_sum=None,
            hist=None, row_mask=None):
     _need_cuda(z, E, idx)

@@ -275,10 +275,9 @@ class VectorQuantizerEMA(nn.Module):
                 if ops.fused_supported(N, self.K, D, mode):  # one kernel: search + gather + loss + histogram
                     ops.quantize_fused(flat, E, cache, mode, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
                                        hist=hist, row_mask=valid_u8)
-                else:
-                    ops.search(flat, E, cache, 0, mode, idx)
-                    ops.gather(flat, E, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist,
-                               row_mask=valid_u8)            # z_q is gathered BEFORE the EMA mutates E (:189 -> :193)
+                else:                                        # search + gather, chunk-pipelined on the tensor path
+                    ops.quantize(flat, E, cache, mode, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
+                                 hist=hist, row_mask=valid_u8)   # z_q is gathered BEFORE the EMA mutates E (:189 -> :193)
                 if ema_ok:
                     self._ema_update(flat, idx, valid_u8)
             self._finalize_stats(hist, float(N), sqerr, N * D, stats3)

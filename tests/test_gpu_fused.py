@@ -82,3 +82,28 @@ def test_fused_hard_rows_and_mask(vq):
     flat = z.reshape(-1, D)
     ok = np.isfinite(flat).all(1)
     assert np.array_equal(idx_f.cpu().numpy().reshape(-1)[ok], O.nearest_code64(flat[ok], E))
+
+
+def test_graphed_forward_matches_eager(vq):
+    """One CUDA graph for the whole residual forward (launch-bound stage-2 shape) == eager results."""
+    dev = torch.device("cuda:0")
+    E, z = large_case_inputs(77, 256, 128, 3, 16, 64)
+    q = vq.VectorQuantizerEMA(256, 128, num_quantizers=3, print_init=False).to(dev).eval()
+    q.embedding.copy_(torch.from_numpy(E).to(dev))
+    zt = torch.from_numpy(z).to(dev)
+    with torch.no_grad():
+        st, zq, idx, stats = [t.clone() for t in q(zt, do_ema_update=False)]
+    g = vq.GraphedForward(q, zt)
+    for _ in range(2):
+        st2, zq2, idx2, stats2 = g(zt)
+    assert torch.equal(idx, idx2) and torch.equal(zq, zq2) and torch.equal(st, st2)
+    assert torch.allclose(stats, stats2)
+    # external codebook write is picked up by the captured cache refresh
+    q.embedding.mul_(-1.0)
+    with torch.no_grad():
+        idx_neg = q(zt, do_ema_update=False)[2].clone()
+    assert torch.equal(g(zt)[2], idx_neg)
+    z_other = torch.randn_like(zt)
+    with torch.no_grad():
+        ref = q(z_other, do_ema_update=False)[2].clone()
+    assert torch.equal(g(z_other)[2], ref)
