@@ -245,7 +245,8 @@ def run_b200(args, w):
     mode = vq.quantizer._MODES[args.mode]
     lib.vqb200_timing_enable(1)
     for _ in range(max(3, min(args.steps, 10))):
-        step()
+        with torch.no_grad():                                    # eager even under --graph: the hooks live in the library calls
+            q(z, do_ema_update=False)
     torch.cuda.synchronize()
     lib.vqb200_timing_enable(0)
     tot, nl = ctypes.c_float(0), ctypes.c_int(0)

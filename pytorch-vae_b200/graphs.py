@@ -10,6 +10,8 @@ from __future__ import annotations
 
 import torch
 
+from . import ops
+
 
 class GraphedForward:
     """``g = GraphedForward(q, z_example); z_q_st, z_q, idx, stats = g(z)`` (eval mode, no EMA update)."""
@@ -29,14 +31,17 @@ class GraphedForward:
                 quantizer(self.z, do_ema_update=False, mask=self.mask)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
+        before = ops.launch_count()
         with torch.no_grad(), torch.cuda.graph(self.graph):
             if quantizer._cache is not None:
                 quantizer._cache.key = None                     # capture the cache refresh: the graph re-derives it
             self.out = quantizer(self.z, do_ema_update=False, mask=self.mask)
+        self.kernels = ops.launch_count() - before             # kernels of this library inside one replay
 
     def __call__(self, z_e: torch.Tensor):
         if z_e.shape != self.z.shape:
             raise RuntimeError(f"captured shape {tuple(self.z.shape)}, got {tuple(z_e.shape)}")
         self.z.copy_(z_e)
         self.graph.replay()
+        ops._count(self.kernels)
         return self.out
