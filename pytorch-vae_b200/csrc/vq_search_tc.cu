@@ -359,6 +359,224 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------ CTA-pair variant
+// Same search, issued as tcgen05.mma.cta_group::2: a cluster of two CTAs (one SM pair) computes a
+// [256 rows x 256 codes] tile per MMA sweep; each CTA stages ITS 128 rows of z and ITS 128 codes of the tile,
+// and receives its 128 rows x 256 columns of accumulator in its own TMEM.  Per CTA a K=16 step moves
+// 4 KB (A) + 4 KB (B) of shared-memory operands per 128 cycles instead of 8 KB per 64 cycles in the 1-CTA
+// kernel, whose M=128 x N=128 MMAs sit exactly at the 128 B/clk shared-memory limit and so run at ~60 %.
+// Protocol: the leader CTA (rank 0) issues every MMA.  Both CTAs' TMA loads credit the LEADER's full / z-full
+// barriers; MMA completions are committed with a multicast arrive to the barriers at the same offsets in both
+// CTAs; both CTAs' epilogue warps arrive (remotely for the peer) on the leader's tmem-empty barriers.
+constexpr int P2_ROWS = 128;        // rows per CTA
+constexpr int P2_BN = 256;          // codes per pair tile (each CTA stages 128 of them)
+constexpr int P2_CS = 2;            // column slices: 8 epilogue warps = 4 lane quarters x 2 slices of 128 columns
+constexpr int P2_NEPI = 8;
+constexpr int P2_WCOLS = P2_BN / P2_CS;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + P2_NEPI * 32, 1)
+search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
+                  const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int KBLK = p.D / TC_KB;
+  const uint32_t z_bytes = static_cast<uint32_t>(P2_ROWS) * p.D * 2;
+  const uint32_t z_smem = base;
+  const uint32_t e_smem = z_smem + p.zbufs * z_bytes;
+  const uint32_t ee_smem = e_smem + static_cast<uint32_t>(p.stages) * TC_STAGE_BYTES;   // [8][128] fp32 staging
+  const uint32_t bar0 = ee_smem + P2_NEPI * P2_WCOLS * 4;
+  const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * 8, bar_tfull = bar0 + 16 * 8, bar_tempty = bar0 + 18 * 8;
+  const uint32_t bar_zfull = bar0 + 20 * 8, bar_zempty = bar0 + 22 * 8, tmem_slot = bar0 + 24 * 8;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 2 * P2_NEPI);   // both CTAs' epilogue warps
+      mbar_init(bar_zfull + 8 * b, 1); mbar_init(bar_zempty + 8 * b, 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {      // the same warp of BOTH CTAs allocates for the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // peer barriers are initialised before any remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  const int n_items = p.row_tiles;                     // 256-row tiles, one per pair step
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs) ==============================
+    uint32_t stage = 0, phase = 0, it = 0;
+    for (int item = pair; item < n_items; item += n_pairs, ++it) {
+      const uint32_t zb = p.zbufs == 2 ? (it & 1) : 0;
+      const uint32_t zuse = p.zbufs == 2 ? (it >> 1) : it;
+      mbar_wait(bar_zempty + 8 * zb, (zuse & 1) ^ 1);
+      if (elect_one()) {
+        if (leader) mbar_expect_tx(bar_zfull + 8 * zb, 2 * z_bytes);           // its own rows + the peer's
+        const uint32_t zf = map_to_cta(bar_zfull + 8 * zb, 0);
+        for (int kb = 0; kb < KBLK; ++kb)
+          tma_load_2d_pair(z_smem + zb * z_bytes + kb * (P2_ROWS * 128), &tmap_z, zf, kb * TC_KB,
+                           item * 2 * P2_ROWS + static_cast<int>(crank) * P2_ROWS);
+      }
+      __syncwarp();
+      for (int t = 0; t < p.code_tiles; ++t) {
+        for (int kb = 0; kb < KBLK; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(bar_full + 8 * stage, 2 * TC_STAGE_BYTES);
+            tma_load_2d_pair(e_smem + stage * TC_STAGE_BYTES, &tmap_e, map_to_cta(bar_full + 8 * stage, 0), kb * TC_KB,
+                             t * P2_BN + static_cast<int>(crank) * (P2_BN / 2));
+          }
+          __syncwarp();
+          if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer (leader CTA only) ==============================
+    if (leader) {
+      uint32_t stage = 0, phase = 0, it = 0, tg = 0;
+      const uint32_t z_lo = umma_desc_lo(z_smem), e_lo = umma_desc_lo(e_smem);
+      for (int item = pair; item < n_items; item += n_pairs, ++it) {
+        const uint32_t zb = p.zbufs == 2 ? (it & 1) : 0;
+        const uint32_t zuse = p.zbufs == 2 ? (it >> 1) : it;
+        mbar_wait(bar_zfull + 8 * zb, zuse & 1);
+        for (int t = 0; t < p.code_tiles; ++t, ++tg) {
+          const uint32_t b = tg & 1;
+          mbar_wait(bar_tempty + 8 * b, (tg >> 1) & 1);
+          tc_fence_after();
+          for (int kb = 0; kb < KBLK; ++kb) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a0 = z_lo + ((zb * z_bytes + kb * (P2_ROWS * 128)) >> 4);
+              const uint32_t b0 = e_lo + ((stage * TC_STAGE_BYTES) >> 4);
+              const uint32_t d_tmem = tmem_base + b * P2_BN;
+#pragma unroll
+              for (int k = 0; k < TC_KB / 16; ++k)
+                tc_mma_bf16_pair(d_tmem, umma_desc(a0 + k * 2), umma_desc(b0 + k * 2), kIdescPair, 1u);
+              tc_commit_pair(bar_empty + 8 * stage);
+              if (kb == KBLK - 1) tc_commit_pair(bar_tfull + 8 * b);
+            }
+            __syncwarp();
+            if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (elect_one()) tc_commit_pair(bar_zempty + 8 * zb);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ============================== epilogue (both CTAs, own TMEM) ==============================
+    const int we = warp - 2;
+    const int quarter = warp & 3;
+    const int cs = we >> 2;
+    float* ee_slot = reinterpret_cast<float*>(gen + (ee_smem - base)) + we * P2_WCOLS;
+    const float kNegInf = __int_as_float(0xff800000);
+    const uint32_t tcol = (static_cast<uint32_t>(quarter * 32) << 16) + cs * P2_WCOLS;
+    const uint32_t tempty0 = map_to_cta(bar_tempty, 0);        // the leader's tmem-empty barriers
+    constexpr int BPL = P2_WCOLS / 32;
+    struct Bias { float v[BPL]; };
+    auto load_bias = [&](int t) -> Bias {
+      Bias r;
+#pragma unroll
+      for (int j = 0; j < BPL; ++j) {
+        const int c = t * P2_BN + cs * P2_WCOLS + lane * BPL + j;
+        r.v[j] = (t >= 0 && c < p.K) ? -p.ee_half[c] : kNegInf;
+      }
+      return r;
+    };
+    auto preload = [&](const Bias& bias, uint32_t b) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < BPL; ++j) ee_slot[lane * BPL + j] = bias.v[j];
+      __syncwarp();
+#pragma unroll
+      for (int hh = 0; hh < P2_WCOLS / 16; ++hh) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          const float4 q4 = *reinterpret_cast<const float4*>(ee_slot + hh * 16 + j);
+          w[j + 0] = __float_as_uint(q4.x); w[j + 1] = __float_as_uint(q4.y);
+          w[j + 2] = __float_as_uint(q4.z); w[j + 3] = __float_as_uint(q4.w);
+        }
+        TC_ST16(tmem_base + tcol + b * P2_BN + hh * 16, w);
+      }
+      tc_wait_st();
+    };
+    const int64_t total_tiles = static_cast<int64_t>((n_items - pair + n_pairs - 1) / n_pairs) * p.code_tiles;
+    int64_t la = 0;
+    auto la_next = [&]() -> int { return la < total_tiles ? static_cast<int>((la++) % p.code_tiles) : (la++, -1); };
+    for (uint32_t b = 0; b < 2; ++b) {
+      const int tt = la_next();
+      if (tt >= 0) preload(load_bias(tt), b);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * b);
+    }
+    int t_ahead = la_next();
+    Bias bias_next = load_bias(t_ahead);
+
+    uint32_t tg = 0;
+    for (int item = pair; item < n_items; item += n_pairs) {
+      const int64_t row = static_cast<int64_t>(item) * 2 * P2_ROWS + crank * P2_ROWS + quarter * 32 + lane;
+      const bool row_ok = row < p.n_rows;
+      const float margin = row_ok ? p.margin[row] : __int_as_float(0x7fc00000);
+      const int64_t sub = row_ok ? row * P2_CS + cs : 0;
+      uint2* cand_row = p.cand + sub * TC_SLOTS;
+      float best = kNegInf;
+      float thr = margin == margin ? best : margin;
+      int cnt = 0;
+      for (int t = 0; t < p.code_tiles; ++t, ++tg) {
+        const uint32_t b = tg & 1;
+        const Bias bias = bias_next;
+        const int t_cur_ahead = t_ahead;
+        t_ahead = la_next();
+        bias_next = load_bias(t_ahead);
+        mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + tcol + b * P2_BN;
+        uint32_t v[32];
+        const uint32_t code_t = static_cast<uint32_t>(t * P2_BN + cs * P2_WCOLS);
+#pragma unroll
+        for (int ch = 0; ch < P2_WCOLS / 32; ++ch) {
+          TC_LD32(taddr + ch * 32, v);
+          tc_wait_ld();
+          if (ch == P2_WCOLS / 32 - 1) {
+            if (t_cur_ahead >= 0) preload(bias, b);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * b);
+          }
+          epi_scan(v, code_t + ch * 32, margin, best, thr, cnt, cand_row);
+        }
+      }
+      if (row_ok) {
+        p.cnt[sub] = cnt;
+        p.best[sub] = best;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // neither CTA leaves while the peer may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------ exact re-rank
 // One kernel, two granularities.  Each warp takes 32 rows.
 //  (1) every THREAD prunes its row's candidate records against the final maximum -- loads only, no
@@ -580,7 +798,8 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // (row, split) slots: code splits are only used while row_tiles * ksplit <= #SMs
 static size_t tc_slots(int64_t rows, int BM) {
   const size_t few = static_cast<size_t>(kNumSMs) * BM;
-  return (static_cast<size_t>(rows) > few ? static_cast<size_t>(rows) : few) * tc_cs(BM);   // x column slices
+  (void)BM;
+  return (static_cast<size_t>(rows) > few ? static_cast<size_t>(rows) : few) * 2;   // x column slices (<= 2)
 }
 
 // Workspace of ONE chunk; two chunks' worth is laid out when the rows span several chunks (software pipeline).
@@ -684,6 +903,19 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   if (!make_map(&map_e, E_bf16, K, D, TC_BN)) return VQB200_EDRIVER;
   const int code_tiles = (K + TC_BN - 1) / TC_BN;
 
+  // CTA-pair kernel (cta_group::2): large row counts only (no code splits), z tile of 128 rows must fit
+  const char* env2 = std::getenv("VQB200_TC2");
+  const bool want2 = !(env2 && env2[0] == '0');
+  const int z2 = P2_ROWS * D * 2;
+  const int zbufs2 = (2 * z2 + 4 * TC_STAGE_BYTES + P2_NEPI * P2_WCOLS * 4 + 2048 <= TC_SMEM_LIMIT) ? 2 : 1;
+  int stages2 = (TC_SMEM_LIMIT - (1024 + zbufs2 * z2 + P2_NEPI * P2_WCOLS * 4 + 256)) / TC_STAGE_BYTES;
+  if (stages2 > 8) stages2 = 8;
+  const bool use2 = want2 && stages2 >= 3 && K >= P2_BN && cap >= static_cast<int64_t>(kNumSMs / 2) * 2 * P2_ROWS;
+  static bool attr2_done = false;
+  if (use2 && !attr2_done) {
+    VQ_CUDA(cudaFuncSetAttribute(search_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    attr2_done = true;
+  }
   static bool attr_done[2] = {false, false};
   if (!attr_done[pl.BM == 256]) {
     VQ_CUDA(pl.BM == 256
@@ -718,16 +950,32 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
 
     // ---- stage 2: tensor-core candidates (caller's stream)
     CUtensorMap map_z;
-    if (!make_map(&map_z, w.zb, rows, D, pl.BM)) return VQB200_EDRIVER;
     TcParams p;
     p.n_rows = rows; p.D = D; p.K = K;
+    p.ee_half = bf ? ee_half_bf16 : ee_half;
+    p.margin = w.margin; p.cand = w.cand; p.cnt = w.cnt; p.best = w.best;
+    const bool pair_now = use2 && rows >= static_cast<int64_t>(kNumSMs / 2) * 2 * P2_ROWS;
+    int nsub;
+    if (pair_now) {
+      if (!make_map(&map_z, w.zb, rows, D, P2_ROWS)) return VQB200_EDRIVER;
+      p.row_tiles = static_cast<int>((rows + 2 * P2_ROWS - 1) / (2 * P2_ROWS));
+      p.ksplit = 1; p.tiles_per_split = (K + P2_BN - 1) / P2_BN;
+      p.code_tiles = (K + P2_BN - 1) / P2_BN;
+      p.stages = stages2; p.zbufs = zbufs2;
+      nsub = P2_CS;
+      const int pairs = p.row_tiles < kNumSMs / 2 ? p.row_tiles : kNumSMs / 2;
+      const int smem2 = 1024 + zbufs2 * z2 + stages2 * TC_STAGE_BYTES + P2_NEPI * P2_WCOLS * 4 + 256;
+      timing_mark_begin(s);
+      search_tc2_kernel<<<2 * pairs, 64 + P2_NEPI * 32, smem2, s>>>(map_z, map_e, p);
+      timing_mark_end(s);
+    } else {
+    if (!make_map(&map_z, w.zb, rows, D, pl.BM)) return VQB200_EDRIVER;
     p.row_tiles = static_cast<int>((rows + pl.BM - 1) / pl.BM);
     p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, pl.ksplit_max, &p.tiles_per_split);
     p.code_tiles = code_tiles;
     p.stages = pl.stages;
     p.zbufs = pl.zbufs;
-    p.ee_half = bf ? ee_half_bf16 : ee_half;
-    p.margin = w.margin; p.cand = w.cand; p.cnt = w.cnt; p.best = w.best;
+    nsub = p.ksplit * tc_cs(pl.BM);
     const int items = p.row_tiles * p.ksplit;
     const int grid = items < kNumSMs ? items : kNumSMs;
     timing_mark_begin(s);
@@ -736,6 +984,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     else
       search_tc_kernel<128><<<grid, 64 + 128 * tc_cs(128), pl.smem_bytes, s>>>(map_z, map_e, p);
     timing_mark_end(s);
+    }
     VQ_CUDA(cudaGetLastError());
     if (piped) {
       VQ_CUDA(cudaEventRecord(pipe->tc[b], s));
@@ -748,7 +997,6 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     blocks = (rows + 8 * rpw - 1) / (8 * rpw);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
-    const int nsub = p.ksplit * tc_cs(pl.BM);
     if (bf)
       rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s_rr>>>(zc, w.zb, E, Eb, rows, D, nsub, rpw, w.margin,
                                                                           w.cand, w.cnt, w.best, idx_offset, idx_out + r0,

@@ -12,6 +12,7 @@ kernels); this file is host-side sequencing only.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -275,6 +276,9 @@ class VectorQuantizerEMA(nn.Module):
                 if ops.fused_supported(N, self.K, D, mode):  # one kernel: search + gather + loss + histogram
                     ops.quantize_fused(flat, E, cache, mode, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
                                        hist=hist, row_mask=valid_u8)
+                elif os.environ.get("VQB200_SPLIT_GATHER") == "1":   # measurement switch: gather as a separate pass
+                    ops.search(flat, E, cache, 0, mode, idx)
+                    ops.gather(flat, E, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist, row_mask=valid_u8)
                 else:                                        # search + gather, chunk-pipelined on the tensor path
                     ops.quantize(flat, E, cache, mode, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
                                  hist=hist, row_mask=valid_u8)   # z_q is gathered BEFORE the EMA mutates E (:189 -> :193)

@@ -122,3 +122,28 @@ def test_tc_hands_back_hard_rows(vq):
     z4[4, :] = E4[17] * 1.01
     _, idx4, _ = run_search(vq, z4, E4, K)
     assert (idx4[4 * 64:5 * 64] == 17).all()
+
+
+def run_with_env(vq, z, E, K, env, mode="fp32"):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return run_search(vq, z, E, K, mode=mode)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("K,D,N", [(1000, 128, 20480), (8192, 256, 39936), (2048, 512, 19200), (256, 192, 32768)])
+def test_cta_pair_kernel_matches_single_cta(vq, K, D, N):
+    """tcgen05.mma.cta_group::2 variant (VQB200_TC2=1, default for large N) == 1-CTA kernel == fp64 oracle."""
+    E, z = large_case_inputs(900 + K + D, K, D, 1, N // 64, 64)
+    _, idx2, _ = run_with_env(vq, z, E, K, {"VQB200_TC2": "1", "VQB200_NO_FUSED": "1"})
+    _, idx1, _ = run_with_env(vq, z, E, K, {"VQB200_TC2": "0", "VQB200_NO_FUSED": "1"})
+    assert np.array_equal(idx1, idx2)
+    ref = O.nearest_code64(z.reshape(-1, D), E)
+    mm, outside = O.near_tie_rows(z.reshape(-1, D), E, idx2, ref)
+    assert outside.size == 0 and mm.size <= 2
