@@ -277,7 +277,7 @@ def run_b200(args, w):
         ach = bytes_alg / (kern_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
     kname = ("quantize_fused_kernel (tcgen05 distance+argmin+gather, one pass)" if fused else
-             "search_tc_kernel (tcgen05 distance+argmin)" if on_tc else "search_simt_kernel")
+             "search_tc2_kernel / search_tc_kernel (tcgen05 distance+argmin; cta_group::2 pairs for large N)" if on_tc else "search_simt_kernel")
     roof.update({"traffic": traffic, "kernel": kname,
                  "kernel_ms": kern_ms, "launches_per_step": launches_per_step, "rows_per_launch": rows_per_launch,
                  "kernel_share_of_step": kern_ms * launches_per_step / ms_step, "peak_source": peak_src,
