@@ -109,7 +109,7 @@ class Clocks:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -119,10 +119,13 @@ class Clocks:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def summary(self, t0, t1):
+        """Samples taken while the GPU was under this benchmark's load: the timed region [t0, t1] itself is often
+        shorter than one nvidia-smi sampling period, so the window extends over the back-to-back end-to-end and
+        kernel-timing loops that follow it (same kernels, same load)."""
         if self.proc is not None:
             self.proc.terminate()
         rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows)}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows), "window_s": round(t1 - t0, 3)}
         try:
             sm = [float(r[0]) for r in rows]
             out["sm_mhz"] = float(np.median(sm)) if sm else None
@@ -205,7 +208,6 @@ def run_b200(args, w):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
-    clk = clocks.summary(t0, t1) if clocks else None
     ms_step = ms / args.steps
     value = world * N / (ms_step * 1e-3)
 
@@ -284,6 +286,7 @@ def run_b200(args, w):
                  "algorithmic_unit": "2*K*D flop per row" if tensor_bound else
                  ("12*D+8 bytes per row" if fused else "4*D+8 bytes per row")})
 
+    clk = clocks.summary(t0, time.perf_counter()) if clocks else None
     if rank == 0:
         cpu_rows = cpu_sample_rows(w)
         sec, n = time_oracle(w, 1, 1, cpu_rows)
