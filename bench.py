@@ -1,12 +1,14 @@
 #!/usr/bin/env python
 """Benchmark of the VQ hot path: latents quantized per second (distance + argmin + gather).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|rvq] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|rvq|c4|c5] [--impl reference]
 
 One "step" = one full quantizer forward (search, gather, straight-through, commitment partial sums,
 histogram, statistics) over one batch of synthetic latents resident in HBM.  Rank 0 prints ONE JSON
 line.  Workloads (BASELINE.json configs): c2 = K=512 D=64 N=2^20 (default, configs[1], HBM-bound),
-c3 = K=8192 D=256 N=2^22 (tensor-bound), rvq = stage-2 shape 4x1024 D=512 N=8192.
+c3 = K=8192 D=256 N=2^22 (tensor-bound), rvq = stage-2 shape 4x1024 D=512 N=8192, c4 = index extraction
+(stage-2 RVQ over 2^21 latents per GPU, token-major int32 out), c5 = training step of the path (forward with
+EMA scatter-add, vq_loss, backward) at the stage-2 shape.
 Multi-GPU is weak scaling: every rank quantizes its own N rows against the replicated codebook; the
 only collective is one all-reduce of [sq-err | count | histogram] per step.
 """
@@ -29,6 +31,14 @@ WORKLOADS = {
     "c2": dict(K_per=512, D=64, L=1, N=1 << 20, desc="VectorQuantizer codebook search K=512 D=64, N=1M synthetic latents"),
     "c3": dict(K_per=8192, D=256, L=1, N=1 << 22, desc="large codebook K=8192 D=256 fp32, N=4M latents"),
     "rvq": dict(K_per=1024, D=512, L=4, N=8192, desc="stage2_vq RVQ 4x1024 D=512, N=8192 latents"),
+    # configs[3]: what scripts/extract_code_indices.py executes per rank -- the stage-2 residual quantizer over
+    # 2^21 latents per GPU (2^24 over 8 GPUs), indices re-laid out to token-major [B, M*Q] int32 on the device
+    "c4": dict(K_per=1024, D=512, L=4, N=1 << 21, extract=True,
+               desc="extract_code_indices, stage2 RVQ 4x1024 D=512, 2M latents per GPU (16M over 8), [B, M*Q] int32 out"),
+    # configs[4]: one training step of the path at the stage-2 shape: forward with EMA update (scatter-add),
+    # vq_loss, backward to z_e (straight-through + commitment)
+    "c5": dict(K_per=1024, D=512, L=4, N=8192, train=True,
+               desc="VQ training step (fwd + EMA scatter-add + vq_loss + backward), stage2 RVQ 4x1024 D=512, N=8192 per GPU"),
 }
 METRIC = "latents quantized/sec (distance+argmin+gather)"
 UNIT = "latents/s"
@@ -51,7 +61,7 @@ def synth(w, seed, n_rows=None):
 # ----------------------------------------------------------------------------------------------
 def cpu_sample_rows(w):
     # bounded sample: ~10-30 s of CPU work on a few-dozen-core host
-    return {"c2": 1 << 20, "c3": 1 << 16, "rvq": 8192}[w_name(w)]
+    return {"c2": 1 << 20, "c3": 1 << 16, "rvq": 8192, "c4": 8192, "c5": 8192}[w_name(w)]
 
 
 def w_name(w):
@@ -67,6 +77,17 @@ def time_oracle(w, steps, warmup, n_rows):
     E, z = synth(w, 1234, n_rows)
     Et, zt = torch.from_numpy(E), torch.from_numpy(z).reshape(-1, w["D"])
     chunk = 65536 if w["K_per"] <= 1024 else 16384
+    if w.get("train"):                                   # configs[4]: the reference's training step of the path
+        K = w["K_per"] * w["L"]
+        state = {"E": Et.clone(), "ema_cluster_size": torch.zeros(K), "ema_embedding": torch.zeros(K, w["D"])}
+        g_st = torch.from_numpy(np.random.RandomState(7).standard_normal(zt.shape).astype(np.float32))
+        ts = []
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            torch_port.train_step(zt, state, w["K_per"], w["L"], 0.0005, 0.98, 1e-5, g_st)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)), zt.shape[0]
     for _ in range(warmup):
         torch_port.forward_eval(zt[: max(64, zt.shape[0] // 8)], Et, w["K_per"], w["L"], chunk)
     ts = []
@@ -167,19 +188,41 @@ def run_b200(args, w):
     E, z_host = synth(w, 1234 + rank)                     # rows differ per rank; codebook identical
     E, _ = synth(w, 1234, 64) if rank else (E, None)
     N, D, K, L = z_host.shape[0] * z_host.shape[1], w["D"], w["K_per"], w["L"]
-    q = vq.VectorQuantizerEMA(K, D, num_quantizers=L, print_init=False, search_mode=args.mode).to(dev).eval()
+    train, extract = bool(w.get("train")), bool(w.get("extract"))
+    q = vq.VectorQuantizerEMA(K, D, num_quantizers=L, print_init=False, search_mode=args.mode).to(dev)
     q.embedding.copy_(torch.from_numpy(E))
     q.stats_sync = world > 1
+    if train:                                            # stage-2 schedule values (configs/stage2_vq.yaml:117-123)
+        q.train()
+        q.beta, q.decay = 0.0005, 0.98
+        q.ema_sync = "allreduce" if world > 1 else "local"
+    else:
+        q.eval()
     z_pin = torch.from_numpy(z_host).pin_memory()
     z = z_pin.to(dev)
+    Bz, Mz = z.shape[0], z.shape[1]
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    g_st = torch.randn(z.shape, device=dev, generator=gen) if train else None   # what a decoder would send back
+    beta_t = torch.full((), q.beta, device=dev)
 
-    graphed = vq.GraphedForward(q, z) if args.graph else None
+    graphed = vq.GraphedForward(q, z) if args.graph and not train else None
+
+    def train_step(zd):
+        ze = zd.detach().requires_grad_(True)
+        st, zq, idx, stats = q(ze, do_ema_update=True)
+        torch.autograd.backward([st, q.last_commit], [g_st, beta_t])    # d(recon)/d z_q_st + beta * commit (:1292-1294)
+        return st, zq, idx, stats, ze.grad
 
     def step():
+        if train:
+            return train_step(z)
         if graphed is not None:
             return graphed(z)
         with torch.no_grad():
-            return q(z, do_ema_update=False)
+            o = q(z, do_ema_update=False)
+            if extract:                                  # scripts/extract_code_indices.py:195-209 on the device
+                return o + (vq.ops.relayout_indices(o[2], L, Bz, Mz, torch.int32),)
+            return o
 
     def sync():
         if world > 1:
@@ -211,17 +254,22 @@ def run_b200(args, w):
     ms_step = ms / args.steps
     value = world * N / (ms_step * 1e-3)
 
-    # ---- end to end through the public API with HOST buffers: H2D of the step's latents from pinned
-    # memory, forward, D2H of indices + stats, every step inside the timed region
-    idx_host = torch.empty(out[2].shape, dtype=torch.int64).pin_memory()
-    stats_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    # ---- end to end through the public API with HOST buffers, every step inside the timed region: the
+    # latents start in pinned host memory and the step's result ends in host memory.  Inference workloads go
+    # through VectorQuantizerEMA.forward_host (chunked: H2D, kernels and D2H overlap on three streams); the
+    # training step copies its batch in, runs forward + backward and reads the loss back.
+    idx_dtype = torch.int32 if extract else torch.int64
+    idx_host = torch.empty(L * N, dtype=idx_dtype).pin_memory()
+    loss_host = torch.empty(3, dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        with torch.no_grad():
+        if train:
             zd = z_pin.to(dev, non_blocking=True)
-            o = q(zd, do_ema_update=False)
-            idx_host.copy_(o[2], non_blocking=True)
-            stats_host.copy_(o[3], non_blocking=True)
+            o = train_step(zd)
+            loss_host[:2].copy_(o[3], non_blocking=True)
+            loss_host[2:].copy_(q.last_commit.detach().reshape(1), non_blocking=True)
+        else:
+            q.forward_host(z_pin, out_indices=idx_host, wait=False, token_major=torch.int32 if extract else None)
 
     for _ in range(2):
         e2e_step()
@@ -238,6 +286,7 @@ def run_b200(args, w):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t)
     e2e_val = world * N / (e2e_ms / args.steps * 1e-3)
+    d2h_bytes = (12 if train else L * N * idx_host.element_size() + 8)
 
     # ---- roofline of the dominant kernel: the library brackets every launch of the fused distance+argmin
     # kernel (tcgen05 path; the SIMT kernel on shapes that take it) with CUDA events on the launching stream
@@ -247,8 +296,11 @@ def run_b200(args, w):
     mode = vq.quantizer._MODES[args.mode]
     lib.vqb200_timing_enable(1)
     for _ in range(max(3, min(args.steps, 10))):
-        with torch.no_grad():                                    # eager even under --graph: the hooks live in the library calls
-            q(z, do_ema_update=False)
+        if train:
+            train_step(z)
+        else:
+            with torch.no_grad():                                # eager even under --graph: the hooks live in the library calls
+                q(z, do_ema_update=False)
     torch.cuda.synchronize()
     lib.vqb200_timing_enable(0)
     tot, nl = ctypes.c_float(0), ctypes.c_int(0)
@@ -299,10 +351,13 @@ def run_b200(args, w):
                        if N * D * 12 > 126e6 else "L2-resident working set (no flush)",
                        "parallelism": f"rows sharded x{world}, codebook replicated", "cuda_graph": bool(args.graph)},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": N * D * 4,
-                    "d2h_bytes_per_step": out[2].numel() * 8 + 8, "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps,
+                    "api": "train step: H2D batch, forward+backward, D2H loss" if train else
+                           "VectorQuantizerEMA.forward_host (chunked H2D / kernels / D2H on three streams)"},
             "gpu_launches": launches, "clocks": clk, "roofline": roof,
             "cpu_baseline": {"value": n / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"{n} of {N} rows, one pass, torch ATen port (oracle/torch_port.py) on all host threads"},
+                             "sample": f"{n} of {N} rows, one {'training step' if train else 'pass'}, torch ATen port "
+                                       f"(oracle/torch_port.py) on all host threads"},
         }
         print(json.dumps(line))
     if world > 1:
@@ -314,7 +369,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")   # c4 = extract, c5 = training step
     ap.add_argument("--mode", choices=["fp32", "bf16_input"], default="fp32")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--graph", action="store_true", help="replay the forward as one CUDA graph (launch-bound shapes)")

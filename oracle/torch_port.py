@@ -31,3 +31,34 @@ def forward_eval(z: torch.Tensor, E: torch.Tensor, K_per: int, L: int, chunk: in
     idx = idx_out.reshape(-1)
     usage = torch.bincount(idx, minlength=L * K_per).float()
     return zq_out, idx, usage
+
+
+def train_step(z: torch.Tensor, state: dict, K_per: int, L: int, beta: float, decay: float, eps: float,
+               g_st: torch.Tensor):
+    """One training step of the path on the host cores, as the reference executes it (models/vq_vae.py:226-263
+    with the EMA update of :77-89 after every level, the commitment term of :1292-1294, then autograd back to
+    z): ``state`` holds E / ema_cluster_size / ema_embedding and is updated in place.  ``g_st`` is the
+    gradient a decoder would feed into z_q_st.  Returns (indices [L*N], grad_z [N, D], commit)."""
+    E, cs, es = state["E"], state["ema_cluster_size"], state["ema_embedding"]
+    K_total = L * K_per
+    z = z.detach().requires_grad_(True)
+    residual, picks, codes = z, [], []
+    for lvl in range(L):
+        cb = E[lvl * K_per:(lvl + 1) * K_per]
+        d = residual.pow(2).sum(1, keepdim=True) - 2.0 * (residual @ cb.t()) + cb.pow(2).sum(1, keepdim=True).t()
+        pick = d.argmin(1)
+        gid = pick + lvl * K_per
+        picks.append(gid)
+        code = torch.nn.functional.embedding(pick, cb)
+        codes.append(code)
+        with torch.no_grad():                                 # dense one-hot segment sums, as the reference forms them
+            hot = torch.nn.functional.one_hot(gid, num_classes=K_total).float()
+            cs.mul_(decay).add_(hot.sum(0) * (1 - decay))
+            es.mul_(decay).add_(hot.t() @ residual.detach() * (1 - decay))
+            E.copy_(es / (cs.unsqueeze(1) + eps))
+        residual = residual - code
+    zq = torch.stack(codes, 0).sum(0)
+    st = z + (zq - z).detach()
+    commit = torch.nn.functional.mse_loss(zq.detach(), z)
+    torch.autograd.backward([st, beta * commit], [g_st, torch.ones(())])
+    return torch.cat(picks, 0), z.grad, commit.detach()

@@ -15,18 +15,24 @@
 //   warps 10-11 converters:   fp32 tile (swizzled TMA layout) -> bf16 UMMA operand tile (128-byte swizzle),
 //                             row norms -> admission margins
 // Exactness argument, margin and hand-back rules are those of vq_search_tc.cu.
+#include <cstdio>
+#include <initializer_list>
 #include <cstdlib>
 
 #include "tc_ptx.cuh"
 
 namespace vqb {
 
-constexpr int FZ_BM = 256;
-constexpr int FZ_NEPI = 8;
-constexpr int FZ_NCONV = 2;          // 12 warps = 3 per scheduler: 170 registers per thread, no spills
-constexpr int FZ_THREADS = 64 + FZ_NEPI * 32 + FZ_NCONV * 32;   // 384
+// Two tile heights.  BM = 256: one CTA per SM, 8 epilogue warps (12 warps, 170 registers, no spills).
+// BM = 128: TWO CTAs per SM (half the shared memory, 256 TMEM columns and <= 128 registers each): the scan of
+// one CTA's tile overlaps the re-rank / output phase of the other's -- those phases are latency-bound (TMEM and
+// L2 round trips on dependent chains), so a second resident pipeline roughly doubles the SM's throughput.
+constexpr int fz_nconv(int) { return 2; }   // converter / output warps (12 warps = 3 per scheduler: 168 registers)
+constexpr int fz_nepi(int BM) { return BM / 32; }
+constexpr int fz_threads(int BM) { return 64 + fz_nepi(BM) * 32 + fz_nconv(BM) * 32; }   // 448 / 256
 constexpr int FZ_PAIRS = 64;          // (row, code) pairs scored per warp pass
-constexpr int FZ_HIST = 2048;         // codebooks up to this size get a shared-memory histogram
+constexpr int fz_hist(int BM) { return BM == 256 ? 2048 : 1024; }   // codebooks up to this size: shared-memory histogram
+constexpr int FZ_RING_BYTES = 4 * (2 * 32 * 16 + 32 * 8);           // per warp: FZ_RING entries x 32 lanes x 40 bytes
 constexpr uint32_t FZ_EMPTY = 0xffffffffu;
 
 struct FusedParams {
@@ -47,6 +53,7 @@ struct FusedParams {
   int* fb_rows;
   uint64_t* fb_packed;
   int* counters;
+  long long* dbg;               // VQB200_DEBUG=2: per CTA [smid, globaltimer at start, at end]
 };
 
 // 32 score columns of one row.  Fast path: one compare against the admission threshold.  Slow path: every group
@@ -56,7 +63,8 @@ struct FusedParams {
 // threshold.  Overwriting an entry remembers its maximum: if that could still matter the row is handed back.
 constexpr int FZ_RING = 4;
 __device__ __forceinline__ void fz_scan(const uint32_t (&v)[32], uint32_t code0, float margin, float& best, float& thr,
-                                        uint4* ring, int lane, int& cnt, float& lost) {
+                                        uint4* ring, uint2* rmeta, int lane, int& cnt, float& lost,
+                                        float (&age)[FZ_RING]) {
   float gm[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -70,21 +78,29 @@ __device__ __forceinline__ void fz_scan(const uint32_t (&v)[32], uint32_t code0,
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       if (gm[g] >= thr) {
-        uint4* e = ring + ((cnt & (FZ_RING - 1)) * 3) * 32 + lane;     // fields at e[0], e[32], e[64]
-        if (cnt >= FZ_RING) lost = fmaxf(lost, __uint_as_float(e[64].x));
+        uint4* e = ring + ((cnt & (FZ_RING - 1)) * 2) * 32 + lane;     // score fields at e[0], e[32]
+        uint2* m = rmeta + (cnt & (FZ_RING - 1)) * 32 + lane;           // (group maximum, group id)
+        lost = fmaxf(lost, age[FZ_RING - 1]);        // the entry being overwritten is the oldest: its maximum
+#pragma unroll                                        // sits at the end of a register shift chain (no LDS on this path)
+        for (int a = FZ_RING - 1; a > 0; --a) age[a] = age[a - 1];
+        age[0] = gm[g];
         e[0] = make_uint4(v[g * 8 + 0], v[g * 8 + 1], v[g * 8 + 2], v[g * 8 + 3]);
         e[32] = make_uint4(v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
-        e[64] = make_uint4(__float_as_uint(gm[g]), (code0 >> 3) + g, 0u, 0u);
+        *m = make_uint2(__float_as_uint(gm[g]), (code0 >> 3) + g);
         ++cnt;
       }
     }
   }
 }
 
-template <int D, bool BF16>
-__global__ void __launch_bounds__(FZ_THREADS, 1)
+template <int D, bool BF16, int FZ_BM>
+__global__ void __launch_bounds__(fz_threads(FZ_BM), FZ_BM == 256 ? 1 : 2)
 quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_constant__ CUtensorMap tmap_e,
                       const FusedParams p) {
+  constexpr int FZ_NEPI = fz_nepi(FZ_BM), FZ_THREADS = fz_threads(FZ_BM), FZ_HIST = fz_hist(FZ_BM);
+  constexpr int FZ_NCONV = fz_nconv(FZ_BM);
+  constexpr int HALVES = FZ_BM / 128;              // M = 128 accumulator tiles per row tile
+  constexpr uint32_t TMEM_COLS = 2 * HALVES * TC_BN;   // two accumulator buffers
   constexpr int KBLK = D / TC_KB;                  // bf16 operand blocks along D
   constexpr int KB32 = D / 32;                     // fp32 staging slabs along D (32 floats = 128 bytes)
   constexpr uint32_t ZF_BYTES = FZ_BM * D * 4;
@@ -105,13 +121,15 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
   double* pair_score = reinterpret_cast<double*>(pair_list + FZ_NEPI * FZ_PAIRS);         // [8][64]
   int* hist_s = reinterpret_cast<int*>(pair_score + FZ_NEPI * FZ_PAIRS);                  // [FZ_HIST]
   double* red_s = reinterpret_cast<double*>(hist_s + FZ_HIST);                            // [16]
-  uint4* rings = reinterpret_cast<uint4*>(red_s + 16);                                    // [8][FZ_RING*3][32] x 16 B
+  uint8_t* rings = reinterpret_cast<uint8_t*>(red_s + 16);                                // [NEPI][FZ_RING_BYTES]
+  uint32_t* res_s = reinterpret_cast<uint32_t*>(rings + FZ_NEPI * FZ_RING_BYTES);         // [2][FZ_BM] resolved codes
   const uint32_t bar0 = misc + 2 * FZ_BM * 4 + FZ_NEPI * TC_BN * 4 + FZ_NEPI * FZ_PAIRS * 4 + FZ_NEPI * FZ_PAIRS * 8 +
-                        FZ_HIST * 4 + 16 * 8 + FZ_NEPI * FZ_RING * 3 * 32 * 16;
+                        FZ_HIST * 4 + 16 * 8 + FZ_NEPI * FZ_RING_BYTES + 2 * FZ_BM * 4;
   const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * 8, bar_tfull = bar0 + 16 * 8, bar_tempty = bar0 + 18 * 8;
   const uint32_t bar_zffull = bar0 + 20 * 8, bar_zfempty = bar0 + 21 * 8;
   const uint32_t bar_zbfull = bar0 + 22 * 8, bar_zbempty = bar0 + 24 * 8;    // [2] each
-  const uint32_t tmem_slot = bar0 + 26 * 8;
+  const uint32_t bar_resfull = bar0 + 26 * 8, bar_resempty = bar0 + 28 * 8;  // [2] each
+  const uint32_t tmem_slot = bar0 + 30 * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool smem_hist = p.hist != nullptr && p.K <= FZ_HIST;
@@ -121,6 +139,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, FZ_NEPI);
       mbar_init(bar_zbfull + 8 * b, FZ_NCONV); mbar_init(bar_zbempty + 8 * b, 1);
+      mbar_init(bar_resfull + 8 * b, FZ_NEPI); mbar_init(bar_resempty + 8 * b, FZ_NCONV);
     }
     mbar_init(bar_zffull, 1);
     mbar_init(bar_zfempty, FZ_NCONV);
@@ -128,7 +147,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (smem_hist)
@@ -139,6 +158,11 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int n_items = p.row_tiles;
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned id; asm volatile("mov.u32 %0, %%smid;" : "=r"(id));
+    long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[blockIdx.x * 3] = id; p.dbg[blockIdx.x * 3 + 1] = g;
+  }
   float err_acc = 0.f;                              // sum (z_q - z)^2 over the rows this thread finalises
 
   if (warp == 0) {
@@ -187,8 +211,8 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
             const uint32_t a0 = zb_lo + ((zb * ZB_BYTES + kb * (FZ_BM * 128)) >> 4);
             const uint32_t b0 = e_lo + ((stage * TC_STAGE_BYTES) >> 4);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint32_t d_tmem = tmem_base + b * (2 * TC_BN) + h * TC_BN;
+            for (int h = 0; h < HALVES; ++h) {
+              const uint32_t d_tmem = tmem_base + b * (HALVES * TC_BN) + h * TC_BN;
 #pragma unroll
               for (int k = 0; k < TC_KB / 16; ++k)
                 tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), kIdesc, 1u);
@@ -210,14 +234,75 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     const bool code_bad = p.level_meta[1] != 0.f;
     const float coef = BF16 ? 2.f * static_cast<float>(D + 32) * 1.1920929e-7f
                                                         : 2.f * 0.00391007f * 1.02f;
+    // Output phase of a finished tile (z_q, z_q_st, squared error), run by these warps one tile behind the
+    // epilogue: the epilogue warps publish the tile's resolved codes in shared memory and move on to the next
+    // tile's scan, so the L2 / HBM round trips of the outputs are off the scan -> re-rank critical path.
+    const bool want_out = p.zq_out || p.zq_st_out || p.sqerr_sum;
+    auto emit = [&](int item_o, uint32_t ito) {
+      constexpr int RPS = (FZ_NCONV * 32) / LPV;             // rows per step of the two warps together
+      constexpr int OB = 8;       // steps whose loads are issued together (measured: 16 is slower, 4 warps cost the
+                                  // epilogue its registers: 13-16 warps cap every thread at 128)
+      constexpr int SL = D / (LPV * 4);
+      const uint32_t rbuf = ito & 1;
+      mbar_wait(bar_resfull + 8 * rbuf, (ito >> 1) & 1);
+      const uint32_t* rs = res_s + rbuf * FZ_BM;
+      const int64_t row0 = static_cast<int64_t>(item_o) * FZ_BM;
+      const int ogl = ct % LPV, ogr = ct / LPV;
+#pragma unroll 1
+      for (int rb = 0; rb < FZ_BM; rb += RPS * OB) {
+        float4 e4[OB][SL], z4[OB][SL];
+        bool res[OB];
+#pragma unroll
+        for (int u = 0; u < OB; ++u) {
+          const int rl = rb + u * RPS + ogr;
+          const uint32_t code = rl < FZ_BM ? rs[rl] : FZ_EMPTY;
+          const int64_t grow = row0 + rl;
+          res[u] = code != FZ_EMPTY;
+#pragma unroll
+          for (int sl = 0; sl < SL; ++sl) {
+            const int d = ogl * 4 + sl * LPV * 4;
+            if (res[u]) {
+              e4[u][sl] = __ldg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(code) * D + d));
+              z4[u][sl] = ld_stream(reinterpret_cast<const float4*>(p.z + grow * D + d));
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < OB; ++u) {
+          if (!res[u]) continue;
+          const int64_t grow = row0 + rb + u * RPS + ogr;
+#pragma unroll
+          for (int sl = 0; sl < SL; ++sl) {
+            const int d = ogl * 4 + sl * LPV * 4;
+            const float4 e = e4[u][sl], zz = z4[u][sl];
+            float4 df;
+            df.x = __fsub_rn(e.x, zz.x); df.y = __fsub_rn(e.y, zz.y);
+            df.z = __fsub_rn(e.z, zz.z); df.w = __fsub_rn(e.w, zz.w);
+            if (p.zq_out) st_stream(reinterpret_cast<float4*>(p.zq_out + grow * D + d), e);
+            if (p.zq_st_out) {
+              float4 o;
+              o.x = __fadd_rn(zz.x, df.x); o.y = __fadd_rn(zz.y, df.y);
+              o.z = __fadd_rn(zz.z, df.z); o.w = __fadd_rn(zz.w, df.w);
+              st_stream(reinterpret_cast<float4*>(p.zq_st_out + grow * D + d), o);
+            }
+            err_acc = fmaf(df.x, df.x, err_acc); err_acc = fmaf(df.y, df.y, err_acc);
+            err_acc = fmaf(df.z, df.z, err_acc); err_acc = fmaf(df.w, df.w, err_acc);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_resempty + 8 * rbuf);
+    };
     uint32_t it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+    int item_prev = -1;
+    for (int item = blockIdx.x; item < n_items; item_prev = item, item += gridDim.x, ++it) {
       const uint32_t zb = 0, mb = it & 1;
       mbar_wait(bar_zffull, it & 1);
       mbar_wait(bar_zbempty, (it & 1) ^ 1);             // the MMAs of the previous tile have retired
 #pragma unroll 1
-      for (int rr = 0; rr < FZ_BM / (FZ_NCONV * 32); ++rr) {
+      for (int rr = 0; rr < (FZ_BM + FZ_NCONV * 32 - 1) / (FZ_NCONV * 32); ++rr) {
         const int r = ct + rr * (FZ_NCONV * 32);
+        if (r >= FZ_BM) break;
         const uint32_t sw = static_cast<uint32_t>(r & 7);
         float ss = 0.f;
 #pragma unroll
@@ -253,14 +338,17 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
       __syncwarp();
       if (lane == 0) { mbar_arrive(bar_zbfull); mbar_arrive(bar_zfempty); }
+      if (want_out && item_prev >= 0) emit(item_prev, it - 1);
     }
+    if (want_out && item_prev >= 0) emit(item_prev, it - 1);
   } else {
     // ============================== epilogue + finalise ==============================
     const int we = warp - 2;
     const int quarter = warp & 3, half = we >> 2;
     const int row_in_tile = half * 128 + quarter * 32;
     float* ee_slot = ee_slots + we * TC_BN;
-    uint4* ring = rings + we * (FZ_RING * 3 * 32);
+    uint4* ring = reinterpret_cast<uint4*>(rings + we * FZ_RING_BYTES);
+    uint2* rmeta = reinterpret_cast<uint2*>(rings + we * FZ_RING_BYTES + FZ_RING * 2 * 32 * 16);
     uint32_t* plist = pair_list + we * FZ_PAIRS;
     double* pscore = pair_score + we * FZ_PAIRS;
     const float kNegInf = __int_as_float(0xff800000);
@@ -290,7 +378,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
           w[j + 0] = __float_as_uint(q4.x); w[j + 1] = __float_as_uint(q4.y);
           w[j + 2] = __float_as_uint(q4.z); w[j + 3] = __float_as_uint(q4.w);
         }
-        TC_ST16(tmem_base + tcol + b * (2 * TC_BN) + hh * 16, w);
+        TC_ST16(tmem_base + tcol + b * (HALVES * TC_BN) + hh * 16, w);
       }
       tc_wait_st();
     };
@@ -320,6 +408,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       float thr = margin == margin ? best : margin;
       int rcnt = 0;
       float lost = kNegInf;
+      float age[FZ_RING] = {kNegInf, kNegInf, kNegInf, kNegInf};
 
       for (int t = 0; t < p.code_tiles; ++t, ++tg) {
         const uint32_t b = tg & 1;
@@ -329,7 +418,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
         bias_next = load_bias(t_ahead);
         mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + tcol + b * (2 * TC_BN);
+        const uint32_t taddr = tmem_base + tcol + b * (HALVES * TC_BN);
         // One 32-column chunk in registers at a time (measured: double-buffering the TMEM loads buys nothing
         // here, the scan is bound by its own dependency chains).  After the LAST chunk is out of TMEM the
         // buffer is re-armed with the bias of its next tile and handed back; only then is that chunk scanned.
@@ -344,7 +433,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
           }
-          fz_scan(v, static_cast<uint32_t>(t * TC_BN + ch * 32), margin, best, thr, ring, lane, rcnt, lost);
+          fz_scan(v, static_cast<uint32_t>(t * TC_BN + ch * 32), margin, best, thr, ring, rmeta, lane, rcnt, lost, age);
         }
       }
 
@@ -359,8 +448,8 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       for (int s = 0; s < FZ_RING; ++s) {
         sx[s] = FZ_EMPTY;
         if (s < rcnt) {
-          const uint4* e = ring + (s * 3) * 32 + lane;
-          const uint4 meta = e[64];
+          const uint4* e = ring + (s * 2) * 32 + lane;
+          const uint2 meta = rmeta[s * 32 + lane];
           if (__uint_as_float(meta.x) >= thr) {
             const uint4 a = e[0], b4 = e[32];
             uint32_t mk = 0;
@@ -498,57 +587,22 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
           else atomicAdd(p.hist + p.idx_offset + my_idx, 1);
         }
       }
-      if (p.zq_out || p.zq_st_out || p.sqerr_sum) {
-        constexpr int OB = 4;                                   // row-steps whose loads are issued together
-        constexpr int SL = D / (LPV * 4);
-#pragma unroll 1
-        for (int rb = 0; rb < 32; rb += GROUPS * OB) {
-          float4 e4[OB][SL], z4[OB][SL];
-          bool res[OB];
-#pragma unroll
-          for (int u = 0; u < OB; ++u) {
-            const int rl = rb + u * GROUPS + gi;
-            res[u] = rl < 32 && __shfl_sync(0xffffffffu, static_cast<int>(resolved), rl & 31) != 0;
-            const uint32_t code = __shfl_sync(0xffffffffu, my_idx, rl & 31);
-            const int64_t grow = row0w + rl;
-#pragma unroll
-            for (int sl = 0; sl < SL; ++sl) {
-              const int d = gl * 4 + sl * LPV * 4;
-              if (res[u]) {
-                e4[u][sl] = __ldg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(code) * D + d));
-                z4[u][sl] = ld_stream(reinterpret_cast<const float4*>(p.z + grow * D + d));
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < OB; ++u) {
-            if (!res[u]) continue;
-            const int64_t grow = row0w + rb + u * GROUPS + gi;
-#pragma unroll
-            for (int sl = 0; sl < SL; ++sl) {
-              const int d = gl * 4 + sl * LPV * 4;
-              const float4 e = e4[u][sl], zz = z4[u][sl];
-              float4 df;
-              df.x = __fsub_rn(e.x, zz.x); df.y = __fsub_rn(e.y, zz.y);
-              df.z = __fsub_rn(e.z, zz.z); df.w = __fsub_rn(e.w, zz.w);
-              if (p.zq_out) st_stream(reinterpret_cast<float4*>(p.zq_out + grow * D + d), e);
-              if (p.zq_st_out) {
-                float4 o;
-                o.x = __fadd_rn(zz.x, df.x); o.y = __fadd_rn(zz.y, df.y);
-                o.z = __fadd_rn(zz.z, df.z); o.w = __fadd_rn(zz.w, df.w);
-                st_stream(reinterpret_cast<float4*>(p.zq_st_out + grow * D + d), o);
-              }
-              err_acc = fmaf(df.x, df.x, err_acc); err_acc = fmaf(df.y, df.y, err_acc);
-              err_acc = fmaf(df.z, df.z, err_acc); err_acc = fmaf(df.w, df.w, err_acc);
-            }
-          }
-        }
+      if (p.zq_out || p.zq_st_out || p.sqerr_sum) {              // publish the codes; the output warps take over
+        const uint32_t rbuf = it & 1, use = it >> 1;
+        if (use >= 1) mbar_wait(bar_resempty + 8 * rbuf, (use - 1) & 1);
+        res_s[rbuf * FZ_BM + row_in_tile + lane] = resolved ? my_idx : FZ_EMPTY;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_resfull + 8 * rbuf);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (p.dbg && threadIdx.x == 0) {
+    long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.dbg[blockIdx.x * 3 + 2] = g;
+  }
   if (smem_hist)
     for (int k = threadIdx.x; k < p.K; k += FZ_THREADS) {
       const int v = hist_s[k];
@@ -566,7 +620,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
   }
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -618,9 +672,91 @@ bool fused_supported(int64_t N, int K, int D) {
 
 size_t fused_workspace_bytes(int64_t N) { return 256 + fz_align(static_cast<size_t>(N) * 4) + fz_align(static_cast<size_t>(N) * 8); }
 
-static int fused_smem_bytes(int D, int stages) {
-  return 1024 + FZ_BM * D * 4 + FZ_BM * D * 2 + stages * TC_STAGE_BYTES + 2 * FZ_BM * 4 + FZ_NEPI * TC_BN * 4 +
-         FZ_NEPI * FZ_PAIRS * 4 + FZ_NEPI * FZ_PAIRS * 8 + FZ_HIST * 4 + 16 * 8 + FZ_NEPI * FZ_RING * 3 * 32 * 16 + 256;
+static int fused_smem_bytes(int D, int stages, int BM) {
+  const int nepi = fz_nepi(BM);
+  return 1024 + BM * D * 4 + BM * D * 2 + stages * TC_STAGE_BYTES + 2 * BM * 4 + nepi * TC_BN * 4 +
+         nepi * FZ_PAIRS * 4 + nepi * FZ_PAIRS * 8 + fz_hist(BM) * 4 + 16 * 8 + nepi * FZ_RING_BYTES + 2 * BM * 4 + 256;
+}
+
+// Tile height: 256 rows, one CTA per SM (default), or 128 rows with two co-resident CTAs (VQB200_FUSED_BM=128;
+// measured slower: the same number of epilogue warps per SM, twice the fixed per-tile overheads).
+static int fused_bm() {
+  const char* e = std::getenv("VQB200_FUSED_BM");
+  return (e && e[0] == '1') ? 128 : 256;
+}
+
+template <int BM>
+static int launch_fused_bm(const CUtensorMap& map_zf, const CUtensorMap& map_e, FusedParams& p, bool bf, int D,
+                           cudaStream_t s) {
+  // two CTAs of BM = 128 share one SM's 228 KB (1 KB reserved per CTA)
+  const int limit = BM == 256 ? TC_SMEM_LIMIT : (233472 - 2 * 1024) / 2;
+  int stages = 8;
+  while (stages > 2 && fused_smem_bytes(D, stages, BM) > limit) --stages;
+  if (fused_smem_bytes(D, stages, BM) > limit) return VQB200_ESHAPE;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(quantize_fused_kernel<64, false, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(quantize_fused_kernel<64, true, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    if (e != cudaSuccess) return status_of(e);
+    // co-residency needs the largest shared-memory carve-out the SM offers
+    cudaFuncSetAttribute(quantize_fused_kernel<64, false, BM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(quantize_fused_kernel<64, true, BM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    const char* dbg = std::getenv("VQB200_DEBUG");
+    if (dbg && dbg[0] == '1') {
+      int nb = -1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, quantize_fused_kernel<64, false, BM>, fz_threads(BM),
+                                                    fused_smem_bytes(D, stages, BM));
+      fprintf(stderr, "[vqb200] fused BM=%d stages=%d smem=%d B: %d resident CTA(s) per SM\n", BM, stages,
+              fused_smem_bytes(D, stages, BM), nb);
+      int dev = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&a0, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+      cudaDeviceGetAttribute(&a1, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+      cudaDeviceGetAttribute(&a2, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+      cudaDeviceGetAttribute(&a3, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, quantize_fused_kernel<64, false, BM>);
+      fprintf(stderr, "[vqb200] smem/SM %d reserved/block %d regs/SM %d optin %d | kernel regs %d static smem %zu local %zu maxdyn %d carveout %d\n",
+              a0, a1, a2, a3, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes,
+              fa.preferredShmemCarveout);
+      for (int sm : {114048, 112000, 108000, 100000, 90000, 70000, 50000})
+        for (int th : {256, 224, 192}) {
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, quantize_fused_kernel<64, false, BM>, th, sm);
+          fprintf(stderr, "[vqb200]   dyn smem %d threads %d -> %d CTA/SM\n", sm, th, nb);
+        }
+    }
+    attr_done = true;
+  }
+  p.stages = stages;
+  p.row_tiles = static_cast<int>((p.n_rows + BM - 1) / BM);
+  int slots = kNumSMs * (BM == 256 ? 1 : 2);
+  const char* genv = std::getenv("VQB200_FUSED_GRID");          // measurement switch
+  if (genv && std::atoi(genv) > 0) slots = std::atoi(genv);
+  const int grid = p.row_tiles < slots ? p.row_tiles : slots;
+  const int smem = fused_smem_bytes(D, stages, BM);
+  const char* dbg = std::getenv("VQB200_DEBUG");
+  const bool trace = dbg && dbg[0] == '2';
+  p.dbg = nullptr;
+  if (trace) cudaMallocManaged(&p.dbg, static_cast<size_t>(grid) * 3 * sizeof(long long));
+  timing_mark_begin(s);
+  if (bf) quantize_fused_kernel<64, true, BM><<<grid, fz_threads(BM), smem, s>>>(map_zf, map_e, p);
+  else quantize_fused_kernel<64, false, BM><<<grid, fz_threads(BM), smem, s>>>(map_zf, map_e, p);
+  timing_mark_end(s);
+  if (trace) {                                                   // CTAs that overlapped in time on one SM
+    cudaStreamSynchronize(s);
+    int overlap = 0;
+    long long lo = p.dbg[1], hi = p.dbg[2];
+    for (int i = 0; i < grid; ++i) {
+      if (p.dbg[i * 3 + 1] < lo) lo = p.dbg[i * 3 + 1];
+      if (p.dbg[i * 3 + 2] > hi) hi = p.dbg[i * 3 + 2];
+      for (int j = i + 1; j < grid; ++j)
+        if (p.dbg[i * 3] == p.dbg[j * 3] && p.dbg[i * 3 + 1] < p.dbg[j * 3 + 2] && p.dbg[j * 3 + 1] < p.dbg[i * 3 + 2]) ++overlap;
+    }
+    fprintf(stderr, "[vqb200] fused BM=%d grid=%d: %d co-resident CTA pairs, span %.1f us\n", BM, grid, overlap, (hi - lo) * 1e-3);
+    cudaFree(p.dbg);
+  }
+  return status_of(cudaGetLastError());
 }
 
 int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
@@ -630,9 +766,7 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
   if (!fused_supported(N, K, D)) return VQB200_ESHAPE;
   if (workspace_bytes < fused_workspace_bytes(N)) return VQB200_EWORKSPACE;
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
-  int stages = 8;
-  while (stages > 2 && fused_smem_bytes(D, stages) > TC_SMEM_LIMIT) --stages;
-  if (fused_smem_bytes(D, stages) > TC_SMEM_LIMIT) return VQB200_ESHAPE;
+  const int BM = fused_bm();
 
   uint8_t* w = static_cast<uint8_t*>(workspace);
   int* counters = reinterpret_cast<int*>(w); w += 256;
@@ -640,37 +774,24 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
   uint64_t* fb_packed = reinterpret_cast<uint64_t*>(w);
 
   CUtensorMap map_zf, map_e;
-  if (!make_tensor_map_2d(&map_zf, z, N, D, FZ_BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4)) return VQB200_EDRIVER;
+  if (!make_tensor_map_2d(&map_zf, z, N, D, BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4)) return VQB200_EDRIVER;
   if (!make_tensor_map_2d(&map_e, E_bf16, K, D, TC_BN, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2)) return VQB200_EDRIVER;
 
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(quantize_fused_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(quantize_fused_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
-    if (e != cudaSuccess) return status_of(e);
-    attr_done = true;
-  }
   cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(int), s);
   if (e != cudaSuccess) return status_of(e);
 
   FusedParams p;
   p.n_rows = N; p.K = K;
-  p.row_tiles = static_cast<int>((N + FZ_BM - 1) / FZ_BM);
+  p.row_tiles = 0;
   p.code_tiles = (K + TC_BN - 1) / TC_BN;
-  p.stages = stages; p.mode = mode;
+  p.stages = 0; p.mode = mode;
   p.z = z; p.E = E; p.Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
   p.ee_half = bf ? ee_half_bf16 : ee_half; p.level_meta = level_meta;
   p.idx_offset = idx_offset; p.idx_out = idx_out; p.zq_out = zq_out; p.zq_st_out = zq_st_out;
   p.sqerr_sum = sqerr_sum; p.hist = hist; p.row_mask = row_mask;
   p.fb_rows = fb_rows; p.fb_packed = fb_packed; p.counters = counters;
-  const int grid = p.row_tiles < kNumSMs ? p.row_tiles : kNumSMs;
-  timing_mark_begin(s);
-  if (bf) quantize_fused_kernel<64, true><<<grid, FZ_THREADS, fused_smem_bytes(D, stages), s>>>(map_zf, map_e, p);
-  else quantize_fused_kernel<64, false><<<grid, FZ_THREADS, fused_smem_bytes(D, stages), s>>>(map_zf, map_e, p);
-  timing_mark_end(s);
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return status_of(e);
+  const int ls = BM == 256 ? launch_fused_bm<256>(map_zf, map_e, p, bf, D, s) : launch_fused_bm<128>(map_zf, map_e, p, bf, D, s);
+  if (ls != VQB200_OK) return ls;
 
   const int st = launch_search_simt_list(z, fb_rows, counters, N, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0,
                                          idx_offset, fb_packed, s);

@@ -174,13 +174,17 @@ def commit_backward(grad_st, grad_commit, z, zq, scale, out):
 _IDX_BYTES = {torch.int16: 2, torch.int32: 4, torch.int64: 8}
 
 
-def relayout_indices(idx_level_major: torch.Tensor, Q: int, B: int, M: int, dtype=torch.int64) -> torch.Tensor:
+def relayout_indices(idx_level_major: torch.Tensor, Q: int, B: int, M: int, dtype=torch.int64,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
     """Level-major flat RVQ ids [Q*B*M] -> token-major [B, M*Q] (optionally narrowed), on the device."""
     _need_cuda(idx_level_major)
     if idx_level_major.dtype != torch.int64 or idx_level_major.numel() != Q * B * M:
         raise RuntimeError(f"expected {Q * B * M} int64 indices, got {tuple(idx_level_major.shape)} "
                            f"{idx_level_major.dtype}")
-    out = torch.empty(B, M * Q, dtype=dtype, device=idx_level_major.device)
+    if out is None:
+        out = torch.empty(B, M * Q, dtype=dtype, device=idx_level_major.device)
+    elif out.dtype != dtype or out.numel() != Q * B * M or not out.is_contiguous() or not out.is_cuda:
+        raise RuntimeError(f"out must be a contiguous CUDA {dtype} tensor of {Q * B * M} elements")
     check(lib.vqb200_relayout_indices(ptr(idx_level_major.contiguous()), Q, B, M, ptr(out), _IDX_BYTES[dtype],
                                       stream_ptr()), "vqb200_relayout_indices")
     _count(1)

@@ -251,9 +251,6 @@ class VectorQuantizerEMA(nn.Module):
         if not flat.is_contiguous():
             flat = flat.contiguous()
         N = flat.shape[0]
-        mode = _MODES[self.search_mode]
-        cache = self._codebook_cache()
-        E = self.embedding
         L = self.num_quantizers
 
         # one zeroed scratch: [sqerr_sum (double) | hist int32[K]]
@@ -270,42 +267,170 @@ class VectorQuantizerEMA(nn.Module):
         # the reference skips the EMA entirely when no row is valid (:196,253): same host sync, mask only
         ema_ok = do_ema and N > 0 and (valid_u8 is None or bool(valid_u8.any()))
 
-        if L == 1:
-            idx = torch.empty(N, dtype=torch.int64, device=dev)
-            if N > 0:
-                if ops.fused_supported(N, self.K, D, mode):  # one kernel: search + gather + loss + histogram
-                    ops.quantize_fused(flat, E, cache, mode, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
-                                       hist=hist, row_mask=valid_u8)
-                elif os.environ.get("VQB200_SPLIT_GATHER") == "1":   # measurement switch: gather as a separate pass
-                    ops.search(flat, E, cache, 0, mode, idx)
-                    ops.gather(flat, E, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist, row_mask=valid_u8)
-                else:                                        # search + gather, chunk-pipelined on the tensor path
-                    ops.quantize(flat, E, cache, mode, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
-                                 hist=hist, row_mask=valid_u8)   # z_q is gathered BEFORE the EMA mutates E (:189 -> :193)
-                if ema_ok:
-                    self._ema_update(flat, idx, valid_u8)
-            self._finalize_stats(hist, float(N), sqerr, N * D, stats3)
-            return z_q_st.view(B, M, D), z_q.view(B, M, D), idx.view(B, M), stats3
-
-        idx_all = torch.empty(L * N, dtype=torch.int64, device=dev)   # level-major, global ids (:260)
+        idx_all = torch.empty(L * N, dtype=torch.int64, device=dev)   # RVQ: level-major, global ids (:260)
         if N > 0:
-            residual = flat
-            spare = [torch.empty(N, D, dtype=torch.float32, device=dev) for _ in range(min(2, L - 1))]
-            for level in range(L):
-                idx_l = idx_all[level * N:(level + 1) * N]
-                if level > 0 and do_ema:
-                    cache = self._codebook_cache()
-                ops.search(residual, E, cache, level, mode, idx_l)
-                nxt = spare[level % 2] if level < L - 1 else None
-                # level sum in level order (:261); RVQ histogram ignores the mask (:266)
-                ops.gather(residual, E, idx_l, zq_out=z_q, accumulate=level > 0, residual_out=nxt, hist=hist)
-                if ema_ok:
-                    self._ema_update(residual, idx_l, valid_u8)
-                if nxt is not None:
-                    residual = nxt
-            ops.st_loss(flat, z_q, zq_st_out=z_q_st, sqerr_sum=sqerr)
+            self._quantize_rows(flat, [idx_all[l * N:(l + 1) * N] for l in range(L)], z_q, z_q_st, sqerr, hist,
+                                valid_u8, do_ema, ema_ok)
         self._finalize_stats(hist, float(L * N), sqerr, N * D, stats3)
-        return z_q_st.view(B, M, D), z_q.view(B, M, D), idx_all, stats3
+        return z_q_st.view(B, M, D), z_q.view(B, M, D), (idx_all.view(B, M) if L == 1 else idx_all), stats3
+
+    def _quantize_rows(self, flat, idx_levels, z_q, z_q_st, sqerr, hist, valid_u8, do_ema=False, ema_ok=False):
+        """Search + gather (+ EMA) of the rows ``flat`` [n, D] into caller-allocated outputs; ``sqerr`` and
+        ``hist`` ACCUMULATE, so a batch may be fed in several calls (``forward_host``).  ``z_q`` / ``z_q_st``
+        may be None for a single-level codebook (codes only)."""
+        n, D = flat.shape
+        mode = _MODES[self.search_mode]
+        cache = self._codebook_cache()
+        E = self.embedding
+        L = self.num_quantizers
+        if L == 1:
+            idx = idx_levels[0]
+            if ops.fused_supported(n, self.K, D, mode):      # one kernel: search + gather + loss + histogram
+                ops.quantize_fused(flat, E, cache, mode, idx, zq_out=z_q, zq_st_out=z_q_st,
+                                   sqerr_sum=sqerr if z_q is not None else None, hist=hist, row_mask=valid_u8)
+            elif os.environ.get("VQB200_SPLIT_GATHER") == "1":   # measurement switch: gather as a separate pass
+                ops.search(flat, E, cache, 0, mode, idx)
+                ops.gather(flat, E, idx, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist, row_mask=valid_u8)
+            else:                                            # search + gather, chunk-pipelined on the tensor path
+                ops.quantize(flat, E, cache, mode, idx, zq_out=z_q, zq_st_out=z_q_st,
+                             sqerr_sum=sqerr if z_q is not None else None,
+                             hist=hist, row_mask=valid_u8)   # z_q is gathered BEFORE the EMA mutates E (:189 -> :193)
+            if ema_ok:
+                self._ema_update(flat, idx, valid_u8)
+            return
+        residual = flat
+        spare = [torch.empty(n, D, dtype=torch.float32, device=flat.device) for _ in range(min(2, L - 1))]
+        for level in range(L):
+            idx_l = idx_levels[level]
+            if level > 0 and do_ema:
+                cache = self._codebook_cache()
+            ops.search(residual, E, cache, level, mode, idx_l)
+            nxt = spare[level % 2] if level < L - 1 else None
+            # level sum in level order (:261); RVQ histogram ignores the mask (:266)
+            ops.gather(residual, E, idx_l, zq_out=z_q, accumulate=level > 0, residual_out=nxt, hist=hist)
+            if ema_ok:
+                self._ema_update(residual, idx_l, valid_u8)
+            if nxt is not None:
+                residual = nxt
+        ops.st_loss(flat, z_q, zq_st_out=z_q_st, sqerr_sum=sqerr)
+
+    # ------------------------------------------------------------------ host-buffer entry (extraction path)
+    @torch.no_grad()
+    def forward_host(self, z_host: Tensor, chunk_rows: Optional[int] = None, outputs: str = "all",
+                     out_indices: Optional[Tensor] = None, wait: bool = True, token_major=None):
+        """Eval-mode forward over latents that live in (pinned) HOST memory -- the shape of
+        ``scripts/extract_code_indices.py:296-320``, where every batch is copied to the device, quantized and
+        its indices copied back.  The rows stream through a ring of device staging buffers: the H2D copy of
+        chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1's indices run on three streams, so a
+        call costs max(copy, compute) instead of their sum.
+
+        Returns ``(z_q_st, z_q, indices_host, stats_host)``: ``z_q_st`` / ``z_q`` stay on the device
+        (``None`` with ``outputs="indices"``, which also skips writing them), ``indices_host`` is a pinned
+        int64 tensor laid out as ``forward`` lays indices out, ``stats_host`` a pinned float32 [2].  With
+        ``token_major=torch.int32`` (or int16 / int64) the indices are re-laid out on the device to the
+        token-major ``[B, M * Q]`` array of that dtype which ``scripts/extract_code_indices.py:195-209`` saves,
+        chunk by chunk, and THAT is what is copied to the host.  With ``wait=False`` the host buffers are valid
+        only after the current stream has been synchronised."""
+        if outputs not in ("all", "indices"):
+            raise ValueError("outputs must be 'all' or 'indices'")
+        B, M, D = z_host.shape
+        if z_host.is_cuda:
+            raise RuntimeError("forward_host takes a host tensor; call forward() for device tensors")
+        if z_host.dtype != torch.float32:
+            raise RuntimeError(f"expected z_e of dtype float32 (the codebook's dtype), got {z_host.dtype}")
+        if D != self.D:
+            raise RuntimeError(f"z_e has last dim {D}, the codebook has D={self.D}")
+        dev = self.embedding.device
+        if dev.type != "cuda":
+            raise RuntimeError("VectorQuantizerEMA (libvqb200) needs its buffers on an sm_100a device")
+        flat_h = z_host.reshape(-1, D)
+        if not flat_h.is_contiguous():
+            flat_h = flat_h.contiguous()
+        if not flat_h.is_pinned():
+            flat_h = flat_h.pin_memory()                      # pageable memory would serialise the copies
+        N, L = flat_h.shape[0], self.num_quantizers
+        want_all = outputs == "all" or L > 1                  # the residual chain needs z_q anyway
+        if chunk_rows is None:        # 2^17 rows: >= 32 MB per copy (full PCIe rate), several waves of the tensor
+            chunk_rows = 1 << 17      # kernels per launch, and still dozens of chunks to pipeline at extraction sizes
+        n_chunks = max(1, -(-N // chunk_rows))
+        ring = min(3, n_chunks)
+
+        main = torch.cuda.current_stream(dev)
+        pipe = self._host_pipe(dev, ring)
+        s_in, s_out = pipe["in"], pipe["out"]
+        ev_in, ev_run = pipe["ev_in"], pipe["ev_run"]
+
+        scratch = torch.zeros(2 + self.K, dtype=torch.int32, device=dev)
+        sqerr, hist = scratch[:2].view(torch.float64), scratch[2:]
+        stats3 = torch.empty(3, dtype=torch.float32, device=dev)
+        stage = torch.empty(ring, min(chunk_rows, max(N, 1)), D, dtype=torch.float32, device=dev)
+        z_q = torch.empty(N, D, dtype=torch.float32, device=dev) if want_all else None
+        z_q_st = torch.empty(N, D, dtype=torch.float32, device=dev) if want_all else None
+        idt = torch.int64 if token_major is None else token_major
+        idx_all = torch.empty(L * N, dtype=torch.int64, device=dev) if token_major is None else None
+        tok_all = None if token_major is None else torch.empty(N * L, dtype=idt, device=dev)
+        if out_indices is None:
+            out_indices = torch.empty(L * N, dtype=idt).pin_memory()
+        idx_h = out_indices.view(-1)
+        if idx_h.numel() != L * N or idx_h.dtype != idt or idx_h.is_cuda:
+            raise RuntimeError(f"out_indices must be a host {idt} tensor of {L * N} elements")
+        stats_h = pipe["stats_h"]
+        self._codebook_cache()                                # refresh on the caller's stream, before the fork
+        fork = torch.cuda.Event()
+        fork.record(main)
+        s_in.wait_event(fork)
+        s_out.wait_event(fork)
+
+        for c in range(n_chunks):
+            r0, r1 = c * chunk_rows, min(N, (c + 1) * chunk_rows)
+            n, b = r1 - r0, c % ring
+            with torch.cuda.stream(s_in):
+                if c >= ring:
+                    s_in.wait_event(ev_run[b])                # the kernels of chunk c-ring are done with this buffer
+                stage[b, :n].copy_(flat_h[r0:r1], non_blocking=True)
+                ev_in[b].record(s_in)
+            main.wait_event(ev_in[b])
+            if tok_all is None:
+                idx_levels = [idx_all[l * N + r0:l * N + r1] for l in range(L)]
+            else:                                             # chunk-local level-major ids, re-laid out below
+                idx_c = torch.empty(L * n, dtype=torch.int64, device=dev)
+                idx_levels = [idx_c[l * n:(l + 1) * n] for l in range(L)]
+            self._quantize_rows(stage[b, :n], idx_levels,
+                                None if z_q is None else z_q[r0:r1], None if z_q_st is None else z_q_st[r0:r1],
+                                sqerr, hist, None)
+            if tok_all is not None:                           # rows r0:r1 of every level -> tokens [r0*L, r1*L)
+                ops.relayout_indices(idx_c, L, 1, n, idt, out=tok_all[r0 * L:r1 * L])
+            ev_run[b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run[b])
+                if tok_all is not None:
+                    idx_h[r0 * L:r1 * L].copy_(tok_all[r0 * L:r1 * L], non_blocking=True)
+                else:
+                    for l in range(L):
+                        idx_h[l * N + r0:l * N + r1].copy_(idx_all[l * N + r0:l * N + r1], non_blocking=True)
+        self._finalize_stats(hist, float(L * N), sqerr, N * D, stats3)
+        stats_h.copy_(stats3[:2], non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(s_out)
+        main.wait_event(done)                                 # the caller's stream sees every copy finished
+        if wait:
+            main.synchronize()
+        if token_major is not None:
+            idx_ret = out_indices.view(B, M * L)
+        else:
+            idx_ret = out_indices.view(B, M) if L == 1 else out_indices.view(-1)
+        if not want_all:
+            return None, None, idx_ret, stats_h
+        return z_q_st.view(B, M, D), z_q.view(B, M, D), idx_ret, stats_h
+
+    def _host_pipe(self, dev, ring):
+        p = getattr(self, "_hpipe", None)
+        if p is None or p["dev"] != dev:
+            p = self._hpipe = {"dev": dev, "in": torch.cuda.Stream(dev), "out": torch.cuda.Stream(dev),
+                               "ev_in": [torch.cuda.Event() for _ in range(3)],
+                               "ev_run": [torch.cuda.Event() for _ in range(3)],
+                               "stats_h": torch.empty(2, dtype=torch.float32).pin_memory()}
+        return p
 
     def _finalize_stats(self, hist, count_add, sqerr, n_elems, stats3):
         inv = 1.0 / max(n_elems, 1)

@@ -107,3 +107,54 @@ def test_graphed_forward_matches_eager(vq):
     with torch.no_grad():
         ref = q(z_other, do_ema_update=False)[2].clone()
     assert torch.equal(g(z_other)[2], ref)
+
+
+@pytest.mark.parametrize("K,N", [(512, 1 << 16), (1000, 300 * 64), (128, 4096)])
+def test_fused_tile_heights_agree(vq, K, N):
+    """BM = 128 (two CTAs per SM, default) and BM = 256 (one CTA per SM) are the same function."""
+    D = 64
+    E, z = large_case_inputs(900 + K, K, D, 1, N // 64, 64)
+    outs = {}
+    for bm in ("128", "256"):
+        os.environ["VQB200_FUSED_BM"] = bm
+        try:
+            outs[bm] = forward(vq, z, E, K, "fp32", fused=True)
+        finally:
+            os.environ.pop("VQB200_FUSED_BM", None)
+    a, b = outs["128"], outs["256"]
+    assert a[0] and b[0]
+    assert torch.equal(a[3], b[3]) and torch.equal(a[2], b[2]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[5]._ep_usage, b[5]._ep_usage)
+    np.testing.assert_allclose(float(a[5].last_commit), float(b[5].last_commit), rtol=1e-6)
+
+
+@pytest.mark.parametrize("K,D,L,N,chunk", [(512, 64, 1, 40000 // 64 * 64, 8192), (300, 128, 1, 6400, 4096),
+                                           (256, 128, 3, 6400, 2048), (512, 64, 1, 4096, None)])
+def test_forward_host_equals_forward(vq, K, D, L, N, chunk):
+    """The host-buffer entry (chunked H2D / kernels / D2H pipeline) returns what forward() returns."""
+    dev = torch.device("cuda:0")
+    E, z = large_case_inputs(500 + K + D, K, D, L, N // 64, 64)
+    q = vq.VectorQuantizerEMA(K, D, num_quantizers=L, print_init=False).to(dev).eval()
+    q.embedding.copy_(torch.from_numpy(E).to(dev))
+    zt = torch.from_numpy(z)
+    with torch.no_grad():
+        st, zq, idx, stats = q(zt.to(dev), do_ema_update=False)
+    usage1 = q._ep_usage.clone()
+    q.reset_epoch_stats()
+    st_h, zq_h, idx_h, stats_h = q.forward_host(zt.pin_memory(), chunk_rows=chunk)
+    assert not idx_h.is_cuda and idx_h.dtype == torch.int64 and idx_h.shape == idx.shape
+    assert torch.equal(idx_h, idx.cpu())
+    assert torch.equal(zq_h, zq) and torch.equal(st_h, st)
+    assert torch.equal(q._ep_usage, usage1)
+    np.testing.assert_allclose(stats_h.numpy(), stats.cpu().numpy(), rtol=1e-6)
+    # token-major int32 output == the re-layout of scripts/extract_code_indices.py:195-209 on forward()'s ids
+    _, _, tok_h, _ = q.forward_host(zt, chunk_rows=chunk, token_major=torch.int32)      # pageable input is pinned inside
+    B, M = z.shape[0], z.shape[1]
+    want = O.rvq_indices_batch_first(idx.cpu().numpy().reshape(-1), B, L) if L > 1 else idx.cpu().numpy().reshape(B, M)
+    assert tok_h.dtype == torch.int32 and tuple(tok_h.shape) == (B, M * L)
+    assert np.array_equal(tok_h.numpy().astype(np.int64), want)
+    # codes only
+    none_st, none_zq, idx_c, _ = q.forward_host(zt, chunk_rows=chunk, outputs="indices")
+    assert torch.equal(idx_c, idx.cpu())
+    if L == 1:
+        assert none_st is None and none_zq is None
