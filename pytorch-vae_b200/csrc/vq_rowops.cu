@@ -115,7 +115,7 @@ constexpr int GATHER_ILP = 4;   // independent 128-bit items per thread kept in 
 constexpr int HIST_SMEM_BINS = 2048;   // small codebooks: all counts land on a few L2 lines, privatise per CTA
 
 template <bool ACC, bool SMEM_HIST>
-__global__ void __launch_bounds__(ROW_THREADS, 3)
+__global__ void __launch_bounds__(ROW_THREADS, 4)
 gather_kernel(const float4* __restrict__ z, const float4* __restrict__ E, const int64_t* __restrict__ idx,
               int64_t N, int D4, int d4_shift, int K_total, float4* zq_out, float4* __restrict__ zq_st_out,
               float4* __restrict__ residual_out, double* sqerr_sum, int32_t* __restrict__ hist,

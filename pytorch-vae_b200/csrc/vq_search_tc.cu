@@ -374,7 +374,12 @@ constexpr int P2_CS = 2;            // column slices: 8 epilogue warps = 4 lane 
 constexpr int P2_NEPI = 8;
 constexpr int P2_WCOLS = P2_BN / P2_CS;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + P2_NEPI * 32, 1)
+// REGS caps the registers per thread.  At 128 (a few spills on the slow path) the ten warps of a CTA leave
+// 4096 registers free in every scheduler partition, which is what lets ONE 256-thread block of the chunk
+// pipeline's side kernels (pre-pass, re-rank, gather: <= 64 registers) co-reside with this persistent kernel
+// (an experiment switch: see launch_search_tc for the measurement; the default build is uncapped).
+template <int REGS>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(REGS)
 search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
                   const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -832,7 +837,7 @@ int tc_launches(int64_t N, int K, int D) {
 // Helper streams for the chunk pipeline (created once per device, never destroyed).
 struct TcPipe {
   bool ready = false;
-  cudaStream_t s1 = nullptr, s2 = nullptr;
+  cudaStream_t s1 = nullptr, s2 = nullptr, stc = nullptr;
   cudaEvent_t fork = nullptr, prep[2] = {nullptr, nullptr}, tc[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
 };
 static TcPipe* tc_pipe() {
@@ -841,8 +846,13 @@ static TcPipe* tc_pipe() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   TcPipe& p = pipes[dev];
   if (!p.ready) {
-    bool ok = cudaStreamCreateWithFlags(&p.s1, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&p.s2, cudaStreamNonBlocking) == cudaSuccess &&
+    // The tensor kernel gets its own HIGH-priority stream: when its CTAs and side-kernel blocks are both
+    // pending, the CTAs are placed first and the side blocks fill what is left of each SM.
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    bool ok = cudaStreamCreateWithPriority(&p.s1, cudaStreamNonBlocking, lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&p.s2, cudaStreamNonBlocking, lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&p.stc, cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i)
       ok = cudaEventCreateWithFlags(&p.prep[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -892,7 +902,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   const int n_chunks = static_cast<int>((N + pl.chunk_rows - 1) / pl.chunk_rows);
   TcPipe* pipe = n_chunks > 1 ? tc_pipe() : nullptr;
   const bool piped = pipe != nullptr;
-  cudaStream_t s_prep = piped ? pipe->s1 : s, s_rr = piped ? pipe->s2 : s;
+  cudaStream_t s_prep = piped ? pipe->s1 : s, s_rr = piped ? pipe->s2 : s, s_tc = piped ? pipe->stc : s;
 
   const size_t set_bytes = tc_set_bytes(cap, D, pl.BM);
   TcSet sets[2];
@@ -911,9 +921,16 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   int stages2 = (TC_SMEM_LIMIT - (1024 + zbufs2 * z2 + P2_NEPI * P2_WCOLS * 4 + 256)) / TC_STAGE_BYTES;
   if (stages2 > 8) stages2 = 8;
   const bool use2 = want2 && stages2 >= 3 && K >= P2_BN && cap >= static_cast<int64_t>(kNumSMs / 2) * 2 * P2_ROWS;
+  // VQB200_TC2_REGS=128 selects the register-capped build under which one side-kernel block per SM co-resides
+  // with the persistent tensor kernel.  Measured (c3, 2^22 rows): 19.2 ms per step against 17.4-17.9 ms -- the
+  // side kernels' warps take issue slots and LSU bandwidth from the epilogue (tensor kernel 2.9 -> 3.8 ms), which
+  // costs more than the overlap returns, so the default keeps the SMs to the tensor kernel.
+  const char* envr = std::getenv("VQB200_TC2_REGS");
+  const bool slim = envr && envr[0] == '1' && envr[1] == '2';
   static bool attr2_done = false;
   if (use2 && !attr2_done) {
-    VQ_CUDA(cudaFuncSetAttribute(search_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    VQ_CUDA(cudaFuncSetAttribute(search_tc2_kernel<168>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    VQ_CUDA(cudaFuncSetAttribute(search_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr2_done = true;
   }
   static bool attr_done[2] = {false, false};
@@ -927,6 +944,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     VQ_CUDA(cudaEventRecord(pipe->fork, s));
     VQ_CUDA(cudaStreamWaitEvent(s_prep, pipe->fork, 0));
     VQ_CUDA(cudaStreamWaitEvent(s_rr, pipe->fork, 0));
+    VQ_CUDA(cudaStreamWaitEvent(s_tc, pipe->fork, 0));
   }
 
   int ci = 0;
@@ -945,7 +963,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     VQ_CUDA(cudaGetLastError());
     if (piped) {
       VQ_CUDA(cudaEventRecord(pipe->prep[b], s_prep));
-      VQ_CUDA(cudaStreamWaitEvent(s, pipe->prep[b], 0));
+      VQ_CUDA(cudaStreamWaitEvent(s_tc, pipe->prep[b], 0));
     }
 
     // ---- stage 2: tensor-core candidates (caller's stream)
@@ -965,9 +983,10 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
       nsub = P2_CS;
       const int pairs = p.row_tiles < kNumSMs / 2 ? p.row_tiles : kNumSMs / 2;
       const int smem2 = 1024 + zbufs2 * z2 + stages2 * TC_STAGE_BYTES + P2_NEPI * P2_WCOLS * 4 + 256;
-      timing_mark_begin(s);
-      search_tc2_kernel<<<2 * pairs, 64 + P2_NEPI * 32, smem2, s>>>(map_z, map_e, p);
-      timing_mark_end(s);
+      timing_mark_begin(s_tc);
+      if (slim) search_tc2_kernel<128><<<2 * pairs, 64 + P2_NEPI * 32, smem2, s_tc>>>(map_z, map_e, p);
+      else search_tc2_kernel<168><<<2 * pairs, 64 + P2_NEPI * 32, smem2, s_tc>>>(map_z, map_e, p);
+      timing_mark_end(s_tc);
     } else {
     if (!make_map(&map_z, w.zb, rows, D, pl.BM)) return VQB200_EDRIVER;
     p.row_tiles = static_cast<int>((rows + pl.BM - 1) / pl.BM);
@@ -978,16 +997,16 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     nsub = p.ksplit * tc_cs(pl.BM);
     const int items = p.row_tiles * p.ksplit;
     const int grid = items < kNumSMs ? items : kNumSMs;
-    timing_mark_begin(s);
+    timing_mark_begin(s_tc);
     if (pl.BM == 256)
-      search_tc_kernel<256><<<grid, 64 + 256 * tc_cs(256), pl.smem_bytes, s>>>(map_z, map_e, p);
+      search_tc_kernel<256><<<grid, 64 + 256 * tc_cs(256), pl.smem_bytes, s_tc>>>(map_z, map_e, p);
     else
-      search_tc_kernel<128><<<grid, 64 + 128 * tc_cs(128), pl.smem_bytes, s>>>(map_z, map_e, p);
-    timing_mark_end(s);
+      search_tc_kernel<128><<<grid, 64 + 128 * tc_cs(128), pl.smem_bytes, s_tc>>>(map_z, map_e, p);
+    timing_mark_end(s_tc);
     }
     VQ_CUDA(cudaGetLastError());
     if (piped) {
-      VQ_CUDA(cudaEventRecord(pipe->tc[b], s));
+      VQ_CUDA(cudaEventRecord(pipe->tc[b], s_tc));
       VQ_CUDA(cudaStreamWaitEvent(s_rr, pipe->tc[b], 0));
     }
 
