@@ -30,9 +30,9 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 1
+#define VQB200_ABI_VERSION 2
 #define VQB200_MAX_LEVELS 32
-#define VQB200_LEVEL_META_FLOATS 4 /* per level: max|e|, non-finite flag, max|bf16(e)|, reserved */
+#define VQB200_LEVEL_META_FLOATS 4 /* per level: max|e|, non-finite flag, max|bf16(e)|, max|e - bf16(e)| */
 
 enum {
   VQB200_OK = 0,
@@ -150,6 +150,12 @@ VQB200_API int vqb200_ema_finalize(const float* seg_sum, const float* seg_cnt, f
                         float eps, int K_total, int D, int K_per, float* ema_cluster_size,
                         float* ema_embedding, float* E, uint16_t* E_bf16, float* ee_half,
                         float* level_meta, void* stream);
+
+/* Lloyd step of the k-means codebook initialiser (the `--init_codebook` centroids of run.py:74-89 that
+ * models/vq_vae.py:577-613 copies in): E[k] <- seg_sum[k] / seg_cnt[k] where seg_cnt[k] > 0, an empty cluster
+ * keeps its centroid; the derived cache is refreshed in the same pass.  seg_* come from vqb200_scatter_add. */
+VQB200_API int vqb200_kmeans_finalize(const float* seg_sum, const float* seg_cnt, int K_total, int D, int K_per,
+                           float* E, uint16_t* E_bf16, float* ee_half, float* level_meta, void* stream);
 
 /* Backward of the two differentiable outputs (straight-through + commitment):
  *   grad_z = grad_st + (*grad_commit) * scale * (z - zq),  scale = 2 / (N D)

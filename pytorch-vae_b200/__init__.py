@@ -8,5 +8,7 @@ from . import _cabi, ops  # noqa: F401  (loads the shared library; ImportError i
 from .quantizer import VectorQuantizer, VectorQuantizerEMA  # noqa: F401
 from .integration import install, uninstall  # noqa: F401
 from .graphs import GraphedForward  # noqa: F401
+from .kmeans import kmeans_fit, rvq_kmeans_fit  # noqa: F401
 
-__all__ = ["VectorQuantizerEMA", "VectorQuantizer", "GraphedForward", "install", "uninstall", "ops"]
+__all__ = ["VectorQuantizerEMA", "VectorQuantizer", "GraphedForward", "kmeans_fit", "rvq_kmeans_fit", "install",
+           "uninstall", "ops"]

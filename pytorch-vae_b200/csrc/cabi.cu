@@ -80,7 +80,7 @@ int vqb200_codebook_prepare(const float* E, int K_total, int D, int K_per, uint1
   VQ_REQUIRE(K_total > 0 && K_per > 0, VQB200_EINVAL);
   VQ_REQUIRE(shape_ok(D) && K_total % K_per == 0 && K_total / K_per <= VQB200_MAX_LEVELS, VQB200_ESHAPE);
   VQ_REQUIRE(aligned16(E) && aligned16(E_bf16), VQB200_EALIGN);
-  return launch_codebook_refresh(false, nullptr, nullptr, 0.f, 0.f, 0.f, K_total, D, K_per, nullptr, nullptr,
+  return launch_codebook_refresh(0, nullptr, nullptr, 0.f, 0.f, 0.f, K_total, D, K_per, nullptr, nullptr,
                                  const_cast<float*>(E), E_bf16, ee_half, level_meta,
                                  static_cast<cudaStream_t>(stream));
 }
@@ -219,9 +219,19 @@ int vqb200_ema_finalize(const float* seg_sum, const float* seg_cnt, float decay,
   VQ_REQUIRE(K_total > 0 && K_per > 0, VQB200_EINVAL);
   VQ_REQUIRE(shape_ok(D) && K_total % K_per == 0 && K_total / K_per <= VQB200_MAX_LEVELS, VQB200_ESHAPE);
   VQ_REQUIRE(aligned16(seg_sum) && aligned16(ema_embedding) && aligned16(E) && aligned16(E_bf16), VQB200_EALIGN);
-  return launch_codebook_refresh(true, seg_sum, seg_cnt, decay, one_minus_decay, eps, K_total, D, K_per,
+  return launch_codebook_refresh(1, seg_sum, seg_cnt, decay, one_minus_decay, eps, K_total, D, K_per,
                                  ema_cluster_size, ema_embedding, E, E_bf16, ee_half, level_meta,
                                  static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_kmeans_finalize(const float* seg_sum, const float* seg_cnt, int K_total, int D, int K_per, float* E,
+                           uint16_t* E_bf16, float* ee_half, float* level_meta, void* stream) {
+  VQ_REQUIRE(seg_sum && seg_cnt && E && E_bf16 && ee_half && level_meta, VQB200_EINVAL);
+  VQ_REQUIRE(K_total > 0 && K_per > 0, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D) && K_total % K_per == 0 && K_total / K_per <= VQB200_MAX_LEVELS, VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(seg_sum) && aligned16(E) && aligned16(E_bf16), VQB200_EALIGN);
+  return launch_codebook_refresh(2, seg_sum, seg_cnt, 0.f, 0.f, 0.f, K_total, D, K_per, nullptr, nullptr, E, E_bf16,
+                                 ee_half, level_meta, static_cast<cudaStream_t>(stream));
 }
 
 int vqb200_commit_backward(const float* grad_st, const float* grad_commit, const float* z, const float* zq,

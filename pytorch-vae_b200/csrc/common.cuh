@@ -63,6 +63,19 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Internal launchers (defined in the .cu files, called from cabi.cu).
 namespace vqb {
 // measurement hook, see vqb200_timing_enable
+// Admission margin of one row in fp32 mode.  The tensor core scores s~ = z~.e~ - |e|^2/2 with z~ = bf16(z),
+// e~ = bf16(e); the exact score is s = z.e - |e|^2/2, and
+//     s~ - s = (z~ - z).e~ + z.(e~ - e)   =>   |s~ - s| <= |z - z~| |e~| + |z| |e - e~|      (Cauchy-Schwarz)
+// with the ACTUAL rounding-error norms |z - z~| (this row, summed while converting) and max_k |e_k - e~_k|
+// (codebook cache, level_meta[3]) -- tighter than the worst case (2u + u^2)|z||e|, u = 2^-8, by about 2.5x and
+// rigorous all the same.  For the true arg max a and the approximate one b:  s~_a >= s~_b - (err_a + err_b), so
+// the margin is twice the bound, +4 % for the fp32 accumulation inside the tensor core (<= D 2^-23 |z||e|,
+// D <= 512) and an absolute term for the rounding of the fp32 bias.  ss = |z|^2, sse = |z - z~|^2.
+__device__ __forceinline__ float admission_margin_fp32(float ss, float sse, float emax, float emax_b, float rho_e) {
+  const float nz = sqrtf(ss) * 1.0001f, ne = sqrtf(sse) * 1.0001f;
+  return 2.08f * (ne * emax_b + nz * rho_e) + 1e-6f * emax * (emax + nz) + 1e-30f;
+}
+
 void timing_mark_begin(cudaStream_t s);
 void timing_mark_end(cudaStream_t s);
 int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, int D, const float* E,
@@ -94,7 +107,7 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
                           const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                           int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
                           const uint8_t* row_mask, void* workspace, size_t workspace_bytes, cudaStream_t s);
-int launch_codebook_refresh(bool ema, const float* seg_sum, const float* seg_cnt, float decay, float omd,
+int launch_codebook_refresh(int mode, const float* seg_sum, const float* seg_cnt, float decay, float omd,
                             float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb, float* E,
                             uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s);
 int launch_gather(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int K_total, float* zq_out,

@@ -13,10 +13,7 @@ constexpr int TC_KB = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int TC_STAGE_BYTES = TC_BN * TC_KB * 2;   // 16 KB
 constexpr int TC_SMEM_LIMIT = 232448;               // 227 KB
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 22;
-// suspend-time hint of mbarrier.try_wait: a waiting warp sleeps in hardware until the phase completes (or this
-// many ns pass) instead of re-issuing the poll every ~30 cycles -- the producer / MMA warps' polls were 20 % of
-// all issued instructions of the fused kernel, taken from the schedulers the epilogue warps run on
-constexpr uint32_t kMbarSuspendNs = 20000;
+constexpr uint32_t kMbarSuspendNs = 20000;          // suspend-time hint of mbar_wait_sleep
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -31,7 +28,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Spin on the phase (lowest wake-up latency): the tensor-bound search kernels, whose waits sit on the MMA
+// critical path (measured: the suspending form below costs the pair kernel 4 % at K=8192 D=256).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > TC_SPIN_LIMIT) __trap();   // a protocol bug must fault, never hang the GPU
+  }
+}
+// Same wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint
+// expires) instead of re-issuing the poll every ~30 cycles.  For kernels whose producer / MMA warps wait long and
+// share schedulers with latency-bound epilogue warps (the fused small-D kernel: polls were 20 % of its issued
+// instructions).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
@@ -42,7 +59,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity), "r"(kMbarSuspendNs)
         : "memory");
     if (done) break;
-    if (++spins > TC_SPIN_LIMIT) __trap();   // a protocol bug must fault, never hang the GPU
+    if (++spins > TC_SPIN_LIMIT) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {

@@ -169,7 +169,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     // ============================== TMA producer ==============================
     uint32_t stage = 0, phase = 0, it = 0;
     auto load_z = [&](int item, uint32_t seq) {
-      mbar_wait(bar_zfempty, (seq & 1) ^ 1);
+      mbar_wait_sleep(bar_zfempty, (seq & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(bar_zffull, ZF_BYTES);
         for (int kb = 0; kb < KB32; ++kb)
@@ -183,7 +183,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       if (nxt < n_items) load_z(nxt, it + 1);       // the next tile's latents ride ahead of this tile's codebook blocks
       for (int t = 0; t < p.code_tiles; ++t) {
         for (int kb = 0; kb < KBLK; ++kb) {
-          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          mbar_wait_sleep(bar_empty + 8 * stage, phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
             tma_load_2d(e_smem + stage * TC_STAGE_BYTES, &tmap_e, bar_full + 8 * stage, kb * TC_KB, t * TC_BN);
@@ -199,13 +199,13 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     const uint32_t zb_lo = umma_desc_lo(zb_smem), e_lo = umma_desc_lo(e_smem);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t zb = 0;
-      mbar_wait(bar_zbfull, it & 1);
+      mbar_wait_sleep(bar_zbfull, it & 1);
       for (int t = 0; t < p.code_tiles; ++t, ++tg) {
         const uint32_t b = tg & 1;
-        mbar_wait(bar_tempty + 8 * b, (tg >> 1) & 1);       // drained AND pre-loaded with -|e|^2/2
+        mbar_wait_sleep(bar_tempty + 8 * b, (tg >> 1) & 1);       // drained AND pre-loaded with -|e|^2/2
         tc_fence_after();
         for (int kb = 0; kb < KBLK; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
+          mbar_wait_sleep(bar_full + 8 * stage, phase);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a0 = zb_lo + ((zb * ZB_BYTES + kb * (FZ_BM * 128)) >> 4);
@@ -231,9 +231,9 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     // ============================== converters: fp32 tile -> bf16 operand tile + margins ==============================
     const int ct = (warp - 2 - FZ_NEPI) * 32 + lane;     // 0..63: rows ct, ct+64, ct+128, ct+192 of the tile
     const float emax = BF16 ? p.level_meta[2] : p.level_meta[0];
+    const float emax_b = p.level_meta[2], rho_e = p.level_meta[3];
     const bool code_bad = p.level_meta[1] != 0.f;
-    const float coef = BF16 ? 2.f * static_cast<float>(D + 32) * 1.1920929e-7f
-                                                        : 2.f * 0.00391007f * 1.02f;
+    const float coef = 2.f * static_cast<float>(D + 32) * 1.1920929e-7f;      // bf16 mode (see zprep_kernel)
     // Output phase of a finished tile (z_q, z_q_st, squared error), run by these warps one tile behind the
     // epilogue: the epilogue warps publish the tile's resolved codes in shared memory and move on to the next
     // tile's scan, so the L2 / HBM round trips of the outputs are off the scan -> re-rank critical path.
@@ -244,7 +244,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
                                   // epilogue its registers: 13-16 warps cap every thread at 128)
       constexpr int SL = D / (LPV * 4);
       const uint32_t rbuf = ito & 1;
-      mbar_wait(bar_resfull + 8 * rbuf, (ito >> 1) & 1);
+      mbar_wait_sleep(bar_resfull + 8 * rbuf, (ito >> 1) & 1);
       const uint32_t* rs = res_s + rbuf * FZ_BM;
       const int64_t row0 = static_cast<int64_t>(item_o) * FZ_BM;
       const int ogl = ct % LPV, ogr = ct / LPV;
@@ -297,14 +297,14 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     int item_prev = -1;
     for (int item = blockIdx.x; item < n_items; item_prev = item, item += gridDim.x, ++it) {
       const uint32_t zb = 0, mb = it & 1;
-      mbar_wait(bar_zffull, it & 1);
-      mbar_wait(bar_zbempty, (it & 1) ^ 1);             // the MMAs of the previous tile have retired
+      mbar_wait_sleep(bar_zffull, it & 1);
+      mbar_wait_sleep(bar_zbempty, (it & 1) ^ 1);             // the MMAs of the previous tile have retired
 #pragma unroll 1
       for (int rr = 0; rr < (FZ_BM + FZ_NCONV * 32 - 1) / (FZ_NCONV * 32); ++rr) {
         const int r = ct + rr * (FZ_NCONV * 32);
         if (r >= FZ_BM) break;
         const uint32_t sw = static_cast<uint32_t>(r & 7);
-        float ss = 0.f;
+        float ss = 0.f, sse = 0.f;
 #pragma unroll
         for (int q = 0; q < D / 8; ++q) {             // one 16-byte bf16 chunk (8 elements) per step
           const int c = q * 8;                        // first column of the chunk
@@ -323,16 +323,20 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
           const int bslab = c / TC_KB, bj = (c % TC_KB) / 8;
           uint8_t* dst = gen + (zb_smem - base) + zb * ZB_BYTES + bslab * (FZ_BM * 128) + r * 128;
           *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(bj) ^ sw) << 4)) = pk;
+          const float2 a = __bfloat1622float2(p0), b2 = __bfloat1622float2(p1), c2 = __bfloat1622float2(p2),
+                       d2 = __bfloat1622float2(p3);
           if (BF16) {
-            const float2 a = __bfloat1622float2(p0), b2 = __bfloat1622float2(p1), c2 = __bfloat1622float2(p2),
-                         d2 = __bfloat1622float2(p3);
             ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y + c2.x * c2.x + c2.y * c2.y + d2.x * d2.x + d2.y * d2.y;
           } else {
             ss += lo.x * lo.x + lo.y * lo.y + lo.z * lo.z + lo.w * lo.w + hi.x * hi.x + hi.y * hi.y + hi.z * hi.z + hi.w * hi.w;
+            const float e0 = lo.x - a.x, e1 = lo.y - a.y, e2 = lo.z - b2.x, e3 = lo.w - b2.y,      // exact differences
+                        e4 = hi.x - c2.x, e5 = hi.y - c2.y, e6 = hi.z - d2.x, e7 = hi.w - d2.y;
+            sse += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 + e4 * e4 + e5 * e5 + e6 * e6 + e7 * e7;
           }
         }
-        float m = coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f;
-        if (code_bad || !(ss < __int_as_float(0x7f800000))) m = __int_as_float(0x7fc00000);   // NaN: exact path
+        float m = BF16 ? coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f : admission_margin_fp32(ss, sse, emax, emax_b, rho_e);
+        if (code_bad || !(ss < __int_as_float(0x7f800000)) || !(sse < __int_as_float(0x7f800000)))
+          m = __int_as_float(0x7fc00000);   // NaN: exact path
         margin_s[mb * FZ_BM + r] = m;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
@@ -402,7 +406,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       const int64_t row0w = static_cast<int64_t>(item) * FZ_BM + row_in_tile;
       const int64_t row = row0w + lane;
       const bool row_ok = row < p.n_rows;
-      mbar_wait(bar_zbfull, it & 1);                          // margins of this tile are in shared memory
+      mbar_wait_sleep(bar_zbfull, it & 1);                          // margins of this tile are in shared memory
       const float margin = row_ok ? margin_s[(it & 1) * FZ_BM + row_in_tile + lane] : __int_as_float(0x7fc00000);
       float best = kNegInf;
       float thr = margin == margin ? best : margin;
@@ -416,7 +420,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
         const int t_cur_ahead = t_ahead;
         t_ahead = la_next();
         bias_next = load_bias(t_ahead);
-        mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
+        mbar_wait_sleep(bar_tfull + 8 * b, (tg >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + tcol + b * (HALVES * TC_BN);
         // One 32-column chunk in registers at a time (measured: double-buffering the TMEM loads buys nothing
@@ -589,7 +593,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       }
       if (p.zq_out || p.zq_st_out || p.sqerr_sum) {              // publish the codes; the output warps take over
         const uint32_t rbuf = it & 1, use = it >> 1;
-        if (use >= 1) mbar_wait(bar_resempty + 8 * rbuf, (use - 1) & 1);
+        if (use >= 1) mbar_wait_sleep(bar_resempty + 8 * rbuf, (use - 1) & 1);
         res_s[rbuf * FZ_BM + row_in_tile + lane] = resolved ? my_idx : FZ_EMPTY;
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_resfull + 8 * rbuf);

@@ -9,7 +9,10 @@ namespace vqb {
 // --------------------------------------------------------------------------------------------
 // codebook refresh: one warp per code row
 // --------------------------------------------------------------------------------------------
-template <bool EMA>
+// MODE 0: derive the cache from E.  MODE 1: EMA update (models/vq_vae.py:85-89) then the cache.
+// MODE 2: Lloyd step of the k-means initialiser -- E <- segment mean where the segment is non-empty (an empty
+// cluster keeps its centroid), then the cache.
+template <int MODE>
 __global__ void __launch_bounds__(256)
 codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restrict__ seg_cnt, float decay,
                         float omd, float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb,
@@ -19,7 +22,9 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= K_total) return;
   const int D4 = D >> 2;
+  constexpr bool EMA = MODE == 1;
   float denom = 1.f;
+  if (MODE == 2) denom = seg_cnt[row];
   if (EMA) {
     // models/vq_vae.py:85: cs.mul_(decay).add_(n * (1 - decay)) -- two roundings, no fma contraction
     const float cs = __fadd_rn(__fmul_rn(ema_cs[row], decay), __fmul_rn(seg_cnt[row], omd));
@@ -27,7 +32,7 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
     if (lane == 0) ema_cs[row] = cs;
     denom = __fadd_rn(cs, eps);
   }
-  double acc = 0.0, accb = 0.0;
+  double acc = 0.0, accb = 0.0, accd = 0.0;
   bool bad = false;
   for (int c = lane; c < D4; c += 32) {
     const int64_t o = static_cast<int64_t>(row) * D4 + c;
@@ -44,6 +49,11 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
       e.x = __fdiv_rn(n.x, denom); e.y = __fdiv_rn(n.y, denom);       // :88 E = es / (cs + eps)
       e.z = __fdiv_rn(n.z, denom); e.w = __fdiv_rn(n.w, denom);
       reinterpret_cast<float4*>(E)[o] = e;
+    } else if (MODE == 2 && denom > 0.f) {
+      const float4 sm = reinterpret_cast<const float4*>(seg_sum)[o];
+      e.x = __fdiv_rn(sm.x, denom); e.y = __fdiv_rn(sm.y, denom);
+      e.z = __fdiv_rn(sm.z, denom); e.w = __fdiv_rn(sm.w, denom);
+      reinterpret_cast<float4*>(E)[o] = e;
     } else {
       e = reinterpret_cast<const float4*>(E)[o];
     }
@@ -59,10 +69,15 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
            static_cast<double>(e.z) * e.z + static_cast<double>(e.w) * e.w;
     accb += static_cast<double>(f0) * f0 + static_cast<double>(f1) * f1 + static_cast<double>(f2) * f2 +
             static_cast<double>(f3) * f3;
+    {   // |e - bf16(e)|^2: the ACTUAL rounding error of this row (each difference is exact in fp32)
+      const double d0 = e.x - f0, d1 = e.y - f1, d2 = e.z - f2, d3 = e.w - f3;
+      accd += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
     bad |= !(isfinite(e.x) && isfinite(e.y) && isfinite(e.z) && isfinite(e.w));
   }
   acc = warp_sum(acc);
   accb = warp_sum(accb);
+  accd = warp_sum(accd);
   bad = __any_sync(0xffffffffu, bad);
   if (lane == 0) {
     ee_half[row] = static_cast<float>(0.5 * acc);
@@ -72,11 +87,13 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
     const float n0 = static_cast<float>(sqrt(acc)) * 1.0000002f, n1 = static_cast<float>(sqrt(accb)) * 1.0000002f;
     if (n0 == n0 && n0 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 0), __float_as_int(n0));
     if (n1 == n1 && n1 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 2), __float_as_int(n1));
+    const float n3 = static_cast<float>(sqrt(accd)) * 1.0000002f;          // max_k |e_k - bf16(e_k)|
+    if (n3 == n3 && n3 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 3), __float_as_int(n3));
     if (bad || !(acc == acc) || isinf(static_cast<float>(acc))) meta[1] = 1.0f;
   }
 }
 
-int launch_codebook_refresh(bool ema, const float* seg_sum, const float* seg_cnt, float decay, float omd,
+int launch_codebook_refresh(int mode, const float* seg_sum, const float* seg_cnt, float decay, float omd,
                             float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb, float* E,
                             uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s) {
   const int levels = K_total / K_per;
@@ -84,12 +101,15 @@ int launch_codebook_refresh(bool ema, const float* seg_sum, const float* seg_cnt
   if (e != cudaSuccess) return status_of(e);
   const int wpb = 8;
   const int blocks = (K_total + wpb - 1) / wpb;
-  if (ema)
-    codebook_refresh_kernel<true><<<blocks, wpb * 32, 0, s>>>(seg_sum, seg_cnt, decay, omd, eps, K_total, D,
-                                                             K_per, ema_cs, ema_emb, E, E_bf16, ee_half, level_meta);
+  if (mode == 1)
+    codebook_refresh_kernel<1><<<blocks, wpb * 32, 0, s>>>(seg_sum, seg_cnt, decay, omd, eps, K_total, D,
+                                                          K_per, ema_cs, ema_emb, E, E_bf16, ee_half, level_meta);
+  else if (mode == 2)
+    codebook_refresh_kernel<2><<<blocks, wpb * 32, 0, s>>>(seg_sum, seg_cnt, 0.f, 0.f, 0.f, K_total, D, K_per,
+                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta);
   else
-    codebook_refresh_kernel<false><<<blocks, wpb * 32, 0, s>>>(nullptr, nullptr, 0.f, 0.f, 0.f, K_total, D, K_per,
-                                                              nullptr, nullptr, E, E_bf16, ee_half, level_meta);
+    codebook_refresh_kernel<0><<<blocks, wpb * 32, 0, s>>>(nullptr, nullptr, 0.f, 0.f, 0.f, K_total, D, K_per,
+                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta);
   return status_of(cudaGetLastError());
 }
 
@@ -115,7 +135,7 @@ constexpr int GATHER_ILP = 4;   // independent 128-bit items per thread kept in 
 constexpr int HIST_SMEM_BINS = 2048;   // small codebooks: all counts land on a few L2 lines, privatise per CTA
 
 template <bool ACC, bool SMEM_HIST>
-__global__ void __launch_bounds__(ROW_THREADS, 4)
+__global__ void __launch_bounds__(ROW_THREADS, 3)
 gather_kernel(const float4* __restrict__ z, const float4* __restrict__ E, const int64_t* __restrict__ idx,
               int64_t N, int D4, int d4_shift, int K_total, float4* zq_out, float4* __restrict__ zq_st_out,
               float4* __restrict__ residual_out, double* sqerr_sum, int32_t* __restrict__ hist,

@@ -6,8 +6,9 @@
 // cannot decide near-ties, so the epilogue does not pick a winner; it keeps, per row, every code
 // whose approximate score  s~ = z~.e~ - |e|^2/2  lies within a RIGOROUS error bound of the running
 // maximum:
-//     |z~.e~ - z.e| <= (2u + u^2) |z||e|,  u = 2^-9 (bf16 round-to-nearest)  [+ fp32 accumulation slack]
-// so the true argmax a satisfies  s~_a >= max s~ - margin,  margin = 2 (2u+u^2) |z| max_k|e_k| * 1.02.
+//     |z~.e~ - z.e| <= |z - z~| max|e~| + |z| max|e - e~|      [+ fp32 accumulation slack]
+// (the ACTUAL rounding-error norms of the row and of the codebook, see admission_margin_fp32 in common.cuh)
+// so the true argmax a satisfies  s~_a >= max s~ - margin,  margin = 2 x that bound x 1.04.
 // A tiny re-rank kernel then evaluates the few survivors exactly (fp64 accumulation of the fp32
 // inputs) and takes the lowest index among exact ties.  Rows whose list overflows, rows with
 // non-finite values and non-finite codebooks are handed to the exact SIMT kernel.  In bf16-input
@@ -38,14 +39,15 @@ zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const floa
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   const int D4 = D >> 2;
-  const float emax = mode == VQB200_MODE_BF16_INPUT ? level_meta[2] : level_meta[0];
+  const bool bfm = mode == VQB200_MODE_BF16_INPUT;
+  const float emax = bfm ? level_meta[2] : level_meta[0];
+  const float emax_b = level_meta[2], rho_e = level_meta[3];
   const bool code_bad = level_meta[1] != 0.f;
-  // fp32 mode: 2 (2u + u^2) with u = 2^-9, +2% for the fp32 accumulation inside the tensor core
+  // fp32 mode: admission_margin_fp32 (common.cuh)
   // bf16 mode: inputs are exact, only accumulation order differs: 2 (D + 32) 2^-23
-  const float coef = mode == VQB200_MODE_BF16_INPUT ? 2.f * static_cast<float>(D + 32) * 1.1920929e-7f
-                                                    : 2.f * 0.00391007f * 1.02f;
+  const float coef = 2.f * static_cast<float>(D + 32) * 1.1920929e-7f;
   for (int64_t row = warp; row < n; row += nwarps) {
-    float ss = 0.f;
+    float ss = 0.f, sse = 0.f;
     for (int c = lane; c < D4; c += 32) {
       const float4 v = ld_stream(reinterpret_cast<const float4*>(z) + row * D4 + c);
       const __nv_bfloat16 b0 = __float2bfloat16_rn(v.x), b1 = __float2bfloat16_rn(v.y),
@@ -54,18 +56,22 @@ zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const floa
       pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(b0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
       pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(b2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b3)) << 16);
       reinterpret_cast<uint2*>(zb)[row * D4 + c] = pk;
-      if (mode == VQB200_MODE_BF16_INPUT) {
-        const float f0 = __bfloat162float(b0), f1 = __bfloat162float(b1), f2 = __bfloat162float(b2),
-                    f3 = __bfloat162float(b3);
+      const float f0 = __bfloat162float(b0), f1 = __bfloat162float(b1), f2 = __bfloat162float(b2),
+                  f3 = __bfloat162float(b3);
+      if (bfm) {
         ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
       } else {
         ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        const float d0 = v.x - f0, d1 = v.y - f1, d2 = v.z - f2, d3 = v.w - f3;      // exact differences
+        sse += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
       }
     }
     ss = warp_sum(ss);
+    sse = warp_sum(sse);
     if (lane == 0) {
-      float m = coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f;
-      if (code_bad || !(ss < __int_as_float(0x7f800000))) m = __int_as_float(0x7fc00000);   // NaN: exact path
+      float m = bfm ? coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f : admission_margin_fp32(ss, sse, emax, emax_b, rho_e);
+      if (code_bad || !(ss < __int_as_float(0x7f800000)) || !(sse < __int_as_float(0x7f800000)))
+        m = __int_as_float(0x7fc00000);   // NaN: exact path
       margin[row] = m;
     }
   }
@@ -902,7 +908,12 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   const int n_chunks = static_cast<int>((N + pl.chunk_rows - 1) / pl.chunk_rows);
   TcPipe* pipe = n_chunks > 1 ? tc_pipe() : nullptr;
   const bool piped = pipe != nullptr;
-  cudaStream_t s_prep = piped ? pipe->s1 : s, s_rr = piped ? pipe->s2 : s, s_tc = piped ? pipe->stc : s;
+  // VQB200_TC_PRIO=1 runs the tensor kernel on a high-priority helper stream (measured: 17.9 ms against 17.4 ms
+  // per c3 step on the caller's stream -- nothing co-resides with the persistent kernel, so priority only adds
+  // event hops); the default keeps it on the caller's stream.
+  const char* envp = std::getenv("VQB200_TC_PRIO");
+  const bool prio = piped && envp && envp[0] == '1';
+  cudaStream_t s_prep = piped ? pipe->s1 : s, s_rr = piped ? pipe->s2 : s, s_tc = prio ? pipe->stc : s;
 
   const size_t set_bytes = tc_set_bytes(cap, D, pl.BM);
   TcSet sets[2];
@@ -944,7 +955,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     VQ_CUDA(cudaEventRecord(pipe->fork, s));
     VQ_CUDA(cudaStreamWaitEvent(s_prep, pipe->fork, 0));
     VQ_CUDA(cudaStreamWaitEvent(s_rr, pipe->fork, 0));
-    VQ_CUDA(cudaStreamWaitEvent(s_tc, pipe->fork, 0));
+    if (prio) VQ_CUDA(cudaStreamWaitEvent(s_tc, pipe->fork, 0));
   }
 
   int ci = 0;

@@ -165,6 +165,14 @@ def ema_finalize(seg_sum, seg_cnt, decay, eps, ema_cluster_size, ema_embedding, 
     _count(1)
 
 
+def kmeans_finalize(seg_sum, seg_cnt, E, cache: CodebookCache):
+    """Lloyd step: E[k] <- mean of the rows assigned to k (empty clusters keep their centroid) + cache refresh."""
+    check(lib.vqb200_kmeans_finalize(ptr(seg_sum), ptr(seg_cnt), cache.K_total, cache.D, cache.K_per, ptr(E),
+                                     ptr(cache.E_bf16), ptr(cache.ee_half), ptr(cache.level_meta), stream_ptr()),
+          "vqb200_kmeans_finalize")
+    _count(1)
+
+
 def commit_backward(grad_st, grad_commit, z, zq, scale, out):
     check(lib.vqb200_commit_backward(ptr(grad_st), ptr(grad_commit), ptr(z), ptr(zq), z.numel(), float(scale),
                                      ptr(out), stream_ptr()), "vqb200_commit_backward")

@@ -147,3 +147,57 @@ def test_cta_pair_kernel_matches_single_cta(vq, K, D, N):
     ref = O.nearest_code64(z.reshape(-1, D), E)
     mm, outside = O.near_tie_rows(z.reshape(-1, D), E, idx2, ref)
     assert outside.size == 0 and mm.size <= 2
+
+
+def _bf16(a):
+    return torch.from_numpy(np.asarray(a, dtype=np.float32)).bfloat16().float().numpy()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_margin_holds_when_rounding_errors_align(vq, fused):
+    """Adversarial rounding: every element of the latent and of code a sits just BELOW a bf16 rounding
+    midpoint on dims 0..31 (their product is under-estimated by 2u, u = 2^-8) and just ABOVE one on dims
+    32..62 for code b (over-estimated by 2u).  The approximate scores prefer b by ~0.44 although a wins
+    exactly by ~0.047 -- more than the worst-case-halved bound 2(2u'+u'^2)|z||e| with u' = 2^-9 admits, less
+    than the bound from the actual rounding-error norms (common.cuh: admission_margin_fp32)."""
+    D, K, N = 64, 256, 8192
+    f64 = lambda v: v.astype(np.float64)
+    x_dn, x_up = np.float32(1 + 2.0 ** -8 - 2.0 ** -16), np.float32(1 + 2.0 ** -8 + 2.0 ** -16)
+    z1 = np.zeros(D, np.float32); z1[:32] = x_dn; z1[32:63] = x_up; z1[63] = 1.0
+    ea = np.zeros(D, np.float32); ea[:32] = x_dn; ea[63] = np.float32(-49 / 128)
+    eb = np.zeros(D, np.float32); eb[32:63] = x_up
+    s = lambda zz, e, e0: float(f64(zz) @ f64(e) - 0.5 * (f64(e0) ** 2).sum())
+    gap_exact = s(z1, ea, ea) - s(z1, eb, eb)
+    gap_approx = s(_bf16(z1), _bf16(eb), eb) - s(_bf16(z1), _bf16(ea), ea)
+    nz, emax = np.linalg.norm(f64(z1)), max(np.linalg.norm(f64(ea)), np.linalg.norm(f64(eb)))
+    assert 0.03 < gap_exact < 0.06 and gap_approx > 2 * 0.00391007 * 1.02 * nz * emax        # the old margin loses a
+    rz = np.linalg.norm(f64(z1 - _bf16(z1)))
+    re = max(np.linalg.norm(f64(ea - _bf16(ea))), np.linalg.norm(f64(eb - _bf16(eb))))
+    emb = max(np.linalg.norm(f64(_bf16(ea))), np.linalg.norm(f64(_bf16(eb))))
+    assert gap_approx < 2.0 * (rz * emb + nz * re)                                              # the new one keeps it
+
+    rs = np.random.RandomState(5)
+    E = (rs.standard_normal((K, D)) * 0.25).astype(np.float32)        # |e| ~ 2: never wins, never sets max|e|
+    ia, ib = 77, 5                                                    # b has the LOWER index: a tie-break cannot save a
+    E[ia], E[ib] = ea, eb
+    z = rs.standard_normal((N, D)).astype(np.float32)
+    hot = np.arange(0, N, 3)
+    z[hot] = z1 * np.float32(2.0) ** rs.randint(-3, 4, size=(hot.size, 1)).astype(np.float32)   # exact rescalings
+    # a wins exactly only at scale 1 (the score is not scale-invariant); keep the scale-1 rows as the probe
+    probe = hot[np.all(z[hot] == z1, axis=1)]
+    assert probe.size > 100
+    old = os.environ.get("VQB200_NO_FUSED")
+    os.environ["VQB200_NO_FUSED"] = "0" if fused else "1"
+    try:
+        assert bool(vq.ops.fused_supported(N, K, D, 0)) == fused
+        path, idx, _ = run_search(vq, z.reshape(N // 64, 64, D), E, K)
+    finally:
+        if old is None:
+            os.environ.pop("VQB200_NO_FUSED", None)
+        else:
+            os.environ["VQB200_NO_FUSED"] = old
+    assert path == 1
+    assert (idx[probe] == ia).all(), f"{(idx[probe] != ia).sum()} of {probe.size} adversarial rows lost the exact winner"
+    ref = O.nearest_code64(z, E)
+    mm, outside = O.near_tie_rows(z, E, idx, ref)
+    assert outside.size == 0

@@ -183,3 +183,23 @@ def test_torch_port_matches_golden(golden):
         assert np.array_equal(idx.numpy(), g["idx"].astype(np.int64).reshape(-1))
         assert sha(zq.numpy()) == str(g["sha_zq"])
         assert float(usage.sum()) == L * B * M
+
+
+def test_oracle_kmeans_recovers_planted_clusters():
+    """Known answer for the k-means restatement: well-separated planted clusters are recovered from perturbed
+    starts, the inertia never increases, an empty cluster keeps its centroid."""
+    rs = np.random.RandomState(11)
+    K, D, per = 12, 8, 50
+    centers = (rs.standard_normal((K, D)) * 10).astype(np.float32)
+    z = (np.repeat(centers, per, 0) + 0.05 * rs.standard_normal((K * per, D))).astype(np.float32)
+    init = centers + 0.5 * rs.standard_normal((K, D)).astype(np.float32)
+    E, idx, hist = O.kmeans_lloyd(z, init, 5)
+    assert np.array_equal(idx, np.repeat(np.arange(K), per))
+    np.testing.assert_allclose(E, z.reshape(K, per, D).mean(1), rtol=1e-5, atol=1e-5)
+    assert all(b <= a * (1 + 1e-12) for a, b in zip(hist, hist[1:]))
+    far = np.vstack([init, np.full((1, D), 1e3, np.float32)])            # a centroid nobody is assigned to
+    E2, _, _ = O.kmeans_lloyd(z, far, 3)
+    assert np.array_equal(E2[-1], far[-1])
+    lv = O.rvq_kmeans_lloyd(z, np.stack([init, 0.05 * rs.standard_normal((K, D)).astype(np.float32)]), 4)
+    assert lv.shape == (2, K, D)
+    np.testing.assert_allclose(lv[0], E, rtol=0, atol=0)
