@@ -30,9 +30,10 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 2
+#define VQB200_ABI_VERSION 3
 #define VQB200_MAX_LEVELS 32
-#define VQB200_LEVEL_META_FLOATS 4 /* per level: max|e|, non-finite flag, max|bf16(e)|, max|e - bf16(e)| */
+#define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
+                                      [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] reserved */
 
 enum {
   VQB200_OK = 0,
@@ -60,9 +61,11 @@ VQB200_API int vqb200_search_path(int64_t N, int K, int D, int mode);
  * recomputed by the reference on every forward, plus the operand conversion for the tensor path.
  *   E          [K_total, D] fp32 codebook (the module's `embedding` buffer, source of truth)
  *   K_per      codes per residual level (K_total % K_per == 0, at most VQB200_MAX_LEVELS levels)
- *   E_bf16     [K_total, D] bf16 (RN) copy
+ *   E_bf16     [2, K_total, D] 16-bit tensor-core operand copies: plane 0 = bf16 (RN), the operand of
+ *              bf16_input mode; plane 1 = fp16 (RN, subnormals flushed), the operand of fp32 mode -- three more
+ *              significand bits shrink the admission margin, and with it the exact re-rank, eightfold
  *   ee_half    [2, K_total]: plane 0 = |e|^2/2 of the fp32 rows, plane 1 = of the bf16-rounded rows
- *   level_meta [levels, 4] fp32, see VQB200_LEVEL_META_FLOATS
+ *   level_meta [levels, 8] fp32, see VQB200_LEVEL_META_FLOATS
  */
 VQB200_API int vqb200_codebook_prepare(const float* E, int K_total, int D, int K_per, uint16_t* E_bf16,
                             float* ee_half, float* level_meta, void* stream);
@@ -70,7 +73,9 @@ VQB200_API int vqb200_codebook_prepare(const float* E, int K_total, int D, int K
 /* Nearest-code search for ONE level: replaces the distance assembly + argmin
  * (models/vq_vae.py:183-188 and :238-245).  The N x K distance matrix is never written.
  *   z          [N, D] fp32 latents (or the RVQ residual)
- *   E, E_bf16, ee_half(plane 0), ee_half_bf16(plane 1), level_meta: this level's slices of the cache
+ *   E, ee_half(plane 0), ee_half_bf16(plane 1), level_meta: this level's slices of the cache
+ *   E_bf16     this level's slice of the operand plane OF THE MODE (plane 1 / fp16 for fp32 mode, plane 0 /
+ *              bf16 for bf16_input mode); same meaning in vqb200_quantize and vqb200_quantize_fused
  *   idx_out    [N] int64 = idx_offset + argmin_k |z - e_k|^2; first index on exact ties; a NaN
  *              distance counts as the minimum (torch.argmin semantics)
  */

@@ -15,8 +15,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvqb200.so")
 MODE_FP32_EXACT = 0
 MODE_BF16_INPUT = 1
 MAX_LEVELS = 32
-LEVEL_META_FLOATS = 4
-ABI_VERSION = 2
+LEVEL_META_FLOATS = 8
+ABI_VERSION = 3
 
 _p = C.c_void_p
 _i = C.c_int

@@ -1,6 +1,7 @@
 // Shared device helpers for libvqb200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -63,17 +64,40 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Internal launchers (defined in the .cu files, called from cabi.cu).
 namespace vqb {
 // measurement hook, see vqb200_timing_enable
-// Admission margin of one row in fp32 mode.  The tensor core scores s~ = z~.e~ - |e|^2/2 with z~ = bf16(z),
-// e~ = bf16(e); the exact score is s = z.e - |e|^2/2, and
+// Admission margin of one row in fp32 mode.  The tensor core scores s~ = z~.e~ - |e|^2/2 with z~ = f16(z),
+// e~ = f16(e) (round to nearest, subnormals flushed); the exact score is s = z.e - |e|^2/2, and
 //     s~ - s = (z~ - z).e~ + z.(e~ - e)   =>   |s~ - s| <= |z - z~| |e~| + |z| |e - e~|      (Cauchy-Schwarz)
 // with the ACTUAL rounding-error norms |z - z~| (this row, summed while converting) and max_k |e_k - e~_k|
-// (codebook cache, level_meta[3]) -- tighter than the worst case (2u + u^2)|z||e|, u = 2^-8, by about 2.5x and
-// rigorous all the same.  For the true arg max a and the approximate one b:  s~_a >= s~_b - (err_a + err_b), so
-// the margin is twice the bound, +4 % for the fp32 accumulation inside the tensor core (<= D 2^-23 |z||e|,
-// D <= 512) and an absolute term for the rounding of the fp32 bias.  ss = |z|^2, sse = |z - z~|^2.
-__device__ __forceinline__ float admission_margin_fp32(float ss, float sse, float emax, float emax_b, float rho_e) {
+// (codebook cache, level_meta[5]) -- tighter than the worst case (2u + u^2)|z||e|, u = 2^-11, by about 2.5x,
+// rigorous all the same, and valid whatever the conversion did (underflow, flushed subnormals: the error is
+// measured, not assumed; an overflow makes it infinite and sends the row to the exact kernel).  For the true
+// arg max a and the approximate one b:  s~_a >= s~_b - (err_a + err_b), so the margin is twice the bound, plus
+// the fp32 accumulation inside the tensor core (<= (D + 32) 2^-23 |z~||e~| per score, as in bf16_input mode)
+// and an absolute term for the rounding of the fp32 bias.  ss = |z|^2, sse = |z - z~|^2.
+__device__ __forceinline__ float admission_margin_fp32(float ss, float sse, float emax, float emax_lp, float rho_e,
+                                                       int D) {
   const float nz = sqrtf(ss) * 1.0001f, ne = sqrtf(sse) * 1.0001f;
-  return 2.08f * (ne * emax_b + nz * rho_e) + 1e-6f * emax * (emax + nz) + 1e-30f;
+  return 2.001f * (ne * emax_lp + nz * rho_e) + 2.f * static_cast<float>(D + 32) * 1.1920929e-7f * nz * emax_lp +
+         1e-6f * emax * (emax + nz) + 1e-30f;
+}
+
+// fp32 -> fp16 bits, round to nearest even, results below the normal range flushed to zero (the tensor core is
+// then never fed a subnormal; the flush is part of the measured conversion error)
+__device__ __forceinline__ uint16_t f16_bits_flush(float x) {
+  const uint16_t h = __half_as_ushort(__float2half_rn(x));
+  return (h & 0x7c00u) ? h : static_cast<uint16_t>(h & 0x8000u);
+}
+__device__ __forceinline__ float f16_bits_to_float(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+// two at a time: packed convert, then clear the halves whose exponent field is zero (subnormal or zero)
+__device__ __forceinline__ uint32_t f16x2_bits_flush(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  const uint32_t b = *reinterpret_cast<const uint32_t*>(&h);
+  const uint32_t e = b & 0x7c007c00u;
+  const uint32_t keep = ((e & 0x0000ffffu) ? 0x0000ffffu : 0x00008000u) | ((e & 0xffff0000u) ? 0xffff0000u : 0x80000000u);
+  return b & keep;
+}
+__device__ __forceinline__ float2 f16x2_bits_to_float2(uint32_t b) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&b));
 }
 
 void timing_mark_begin(cudaStream_t s);

@@ -13,7 +13,6 @@ constexpr int TC_KB = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int TC_STAGE_BYTES = TC_BN * TC_KB * 2;   // 16 KB
 constexpr int TC_SMEM_LIMIT = 232448;               // 227 KB
 constexpr uint32_t TC_SPIN_LIMIT = 1u << 22;
-constexpr uint32_t kMbarSuspendNs = 20000;          // suspend-time hint of mbar_wait_sleep
 
 // ------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -28,8 +27,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Spin on the phase (lowest wake-up latency): the tensor-bound search kernels, whose waits sit on the MMA
-// critical path (measured: the suspending form below costs the pair kernel 4 % at K=8192 D=256).
+// Poll the phase.  (A suspend-time hint on try_wait was measured: no effect on the fused small-D kernel whichever
+// warp roles used it, and 2-4 % slower on the tensor-bound pair kernel, so the plain form is used everywhere.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0, spins = 0;
   while (true) {
@@ -42,24 +41,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (done) break;
     if (++spins > TC_SPIN_LIMIT) __trap();   // a protocol bug must fault, never hang the GPU
-  }
-}
-// Same wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint
-// expires) instead of re-issuing the poll every ~30 cycles.  For kernels whose producer / MMA warps wait long and
-// share schedulers with latency-bound epilogue warps (the fused small-D kernel: polls were 20 % of its issued
-// instructions).
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(kMbarSuspendNs)
-        : "memory");
-    if (done) break;
-    if (++spins > TC_SPIN_LIMIT) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -97,6 +78,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t lo) {
 }
 // kind::f16, A = B = bf16, D = fp32, both K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((128u >> 4) << 24);
+// the same with A = B = fp16 (format field 0): the operands of fp32 mode
+constexpr uint32_t kIdescF16 = kIdesc & ~((1u << 7) | (1u << 10));
 
 #define TC_LD32(taddr, v)                                                                                          \
   asm volatile(                                                                                                    \
@@ -174,6 +157,7 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
 }
 // kind::f16, bf16 x bf16 -> fp32, K-major, M = 256 (two CTAs x 128 rows), N = 256
 constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+constexpr uint32_t kIdescPairF16 = kIdescPair & ~((1u << 7) | (1u << 10));
 
 // ------------------------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

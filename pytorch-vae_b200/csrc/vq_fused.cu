@@ -27,7 +27,7 @@ namespace vqb {
 // BM = 128: TWO CTAs per SM (half the shared memory, 256 TMEM columns and <= 128 registers each): the scan of
 // one CTA's tile overlaps the re-rank / output phase of the other's -- those phases are latency-bound (TMEM and
 // L2 round trips on dependent chains), so a second resident pipeline roughly doubles the SM's throughput.
-constexpr int fz_nconv(int) { return 2; }   // converter / output warps (12 warps = 3 per scheduler: 168 registers)
+constexpr int fz_nconv(int BM) { return BM == 256 ? 6 : 2; }   // converter / output warps (16 warps: 128 registers each)
 constexpr int fz_nepi(int BM) { return BM / 32; }
 constexpr int fz_threads(int BM) { return 64 + fz_nepi(BM) * 32 + fz_nconv(BM) * 32; }   // 448 / 256
 constexpr int FZ_PAIRS = 64;          // (row, code) pairs scored per warp pass
@@ -169,7 +169,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     // ============================== TMA producer ==============================
     uint32_t stage = 0, phase = 0, it = 0;
     auto load_z = [&](int item, uint32_t seq) {
-      mbar_wait_sleep(bar_zfempty, (seq & 1) ^ 1);
+      mbar_wait(bar_zfempty, (seq & 1) ^ 1);
       if (elect_one()) {
         mbar_expect_tx(bar_zffull, ZF_BYTES);
         for (int kb = 0; kb < KB32; ++kb)
@@ -183,7 +183,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       if (nxt < n_items) load_z(nxt, it + 1);       // the next tile's latents ride ahead of this tile's codebook blocks
       for (int t = 0; t < p.code_tiles; ++t) {
         for (int kb = 0; kb < KBLK; ++kb) {
-          mbar_wait_sleep(bar_empty + 8 * stage, phase ^ 1);
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (elect_one()) {
             mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
             tma_load_2d(e_smem + stage * TC_STAGE_BYTES, &tmap_e, bar_full + 8 * stage, kb * TC_KB, t * TC_BN);
@@ -199,13 +199,13 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     const uint32_t zb_lo = umma_desc_lo(zb_smem), e_lo = umma_desc_lo(e_smem);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t zb = 0;
-      mbar_wait_sleep(bar_zbfull, it & 1);
+      mbar_wait(bar_zbfull, it & 1);
       for (int t = 0; t < p.code_tiles; ++t, ++tg) {
         const uint32_t b = tg & 1;
-        mbar_wait_sleep(bar_tempty + 8 * b, (tg >> 1) & 1);       // drained AND pre-loaded with -|e|^2/2
+        mbar_wait(bar_tempty + 8 * b, (tg >> 1) & 1);       // drained AND pre-loaded with -|e|^2/2
         tc_fence_after();
         for (int kb = 0; kb < KBLK; ++kb) {
-          mbar_wait_sleep(bar_full + 8 * stage, phase);
+          mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t a0 = zb_lo + ((zb * ZB_BYTES + kb * (FZ_BM * 128)) >> 4);
@@ -215,7 +215,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
               const uint32_t d_tmem = tmem_base + b * (HALVES * TC_BN) + h * TC_BN;
 #pragma unroll
               for (int k = 0; k < TC_KB / 16; ++k)
-                tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), kIdesc, 1u);
+                tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), BF16 ? kIdesc : kIdescF16, 1u);
             }
             tc_commit(bar_empty + 8 * stage);
             if (kb == KBLK - 1) tc_commit(bar_tfull + 8 * b);
@@ -231,7 +231,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     // ============================== converters: fp32 tile -> bf16 operand tile + margins ==============================
     const int ct = (warp - 2 - FZ_NEPI) * 32 + lane;     // 0..63: rows ct, ct+64, ct+128, ct+192 of the tile
     const float emax = BF16 ? p.level_meta[2] : p.level_meta[0];
-    const float emax_b = p.level_meta[2], rho_e = p.level_meta[3];
+    const float emax_lp = p.level_meta[4], rho_e = p.level_meta[5];
     const bool code_bad = p.level_meta[1] != 0.f;
     const float coef = 2.f * static_cast<float>(D + 32) * 1.1920929e-7f;      // bf16 mode (see zprep_kernel)
     // Output phase of a finished tile (z_q, z_q_st, squared error), run by these warps one tile behind the
@@ -244,7 +244,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
                                   // epilogue its registers: 13-16 warps cap every thread at 128)
       constexpr int SL = D / (LPV * 4);
       const uint32_t rbuf = ito & 1;
-      mbar_wait_sleep(bar_resfull + 8 * rbuf, (ito >> 1) & 1);
+      mbar_wait(bar_resfull + 8 * rbuf, (ito >> 1) & 1);
       const uint32_t* rs = res_s + rbuf * FZ_BM;
       const int64_t row0 = static_cast<int64_t>(item_o) * FZ_BM;
       const int ogl = ct % LPV, ogr = ct / LPV;
@@ -297,8 +297,8 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     int item_prev = -1;
     for (int item = blockIdx.x; item < n_items; item_prev = item, item += gridDim.x, ++it) {
       const uint32_t zb = 0, mb = it & 1;
-      mbar_wait_sleep(bar_zffull, it & 1);
-      mbar_wait_sleep(bar_zbempty, (it & 1) ^ 1);             // the MMAs of the previous tile have retired
+      mbar_wait(bar_zffull, it & 1);
+      mbar_wait(bar_zbempty, (it & 1) ^ 1);             // the MMAs of the previous tile have retired
 #pragma unroll 1
       for (int rr = 0; rr < (FZ_BM + FZ_NCONV * 32 - 1) / (FZ_NCONV * 32); ++rr) {
         const int r = ct + rr * (FZ_NCONV * 32);
@@ -315,16 +315,23 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
             lo = *reinterpret_cast<const float4*>(src + ((static_cast<uint32_t>(j) ^ sw) << 4));
             hi = *reinterpret_cast<const float4*>(src + ((static_cast<uint32_t>(j + 1) ^ sw) << 4));
           }
-          const __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w),
-                               p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
           uint4 pk;
-          pk.x = *reinterpret_cast<const uint32_t*>(&p0); pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-          pk.z = *reinterpret_cast<const uint32_t*>(&p2); pk.w = *reinterpret_cast<const uint32_t*>(&p3);
+          float2 a, b2, c2, d2;                       // the stored operand values, back in fp32
+          if (BF16) {
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w),
+                                 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
+            pk.x = *reinterpret_cast<const uint32_t*>(&p0); pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+            pk.z = *reinterpret_cast<const uint32_t*>(&p2); pk.w = *reinterpret_cast<const uint32_t*>(&p3);
+            a = __bfloat1622float2(p0); b2 = __bfloat1622float2(p1); c2 = __bfloat1622float2(p2); d2 = __bfloat1622float2(p3);
+          } else {                                    // fp32 mode: fp16 operands, subnormal results flushed
+            pk.x = f16x2_bits_flush(lo.x, lo.y); pk.y = f16x2_bits_flush(lo.z, lo.w);
+            pk.z = f16x2_bits_flush(hi.x, hi.y); pk.w = f16x2_bits_flush(hi.z, hi.w);
+            a = f16x2_bits_to_float2(pk.x); b2 = f16x2_bits_to_float2(pk.y);
+            c2 = f16x2_bits_to_float2(pk.z); d2 = f16x2_bits_to_float2(pk.w);
+          }
           const int bslab = c / TC_KB, bj = (c % TC_KB) / 8;
           uint8_t* dst = gen + (zb_smem - base) + zb * ZB_BYTES + bslab * (FZ_BM * 128) + r * 128;
           *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(bj) ^ sw) << 4)) = pk;
-          const float2 a = __bfloat1622float2(p0), b2 = __bfloat1622float2(p1), c2 = __bfloat1622float2(p2),
-                       d2 = __bfloat1622float2(p3);
           if (BF16) {
             ss += a.x * a.x + a.y * a.y + b2.x * b2.x + b2.y * b2.y + c2.x * c2.x + c2.y * c2.y + d2.x * d2.x + d2.y * d2.y;
           } else {
@@ -334,7 +341,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
             sse += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3 + e4 * e4 + e5 * e5 + e6 * e6 + e7 * e7;
           }
         }
-        float m = BF16 ? coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f : admission_margin_fp32(ss, sse, emax, emax_b, rho_e);
+        float m = BF16 ? coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f : admission_margin_fp32(ss, sse, emax, emax_lp, rho_e, D);
         if (code_bad || !(ss < __int_as_float(0x7f800000)) || !(sse < __int_as_float(0x7f800000)))
           m = __int_as_float(0x7fc00000);   // NaN: exact path
         margin_s[mb * FZ_BM + r] = m;
@@ -406,7 +413,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       const int64_t row0w = static_cast<int64_t>(item) * FZ_BM + row_in_tile;
       const int64_t row = row0w + lane;
       const bool row_ok = row < p.n_rows;
-      mbar_wait_sleep(bar_zbfull, it & 1);                          // margins of this tile are in shared memory
+      mbar_wait(bar_zbfull, it & 1);                          // margins of this tile are in shared memory
       const float margin = row_ok ? margin_s[(it & 1) * FZ_BM + row_in_tile + lane] : __int_as_float(0x7fc00000);
       float best = kNegInf;
       float thr = margin == margin ? best : margin;
@@ -420,7 +427,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
         const int t_cur_ahead = t_ahead;
         t_ahead = la_next();
         bias_next = load_bias(t_ahead);
-        mbar_wait_sleep(bar_tfull + 8 * b, (tg >> 1) & 1);
+        mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem_base + tcol + b * (HALVES * TC_BN);
         // One 32-column chunk in registers at a time (measured: double-buffering the TMEM loads buys nothing
@@ -593,7 +600,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       }
       if (p.zq_out || p.zq_st_out || p.sqerr_sum) {              // publish the codes; the output warps take over
         const uint32_t rbuf = it & 1, use = it >> 1;
-        if (use >= 1) mbar_wait_sleep(bar_resempty + 8 * rbuf, (use - 1) & 1);
+        if (use >= 1) mbar_wait(bar_resempty + 8 * rbuf, (use - 1) & 1);
         res_s[rbuf * FZ_BM + row_in_tile + lane] = resolved ? my_idx : FZ_EMPTY;
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_resfull + 8 * rbuf);
@@ -779,7 +786,9 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
 
   CUtensorMap map_zf, map_e;
   if (!make_tensor_map_2d(&map_zf, z, N, D, BM, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4)) return VQB200_EDRIVER;
-  if (!make_tensor_map_2d(&map_e, E_bf16, K, D, TC_BN, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2)) return VQB200_EDRIVER;
+  if (!make_tensor_map_2d(&map_e, E_bf16, K, D, TC_BN,
+                          bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2))
+    return VQB200_EDRIVER;
 
   cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(int), s);
   if (e != cudaSuccess) return status_of(e);

@@ -32,8 +32,9 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
     if (lane == 0) ema_cs[row] = cs;
     denom = __fadd_rn(cs, eps);
   }
-  double acc = 0.0, accb = 0.0, accd = 0.0;
+  double acc = 0.0, accb = 0.0, accd = 0.0, acch = 0.0, accdh = 0.0;
   bool bad = false;
+  uint16_t* E_f16 = E_bf16 + static_cast<int64_t>(K_total) * D;        // operand plane 1
   for (int c = lane; c < D4; c += 32) {
     const int64_t o = static_cast<int64_t>(row) * D4 + c;
     float4 e;
@@ -73,11 +74,26 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
       const double d0 = e.x - f0, d1 = e.y - f1, d2 = e.z - f2, d3 = e.w - f3;
       accd += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
     }
+    {   // fp16 plane (the fp32-mode operand) and its norms
+      const uint16_t h0 = f16_bits_flush(e.x), h1 = f16_bits_flush(e.y), h2 = f16_bits_flush(e.z),
+                     h3 = f16_bits_flush(e.w);
+      uint2 ph;
+      ph.x = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
+      ph.y = static_cast<uint32_t>(h2) | (static_cast<uint32_t>(h3) << 16);
+      reinterpret_cast<uint2*>(E_f16)[o] = ph;
+      const double g0 = f16_bits_to_float(h0), g1 = f16_bits_to_float(h1), g2 = f16_bits_to_float(h2),
+                   g3 = f16_bits_to_float(h3);
+      acch += g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3;
+      const double d0 = e.x - g0, d1 = e.y - g1, d2 = e.z - g2, d3 = e.w - g3;
+      accdh += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
     bad |= !(isfinite(e.x) && isfinite(e.y) && isfinite(e.z) && isfinite(e.w));
   }
   acc = warp_sum(acc);
   accb = warp_sum(accb);
   accd = warp_sum(accd);
+  acch = warp_sum(acch);
+  accdh = warp_sum(accdh);
   bad = __any_sync(0xffffffffu, bad);
   if (lane == 0) {
     ee_half[row] = static_cast<float>(0.5 * acc);
@@ -89,6 +105,10 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
     if (n1 == n1 && n1 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 2), __float_as_int(n1));
     const float n3 = static_cast<float>(sqrt(accd)) * 1.0000002f;          // max_k |e_k - bf16(e_k)|
     if (n3 == n3 && n3 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 3), __float_as_int(n3));
+    // fp16 plane: an overflowed element makes these +inf, which the pre-pass turns into "exact path for every row"
+    const float n4 = static_cast<float>(sqrt(acch)) * 1.0000002f, n5 = static_cast<float>(sqrt(accdh)) * 1.0000002f;
+    if (n4 == n4) atomicMax(reinterpret_cast<int*>(meta + 4), __float_as_int(n4));
+    if (n5 == n5) atomicMax(reinterpret_cast<int*>(meta + 5), __float_as_int(n5));
     if (bad || !(acc == acc) || isinf(static_cast<float>(acc))) meta[1] = 1.0f;
   }
 }

@@ -31,7 +31,8 @@ constexpr int TC_CAND = 31;         // candidate records per (row, code split); 
 constexpr int TC_SLOTS = TC_CAND + 1;
 
 // ------------------------------------------------------------------------------------ z pre-pass
-// z fp32 -> bf16 (RN) plus the per-row admission margin.  One warp per row.
+// z fp32 -> 16-bit tensor-core operand (fp16 in fp32 mode, bf16 in bf16_input mode; RN) plus the per-row
+// admission margin.  One warp per row.
 __global__ void __launch_bounds__(256)
 zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const float* __restrict__ level_meta,
              __nv_bfloat16* __restrict__ zb, float* __restrict__ margin) {
@@ -41,7 +42,7 @@ zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const floa
   const int D4 = D >> 2;
   const bool bfm = mode == VQB200_MODE_BF16_INPUT;
   const float emax = bfm ? level_meta[2] : level_meta[0];
-  const float emax_b = level_meta[2], rho_e = level_meta[3];
+  const float emax_lp = level_meta[4], rho_e = level_meta[5];
   const bool code_bad = level_meta[1] != 0.f;
   // fp32 mode: admission_margin_fp32 (common.cuh)
   // bf16 mode: inputs are exact, only accumulation order differs: 2 (D + 32) 2^-23
@@ -50,14 +51,24 @@ zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const floa
     float ss = 0.f, sse = 0.f;
     for (int c = lane; c < D4; c += 32) {
       const float4 v = ld_stream(reinterpret_cast<const float4*>(z) + row * D4 + c);
-      const __nv_bfloat16 b0 = __float2bfloat16_rn(v.x), b1 = __float2bfloat16_rn(v.y),
-                          b2 = __float2bfloat16_rn(v.z), b3 = __float2bfloat16_rn(v.w);
+      uint16_t b0, b1, b2, b3;
+      float f0, f1, f2, f3;
+      if (bfm) {
+        b0 = __bfloat16_as_ushort(__float2bfloat16_rn(v.x)); b1 = __bfloat16_as_ushort(__float2bfloat16_rn(v.y));
+        b2 = __bfloat16_as_ushort(__float2bfloat16_rn(v.z)); b3 = __bfloat16_as_ushort(__float2bfloat16_rn(v.w));
+        f0 = __uint_as_float(static_cast<uint32_t>(b0) << 16); f1 = __uint_as_float(static_cast<uint32_t>(b1) << 16);
+        f2 = __uint_as_float(static_cast<uint32_t>(b2) << 16); f3 = __uint_as_float(static_cast<uint32_t>(b3) << 16);
+      } else {
+        const uint32_t q0 = f16x2_bits_flush(v.x, v.y), q1 = f16x2_bits_flush(v.z, v.w);
+        b0 = static_cast<uint16_t>(q0); b1 = static_cast<uint16_t>(q0 >> 16);
+        b2 = static_cast<uint16_t>(q1); b3 = static_cast<uint16_t>(q1 >> 16);
+        const float2 g0 = f16x2_bits_to_float2(q0), g1 = f16x2_bits_to_float2(q1);
+        f0 = g0.x; f1 = g0.y; f2 = g1.x; f3 = g1.y;
+      }
       uint2 pk;
-      pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(b0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
-      pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(b2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b3)) << 16);
+      pk.x = static_cast<uint32_t>(b0) | (static_cast<uint32_t>(b1) << 16);
+      pk.y = static_cast<uint32_t>(b2) | (static_cast<uint32_t>(b3) << 16);
       reinterpret_cast<uint2*>(zb)[row * D4 + c] = pk;
-      const float f0 = __bfloat162float(b0), f1 = __bfloat162float(b1), f2 = __bfloat162float(b2),
-                  f3 = __bfloat162float(b3);
       if (bfm) {
         ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
       } else {
@@ -69,7 +80,7 @@ zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const floa
     ss = warp_sum(ss);
     sse = warp_sum(sse);
     if (lane == 0) {
-      float m = bfm ? coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f : admission_margin_fp32(ss, sse, emax, emax_b, rho_e);
+      float m = bfm ? coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f : admission_margin_fp32(ss, sse, emax, emax_lp, rho_e, D);
       if (code_bad || !(ss < __int_as_float(0x7f800000)) || !(sse < __int_as_float(0x7f800000)))
         m = __int_as_float(0x7fc00000);   // NaN: exact path
       margin[row] = m;
@@ -84,6 +95,7 @@ struct TcParams {
   int row_tiles, ksplit, tiles_per_split, code_tiles;
   int stages;
   int zbufs;             // 1 or 2 z-tile buffers (2 when shared memory allows: next item's rows prefetch)
+  uint32_t idesc;        // UMMA instruction descriptor: bf16 or fp16 operands (by mode), this kernel's M x N
   const float* ee_half;  // [K] (plane chosen by mode)
   const float* margin;   // [n_rows]
   uint2* cand;           // [n_rows][ksplit][TC_SLOTS] records {code group << 8 | admit mask, group max}
@@ -230,7 +242,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
               const uint32_t d_tmem = tmem_base + b * (NHALF * TC_BN) + h * TC_BN;
 #pragma unroll
               for (int k = 0; k < TC_KB / 16; ++k)
-                tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), kIdesc, 1u);
+                tc_mma_bf16(d_tmem, umma_desc(a0 + h * ((128 * 128) >> 4) + k * 2), umma_desc(b0 + k * 2), p.idesc, 1u);
             }
             tc_commit(bar_empty + 8 * stage);          // frees the smem stage when these MMAs retire
             if (kb == KBLK - 1) tc_commit(bar_tfull + 8 * b);   // accumulator tile complete
@@ -475,7 +487,7 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_const
               const uint32_t d_tmem = tmem_base + b * P2_BN;
 #pragma unroll
               for (int k = 0; k < TC_KB / 16; ++k)
-                tc_mma_bf16_pair(d_tmem, umma_desc(a0 + k * 2), umma_desc(b0 + k * 2), kIdescPair, 1u);
+                tc_mma_bf16_pair(d_tmem, umma_desc(a0 + k * 2), umma_desc(b0 + k * 2), p.idesc, 1u);
               tc_commit_pair(bar_empty + 8 * stage);
               if (kb == KBLK - 1) tc_commit_pair(bar_tfull + 8 * b);
             }
@@ -747,8 +759,9 @@ __global__ void fb_unpack_kernel(const int* __restrict__ fb_rows, const uint64_t
 }
 
 // ------------------------------------------------------------------------------------ host side
-static bool make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int box_rows) {
-  return make_tensor_map_2d(m, base, rows, D, box_rows, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+static bool make_map(CUtensorMap* m, const void* base, int64_t rows, int D, int box_rows, bool f16) {
+  return make_tensor_map_2d(m, base, rows, D, box_rows,
+                            f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
 }
 
 struct TcPlan {
@@ -921,7 +934,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   sets[1] = n_chunks > 1 ? carve(static_cast<uint8_t*>(workspace) + set_bytes, cap, D, pl.BM) : sets[0];
 
   CUtensorMap map_e;
-  if (!make_map(&map_e, E_bf16, K, D, TC_BN)) return VQB200_EDRIVER;
+  if (!make_map(&map_e, E_bf16, K, D, TC_BN, !bf)) return VQB200_EDRIVER;
   const int code_tiles = (K + TC_BN - 1) / TC_BN;
 
   // CTA-pair kernel (cta_group::2): large row counts only (no code splits), z tile of 128 rows must fit
@@ -986,7 +999,8 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     const bool pair_now = use2 && rows >= static_cast<int64_t>(kNumSMs / 2) * 2 * P2_ROWS;
     int nsub;
     if (pair_now) {
-      if (!make_map(&map_z, w.zb, rows, D, P2_ROWS)) return VQB200_EDRIVER;
+      if (!make_map(&map_z, w.zb, rows, D, P2_ROWS, !bf)) return VQB200_EDRIVER;
+      p.idesc = bf ? kIdescPair : kIdescPairF16;
       p.row_tiles = static_cast<int>((rows + 2 * P2_ROWS - 1) / (2 * P2_ROWS));
       p.ksplit = 1; p.tiles_per_split = (K + P2_BN - 1) / P2_BN;
       p.code_tiles = (K + P2_BN - 1) / P2_BN;
@@ -999,7 +1013,8 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
       else search_tc2_kernel<168><<<2 * pairs, 64 + P2_NEPI * 32, smem2, s_tc>>>(map_z, map_e, p);
       timing_mark_end(s_tc);
     } else {
-    if (!make_map(&map_z, w.zb, rows, D, pl.BM)) return VQB200_EDRIVER;
+    if (!make_map(&map_z, w.zb, rows, D, pl.BM, !bf)) return VQB200_EDRIVER;
+    p.idesc = bf ? kIdesc : kIdescF16;
     p.row_tiles = static_cast<int>((rows + pl.BM - 1) / pl.BM);
     p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, pl.ksplit_max, &p.tiles_per_split);
     p.code_tiles = code_tiles;

@@ -43,10 +43,16 @@ class CodebookCache:
     def __init__(self, K_total: int, D: int, K_per: int, device):
         self.K_total, self.D, self.K_per = K_total, D, K_per
         self.levels = K_total // K_per
-        self.E_bf16 = torch.empty(K_total, D, dtype=torch.bfloat16, device=device)
+        # 16-bit operand planes: [0] bf16 (bf16_input mode), [1] fp16 bit patterns (fp32 mode)
+        self.E_bf16 = torch.empty(2, K_total, D, dtype=torch.bfloat16, device=device)
         self.ee_half = torch.empty(2, K_total, dtype=torch.float32, device=device)
         self.level_meta = torch.empty(self.levels, _cabi.LEVEL_META_FLOATS, dtype=torch.float32, device=device)
         self.key = None
+
+    def operand_ptr(self, mode: int, first_code: int) -> int:
+        """Device pointer of the tensor-core operand copy for ``mode`` starting at code ``first_code``."""
+        plane = 0 if mode == _cabi.MODE_BF16_INPUT else 1
+        return self.E_bf16.data_ptr() + (plane * self.K_total + first_code) * self.D * 2
 
     def prepare(self, E: torch.Tensor):
         _need_cuda(E)
@@ -70,7 +76,7 @@ def search(z: torch.Tensor, E: torch.Tensor, cache: CodebookCache, level: int, m
     ws_bytes = lib.vqb200_search_workspace_bytes(N, K, D, mode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
     esz = E.element_size()
-    check(lib.vqb200_search(ptr(z), N, D, E.data_ptr() + s * D * esz, cache.E_bf16.data_ptr() + s * D * 2,
+    check(lib.vqb200_search(ptr(z), N, D, E.data_ptr() + s * D * esz, cache.operand_ptr(mode, s),
                             cache.ee_half.data_ptr() + s * 4, cache.ee_half.data_ptr() + (cache.K_total + s) * 4,
                             cache.level_meta.data_ptr() + level * _cabi.LEVEL_META_FLOATS * 4, K, mode,
                             idx_offset, ptr(idx_out), ptr(ws), ws_bytes, stream_ptr()), "vqb200_search")
@@ -94,7 +100,7 @@ def quantize_fused(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st
     K = cache.K_per
     ws_bytes = lib.vqb200_quantize_fused_workspace_bytes(N, K, D, mode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-    check(lib.vqb200_quantize_fused(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), cache.ee_half.data_ptr(),
+    check(lib.vqb200_quantize_fused(ptr(z), N, D, ptr(E), cache.operand_ptr(mode, 0), cache.ee_half.data_ptr(),
                                     cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, mode, 0,
                                     ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist),
                                     ptr(row_mask), ptr(ws), ws_bytes, stream_ptr()), "vqb200_quantize_fused")
@@ -113,7 +119,7 @@ def quantize(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st_out=N
     K = cache.K_per
     ws_bytes = lib.vqb200_search_workspace_bytes(N, K, D, mode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-    check(lib.vqb200_quantize(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), cache.ee_half.data_ptr(),
+    check(lib.vqb200_quantize(ptr(z), N, D, ptr(E), cache.operand_ptr(mode, 0), cache.ee_half.data_ptr(),
                               cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, mode, 0,
                               ptr(idx_out), ptr(E), E.shape[0], ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist),
                               ptr(row_mask), ptr(ws), ws_bytes, stream_ptr()), "vqb200_quantize")

@@ -201,3 +201,36 @@ def test_margin_holds_when_rounding_errors_align(vq, fused):
     ref = O.nearest_code64(z, E)
     mm, outside = O.near_tie_rows(z, E, idx, ref)
     assert outside.size == 0
+
+
+@pytest.mark.parametrize("D,K", [(64, 256), (128, 384)])
+@pytest.mark.parametrize("case", ["huge_rows", "tiny_rows", "huge_codes", "tiny_codes", "mixed_scales"])
+def test_fp16_operand_range_is_safe(vq, D, K, case):
+    """fp32 mode feeds the tensor core fp16 copies.  Values outside fp16's range must cost speed, never
+    correctness: an overflow makes the measured conversion error infinite (exact path for the row / the level),
+    an underflow is measured like any other rounding error.  Indices must equal the fp64 arbiter's."""
+    N = 8192
+    E, z = large_case_inputs(700 + D, K, D, 1, N // 64, 64)
+    z = z.reshape(N, D).copy()
+    if case == "huge_rows":
+        z[::5] *= np.float32(3e5)                       # > 65504 per element: fp16 overflow on those rows
+        z[1::5] *= np.float32(2.0 ** 14)
+    elif case == "tiny_rows":
+        z[::3] *= np.float32(1e-7)                      # every element flushes to zero
+        z[1::3] *= np.float32(2.0 ** -12)               # partly subnormal in fp16
+    elif case == "huge_codes":
+        E = (E * np.float32(1e6)).astype(np.float32)    # the whole level overflows fp16
+        z = (z * np.float32(1e6)).astype(np.float32)
+    elif case == "tiny_codes":
+        E = (E * np.float32(1e-6)).astype(np.float32)
+        z = (z * np.float32(1e-6)).astype(np.float32)
+    else:
+        E[::7] *= np.float32(1e-4)
+        E[3::11] *= np.float32(50.0)
+        z[::2] *= np.float32(30.0)
+    path, idx, _ = run_search(vq, z.reshape(N // 64, 64, D), E, K)
+    assert path == 1
+    ref = O.nearest_code64(z, E)
+    mm, outside = O.near_tie_rows(z, E, idx, ref)
+    assert outside.size == 0, f"{case}: {outside.size} rows differ from the fp64 arbiter outside near-ties"
+    assert mm.size <= 8
