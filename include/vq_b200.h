@@ -30,7 +30,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 3
+#define VQB200_ABI_VERSION 4
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] reserved */
@@ -161,6 +161,13 @@ VQB200_API int vqb200_ema_finalize(const float* seg_sum, const float* seg_cnt, f
  * keeps its centroid; the derived cache is refreshed in the same pass.  seg_* come from vqb200_scatter_add. */
 VQB200_API int vqb200_kmeans_finalize(const float* seg_sum, const float* seg_cnt, int K_total, int D, int K_per,
                            float* E, uint16_t* E_bf16, float* ee_half, float* level_meta, void* stream);
+
+/* Soft assignment of the soft-VQ training path (models/vq_vae.py:838-843, single-level codebooks):
+ *   z_soft[n] = sum_k softmax_k(-|z_n - e_k|^2 / max(1e-8, tau)) e_k
+ * in one pass with an online softmax; neither the [N, K, D] differences nor the [N, K] logits are stored.
+ * The result is detached in the reference (:852), so there is no backward.  D <= 512. */
+VQB200_API int vqb200_soft_assign(const float* z, int64_t N, int D, const float* E, int K, float tau,
+                       float* z_soft_out, void* stream);
 
 /* Backward of the two differentiable outputs (straight-through + commitment):
  *   grad_z = grad_st + (*grad_commit) * scale * (z - zq),  scale = 2 / (N D)

@@ -261,6 +261,15 @@ int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok,
                                   static_cast<cudaStream_t>(stream));
 }
 
+int vqb200_soft_assign(const float* z, int64_t N, int D, const float* E, int K, float tau, float* z_soft_out,
+                       void* stream) {
+  VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && E && z_soft_out), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(z_soft_out), VQB200_EALIGN);
+  return launch_soft_assign(z, N, D, E, K, tau, z_soft_out, static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_search_packed(const float* z, int64_t N, int D, const float* E, const float* ee_half, int K,
                          int64_t idx_offset, uint64_t* packed_out, void* stream) {
   VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);

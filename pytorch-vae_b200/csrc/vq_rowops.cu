@@ -500,4 +500,97 @@ int launch_minloc_unpack(const uint64_t* p, int64_t N, int64_t* out, cudaStream_
   return status_of(cudaGetLastError());
 }
 
+// --------------------------------------------------------------------------------------------
+// soft assignment (models/vq_vae.py:838-843): z_soft = softmax_k(-|z - e_k|^2 / tau) @ E, one pass, online
+// softmax -- the reference materialises the [N, K, D] difference tensor, the [N, K] logits and a GEMM.
+// One warp per row; the row and its accumulator live in registers (float4 slices, lane-strided); codes are
+// visited four at a time so that the four warp reductions overlap.  SIMT fp32: this is a training-time,
+// single-level, small-N path (N = batch x tokens), not GEMM-sized work.
+// --------------------------------------------------------------------------------------------
+constexpr int SOFT_SLICES = 4;   // float4 slices per lane: D <= 512
+
+__global__ void __launch_bounds__(256)
+soft_assign_kernel(const float4* __restrict__ z, const float4* __restrict__ E, int64_t N, int K, int D4,
+                   float inv_tau, float4* __restrict__ z_soft) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const float kNegInf = __int_as_float(0xff800000);
+  for (int64_t row = warp0; row < N; row += nwarps) {
+    float4 zr[SOFT_SLICES], acc[SOFT_SLICES];
+#pragma unroll
+    for (int j = 0; j < SOFT_SLICES; ++j) {
+      const int c = lane + 32 * j;
+      zr[j] = c < D4 ? z[row * D4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float m = kNegInf, ssum = 0.f;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      float4 ev[4][SOFT_SLICES];
+      float part[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        part[u] = 0.f;
+        const bool live = k0 + u < K;
+#pragma unroll
+        for (int j = 0; j < SOFT_SLICES; ++j) {
+          const int c = lane + 32 * j;
+          ev[u][j] = (live && c < D4) ? __ldg(E + static_cast<int64_t>(k0 + u) * D4 + c) : zr[j];   // zr: difference 0
+          const float dx = zr[j].x - ev[u][j].x, dy = zr[j].y - ev[u][j].y, dz = zr[j].z - ev[u][j].z,
+                      dw = zr[j].w - ev[u][j].w;
+          part[u] += dx * dx + dy * dy + dz * dz + dw * dw;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+      }
+      float lg[4], mx = m;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        lg[u] = (k0 + u < K) ? -part[u] * inv_tau : kNegInf;
+        mx = fmaxf(mx, lg[u]);
+      }
+      if (mx == kNegInf) continue;                        // only NaN-free -inf rows get here: nothing to add yet
+      const float rescale = __expf(m - mx);                // m = -inf on the first group: exp(-inf) = 0
+      ssum *= rescale;
+      float w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { w[u] = expf(lg[u] - mx); ssum += w[u]; }
+#pragma unroll
+      for (int j = 0; j < SOFT_SLICES; ++j) {
+        float4 a = acc[j];
+        a.x *= rescale; a.y *= rescale; a.z *= rescale; a.w *= rescale;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a.x = fmaf(w[u], ev[u][j].x, a.x); a.y = fmaf(w[u], ev[u][j].y, a.y);
+          a.z = fmaf(w[u], ev[u][j].z, a.z); a.w = fmaf(w[u], ev[u][j].w, a.w);
+        }
+        acc[j] = a;
+      }
+      m = mx;
+    }
+    const float inv = 1.f / ssum;
+#pragma unroll
+    for (int j = 0; j < SOFT_SLICES; ++j) {
+      const int c = lane + 32 * j;
+      if (c < D4) z_soft[row * D4 + c] = make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
+    }
+  }
+}
+
+int launch_soft_assign(const float* z, int64_t N, int D, const float* E, int K, float tau, float* z_soft,
+                       cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  if (D > 128 * SOFT_SLICES) return VQB200_ESHAPE;
+  const float t = tau > 1e-8f ? tau : 1e-8f;             // max(1e-8, tau), models/vq_vae.py:840
+  int64_t blocks = (N + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  soft_assign_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(reinterpret_cast<const float4*>(z),
+                                                                  reinterpret_cast<const float4*>(E), N, K, D >> 2,
+                                                                  1.0f / t, reinterpret_cast<float4*>(z_soft));
+  return status_of(cudaGetLastError());
+}
+
 }  // namespace vqb

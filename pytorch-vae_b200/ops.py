@@ -179,6 +179,20 @@ def kmeans_finalize(seg_sum, seg_cnt, E, cache: CodebookCache):
     _count(1)
 
 
+def soft_assign(z, E, tau: float, out=None):
+    """z_soft = softmax(-|z - e|^2 / tau) @ E (models/vq_vae.py:838-843), online softmax, nothing materialised."""
+    _need_cuda(z, E)
+    _f32c(z, "z")
+    _f32c(E, "embedding")
+    N, D = z.shape
+    if out is None:
+        out = torch.empty_like(z)
+    check(lib.vqb200_soft_assign(ptr(z), N, D, ptr(E), E.shape[0], float(tau), ptr(out), stream_ptr()),
+          "vqb200_soft_assign")
+    _count(1)
+    return out
+
+
 def commit_backward(grad_st, grad_commit, z, zq, scale, out):
     check(lib.vqb200_commit_backward(ptr(grad_st), ptr(grad_commit), ptr(z), ptr(zq), z.numel(), float(scale),
                                      ptr(out), stream_ptr()), "vqb200_commit_backward")

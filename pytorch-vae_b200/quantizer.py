@@ -235,6 +235,35 @@ class VectorQuantizerEMA(nn.Module):
         self._last_pair = (z_q, z_e)
         return z_q_st, z_q, indices, stats
 
+    @torch.no_grad()
+    def soft_forward(self, z_e: Tensor, tau: float, do_ema_update: bool = True):
+        """The quantizer's share of the soft-VQ training branch (models/vq_vae.py:828-861, single level):
+        ``z_soft = softmax(-|z - e|^2 / tau) @ E`` (one online-softmax kernel), the hard assignment and
+        ``z_q_hard``, the EMA update from the hard assignment, and ``[perplexity, dead_ratio]`` of this batch.
+        Everything is detached in the reference, so nothing here is differentiable; the epoch accumulators are
+        left alone, as the reference's soft branch never calls ``forward``.  Returns
+        ``(z_soft, z_q_hard, indices [B, M], stats)``; z_soft / z_q_hard use the codebook BEFORE the update."""
+        if self.num_quantizers != 1:
+            raise RuntimeError("soft VQ is defined for single-level codebooks (models/vq_vae.py:828)")
+        B, M, D = z_e.shape
+        if not z_e.is_cuda or z_e.dtype != torch.float32 or D != self.D:
+            raise RuntimeError("soft_forward needs float32 CUDA latents [B, M, D] matching the codebook")
+        dev = z_e.device
+        flat = z_e.detach().reshape(-1, D).contiguous()
+        N = flat.shape[0]
+        z_soft = ops.soft_assign(flat, self.embedding, tau)
+        scratch = torch.zeros(2 + self.K, dtype=torch.int32, device=dev)
+        sqerr, hist = scratch[:2].view(torch.float64), scratch[2:]
+        z_q = torch.empty(N, D, dtype=torch.float32, device=dev)
+        idx = torch.empty(N, dtype=torch.int64, device=dev)
+        do_ema = bool(self.training and do_ema_update and N > 0)
+        if N > 0:
+            self._quantize_rows(flat, [idx], z_q, None, sqerr, hist, None, do_ema, do_ema)
+        stats3 = torch.empty(3, dtype=torch.float32, device=dev)
+        spare = torch.zeros(self.K + 1, dtype=torch.float32, device=dev)      # stand-ins for the epoch accumulators
+        ops.stats_finalize(hist, float(N), sqerr, 1.0 / max(N * D, 1), spare[: self.K], spare[self.K:], stats3)
+        return z_soft.view(B, M, D), z_q.view(B, M, D), idx.view(B, M), stats3[:2]
+
     def commitment_loss(self, z_q: Tensor, z_e: Tensor) -> Tensor:
         """``F.mse_loss(z_q.detach(), z_e)`` (models/vq_vae.py:1293).  When called with the pair the
         last forward produced, returns the value the gather pass already accumulated (its backward is

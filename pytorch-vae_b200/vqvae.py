@@ -68,14 +68,18 @@ class VQVAE(nn.Module):
                  label_smoothing: float = 0.0, ss_tv_lambda: float = 0.0, usage_entropy_lambda: float = 0.0,
                  xyz_align_alpha: float = 0.7, codebook_init_path: Optional[str] = None,
                  ema_decay_start: float = 0.98, ema_decay_end: float = 0.98, ema_decay_warm_steps: int = 0,
-                 soft_vq_use: bool = False, latent_tokens: int = 32, tokenizer_heads: int = 8,
+                 soft_vq_use: bool = False, soft_vq_tau_start: float = 2.0, soft_vq_tau_end: float = 0.5,
+                 soft_vq_tau_warm_steps: int = 0, soft_vq_alpha_warm_steps: int = 0,
+                 latent_tokens: int = 32, tokenizer_heads: int = 8,
                  tokenizer_layers: int = 2, tokenizer_dropout: float = 0.1, latent_sigmoid: bool = False,
                  latent_sigmoid_ae_only: bool = True, reinit_dead_codes: bool = True, reinit_prob: float = 1.0,
                  dead_usage_threshold: int = 0, ema_update_freeze_steps: int = 0, print_init: bool = True,
                  search_mode: str = "fp32", **kwargs):
         super().__init__()
-        if soft_vq_use:
-            raise NotImplementedError("soft-VQ is a 'next' row (SURVEY.md section 8f); both reference configs disable it")
+        self.soft_vq_use = bool(soft_vq_use)                # models/vq_vae.py:436-440
+        self.soft_vq_tau_start, self.soft_vq_tau_end = float(soft_vq_tau_start), float(soft_vq_tau_end)
+        self.soft_vq_tau_warm_steps = int(soft_vq_tau_warm_steps)
+        self.soft_vq_alpha_warm_steps = int(soft_vq_alpha_warm_steps)
         self.input_dim, self.hidden_dim = int(input_dim), int(hidden_dim)
         self.code_dim, self.max_seq_len = int(code_dim), int(max_seq_len)
         self.use_vq = bool(use_vq)
@@ -238,6 +242,19 @@ class VQVAE(nn.Module):
             z_dec, z_q_raw = z_e, z_e
             indices = torch.zeros(z_e.size(0), z_e.size(1), dtype=torch.long, device=z_e.device)
             ppl = dead = torch.tensor(0.0, device=x.device)
+        elif self.soft_vq_use and self.training and not self.residual_vq:
+            # soft VQ, single-level only (models/vq_vae.py:828-861): decode a blend of the softmax-weighted code
+            # mixture and the hard code; the EMA update and the statistics use the hard assignment
+            do_ema = self.training_steps >= self.ema_update_freeze_steps
+            w = self.soft_vq_tau_warm_steps                                   # _interp_linear(:621-625)
+            t = 1.0 if w <= 0 else min(1.0, max(0.0, self.training_steps) / float(w))
+            tau = self.soft_vq_tau_end if w <= 0 else (1.0 - t) * self.soft_vq_tau_start + t * self.soft_vq_tau_end
+            aw = self.soft_vq_alpha_warm_steps                                # _linear_schedule(:615-619)
+            alpha = 1.0 if aw <= 0 else min(1.0, float(self.training_steps) / float(aw))
+            z_soft, z_q_raw, indices, stats = self.quantizer.soft_forward(z_e, tau, do_ema_update=do_ema)
+            z_mix = (1 - alpha) * z_soft + alpha * z_q_raw
+            z_dec = z_e + (z_mix - z_e).detach()
+            ppl, dead = stats[0], stats[1]
         else:
             do_ema = self.training and self.training_steps >= self.ema_update_freeze_steps
             z_dec, z_q_raw, indices, stats = self.quantizer(z_e, do_ema_update=do_ema, allow_reinit=do_ema, mask=None)

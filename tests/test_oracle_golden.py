@@ -203,3 +203,16 @@ def test_oracle_kmeans_recovers_planted_clusters():
     lv = O.rvq_kmeans_lloyd(z, np.stack([init, 0.05 * rs.standard_normal((K, D)).astype(np.float32)]), 4)
     assert lv.shape == (2, K, D)
     np.testing.assert_allclose(lv[0], E, rtol=0, atol=0)
+
+
+def test_oracle_soft_vq_matches_live_reference():
+    """tests/golden/soft_golden.npz holds what the reference's own VQVAE.forward did on its soft-VQ branch
+    (make_golden_soft.py): the numpy restatement reproduces the decoder input, the hard codes and indices."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "soft_golden.npz"))
+    for s in range(int(g["n_steps"])):
+        out, hard, idx = O.soft_vq_decode_input(g[f"step{s}/z_e"], g[f"step{s}/E_before"], float(g[f"step{s}/tau"]),
+                                                float(g[f"step{s}/alpha"]))
+        assert np.array_equal(idx, g[f"step{s}/idx"])
+        assert np.array_equal(hard, g[f"step{s}/zq_hard"])
+        np.testing.assert_allclose(out, g[f"step{s}/z_dec"], rtol=1e-5, atol=1e-6)
