@@ -206,8 +206,11 @@ def run_b200(args, w):
     beta_t = torch.full((), q.beta, device=dev)
 
     graphed = vq.GraphedForward(q, z) if args.graph and not train else None
+    graphed_train = vq.GraphedTrainStep(q, z) if args.graph and train else None
 
     def train_step(zd):
+        if graphed_train is not None:                    # forward + EMA + backward replayed as ONE CUDA graph
+            return graphed_train(zd, g_st, q.beta)
         ze = zd.detach().requires_grad_(True)
         st, zq, idx, stats = q(ze, do_ema_update=True)
         torch.autograd.backward([st, q.last_commit], [g_st, beta_t])    # d(recon)/d z_q_st + beta * commit (:1292-1294)
@@ -297,9 +300,11 @@ def run_b200(args, w):
     lib.vqb200_timing_enable(1)
     for _ in range(max(3, min(args.steps, 10))):
         if train:
+            gt, graphed_train = graphed_train, None              # eager even under --graph: the hooks live in the library calls
             train_step(z)
+            graphed_train = gt
         else:
-            with torch.no_grad():                                # eager even under --graph: the hooks live in the library calls
+            with torch.no_grad():
                 q(z, do_ema_update=False)
     torch.cuda.synchronize()
     lib.vqb200_timing_enable(0)

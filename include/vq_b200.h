@@ -33,7 +33,7 @@ extern "C" {
 #define VQB200_ABI_VERSION 4
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
-                                      [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] reserved */
+                                      [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
 
 enum {
   VQB200_OK = 0,

@@ -7,8 +7,8 @@ there is no fallback implementation.
 from . import _cabi, ops  # noqa: F401  (loads the shared library; ImportError if absent)
 from .quantizer import VectorQuantizer, VectorQuantizerEMA  # noqa: F401
 from .integration import install, uninstall  # noqa: F401
-from .graphs import GraphedForward  # noqa: F401
+from .graphs import GraphedForward, GraphedTrainStep  # noqa: F401
 from .kmeans import kmeans_fit, rvq_kmeans_fit  # noqa: F401
 
-__all__ = ["VectorQuantizerEMA", "VectorQuantizer", "GraphedForward", "kmeans_fit", "rvq_kmeans_fit", "install",
+__all__ = ["VectorQuantizerEMA", "VectorQuantizer", "GraphedForward", "GraphedTrainStep", "kmeans_fit", "rvq_kmeans_fit", "install",
            "uninstall", "ops"]

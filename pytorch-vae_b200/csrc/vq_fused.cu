@@ -416,7 +416,7 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
       mbar_wait(bar_zbfull, it & 1);                          // margins of this tile are in shared memory
       const float margin = row_ok ? margin_s[(it & 1) * FZ_BM + row_in_tile + lane] : __int_as_float(0x7fc00000);
       float best = kNegInf;
-      float thr = margin == margin ? best : margin;
+      float thr = margin == margin ? -3.0e38f : margin;   // lowest finite value: -inf chunks are never admitted
       int rcnt = 0;
       float lost = kNegInf;
       float age[FZ_RING] = {kNegInf, kNegInf, kNegInf, kNegInf};

@@ -20,8 +20,8 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
                         float* __restrict__ level_meta) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= K_total) return;
   const int D4 = D >> 2;
+  if (row < K_total) {
   constexpr bool EMA = MODE == 1;
   float denom = 1.f;
   if (MODE == 2) denom = seg_cnt[row];
@@ -109,7 +109,33 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
     const float n4 = static_cast<float>(sqrt(acch)) * 1.0000002f, n5 = static_cast<float>(sqrt(accdh)) * 1.0000002f;
     if (n4 == n4) atomicMax(reinterpret_cast<int*>(meta + 4), __float_as_int(n4));
     if (n5 == n5) atomicMax(reinterpret_cast<int*>(meta + 5), __float_as_int(n5));
+    // an all-zero row (a dead code after an EMA update from zeroed buffers, models/vq_vae.py:52-53,88): remember
+    // the LOWEST such index of the level as K_per - local index (0 = none) for the de-duplication below
+    if (acc == 0.0) atomicMax(reinterpret_cast<int*>(meta + 7), K_per - (row % K_per));
     if (bad || !(acc == acc) || isinf(static_cast<float>(acc))) meta[1] = 1.0f;
+  }
+  }
+  // De-duplicate dead codes.  Every all-zero row of a level has the same distance to any latent, and arg-min
+  // takes the lowest index, so all but the first can never be chosen: their |e|^2/2 becomes +inf (score -inf).
+  // Without this a collapsed codebook fills every row's candidate list with ties and sends the row to the exact
+  // SIMT kernel (measured: 54 % of the stage-2 training step).  Done by the last block to finish (ticket in
+  // level_meta[6] of level 0, zeroed by the launcher), so it costs no extra launch.
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+    s_last = atomicAdd(reinterpret_cast<int*>(level_meta + 6), 1) == static_cast<int>(gridDim.x) - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float kInf = __int_as_float(0x7f800000);
+  for (int r = threadIdx.x; r < K_total; r += blockDim.x) {
+    const int lvl = r / K_per;
+    const int first = *reinterpret_cast<volatile int*>(level_meta + lvl * VQB200_LEVEL_META_FLOATS + 7);
+    if (first > 0 && *reinterpret_cast<volatile float*>(ee_half + r) == 0.f && K_per - (r % K_per) != first) {
+      ee_half[r] = kInf;
+      ee_half[K_total + r] = kInf;
+    }
   }
 }
 
@@ -363,23 +389,24 @@ __device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
 
 __global__ void __launch_bounds__(256)
 scatter_add_kernel(const float4* __restrict__ z, const int64_t* __restrict__ idx,
-                   const uint8_t* __restrict__ row_mask, int64_t N, int D4, int K_total,
+                   const uint8_t* __restrict__ row_mask, int64_t N, int D4, int K_total, int rpw,
                    float* __restrict__ seg_sum, float* __restrict__ seg_cnt) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-  // each warp owns 32 consecutive rows per step: lane l looks up row base+l, peers with the same code
-  // are merged so the count costs one atomic per distinct code (warp-aggregated atomics).
-  for (int64_t base = warp0 * 32; base < N; base += nwarps * 32) {
+  // each warp owns rpw consecutive rows per step (32 for large N; fewer for small N so that every SM has
+  // warps -- 8192 rows at 32 per warp would occupy 32 of the 148 SMs): lane l < rpw looks up row base+l, peers
+  // with the same code are merged so the count costs one atomic per distinct code (warp-aggregated atomics).
+  for (int64_t base = warp0 * rpw; base < N; base += nwarps * rpw) {
     const int64_t my_row = base + lane;
     int64_t my_k = -1;
-    if (my_row < N && (!row_mask || row_mask[my_row])) {
+    if (lane < rpw && my_row < N && (!row_mask || row_mask[my_row])) {
       my_k = idx[my_row];
       if (my_k < 0 || my_k >= K_total) my_k = -1;
     }
     const unsigned peers = __match_any_sync(0xffffffffu, my_k);
     if (my_k >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(seg_cnt + my_k, static_cast<float>(__popc(peers)));
-    for (int r = 0; r < 32; ++r) {
+    for (int r = 0; r < rpw; ++r) {
       const int64_t k = __shfl_sync(0xffffffffu, my_k, r);
       if (k < 0) continue;
       const float4* src = z + (base + r) * D4;
@@ -392,12 +419,14 @@ scatter_add_kernel(const float4* __restrict__ z, const int64_t* __restrict__ idx
 int launch_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
                        float* seg_sum, float* seg_cnt, cudaStream_t s) {
   if (N == 0) return VQB200_OK;
-  int64_t warps = (N + 31) / 32;
+  int rpw = 32;                                            // rows per warp step: keep >= ~4K warps in flight
+  while (rpw > 1 && N / rpw < 4096) rpw >>= 1;
+  int64_t warps = (N + rpw - 1) / rpw;
   int64_t blocks = (warps + 7) / 8;
   const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
   if (blocks > cap) blocks = cap;
   scatter_add_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(reinterpret_cast<const float4*>(z), idx, row_mask,
-                                                                  N, D >> 2, K_total, seg_sum, seg_cnt);
+                                                                  N, D >> 2, K_total, rpw, seg_sum, seg_cnt);
   return status_of(cudaGetLastError());
 }
 

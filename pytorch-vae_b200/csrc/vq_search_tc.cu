@@ -332,7 +332,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
       const int64_t sub = row_ok ? (row * p.ksplit + ks) * TC_CS + cs : 0;   // this warp's candidate sub-list
       uint2* cand_row = p.cand + sub * TC_SLOTS;
       float best = kNegInf;
-      float thr = margin == margin ? best : margin;     // admission threshold best - margin (NaN: never admits)
+      // admission threshold best - margin (NaN: never admits).  It starts at the lowest FINITE value: a chunk
+      // of -inf scores (padding, de-duplicated dead codes) must not be admitted, or a slice made of such
+      // columns only would overflow its record list with them.
+      float thr = margin == margin ? -3.0e38f : margin;
       int cnt = 0;
 
       for (int t = t0; t < t1; ++t, ++tg) {
@@ -558,7 +561,7 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_const
       const int64_t sub = row_ok ? row * P2_CS + cs : 0;
       uint2* cand_row = p.cand + sub * TC_SLOTS;
       float best = kNegInf;
-      float thr = margin == margin ? best : margin;
+      float thr = margin == margin ? -3.0e38f : margin;   // lowest finite value: -inf chunks are never admitted
       int cnt = 0;
       for (int t = 0; t < p.code_tiles; ++t, ++tg) {
         const uint32_t b = tg & 1;
@@ -642,8 +645,10 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
       bool bad = false;
       for (int sb = 0; sb < nsub; ++sb) {
         const int c = cnt[row * nsub + sb];
-        bad |= (c <= 0 || c > TC_CAND);
-        bmax = fmaxf(bmax, best[row * nsub + sb]);
+        const float bs = best[row * nsub + sb];
+        // an empty list is legitimate only for a slice whose columns are all -inf (masked dead codes, padding)
+        bad |= (c < 0 || c > TC_CAND || (c == 0 && bs != __int_as_float(0xff800000)));
+        bmax = fmaxf(bmax, bs);
       }
       const float mg = margin[row];
       if (!bad && mg == mg) {

@@ -158,3 +158,46 @@ def test_forward_host_equals_forward(vq, K, D, L, N, chunk):
     assert torch.equal(idx_c, idx.cpu())
     if L == 1:
         assert none_st is None and none_zq is None
+
+
+def test_graphed_train_step_matches_eager(vq):
+    """Forward + EMA update + backward as one CUDA graph == the same steps run eagerly (buffers, grads, outputs)."""
+    dev = torch.device("cuda:0")
+    E, z = large_case_inputs(78, 256, 128, 3, 16, 64)
+
+    def make():
+        q = vq.VectorQuantizerEMA(256, 128, num_quantizers=3, print_init=False, decay=0.9).to(dev).train()
+        q.embedding.copy_(torch.from_numpy(E).to(dev))
+        return q
+    qe, qg = make(), make()
+    g = vq.GraphedTrainStep(qg, torch.from_numpy(z).to(dev))
+    assert torch.equal(qg.embedding, qe.embedding) and float(qg.ema_cluster_size.abs().sum()) == 0.0   # capture left no trace
+    rs = np.random.RandomState(5)
+    for step in range(3):
+        zs = torch.from_numpy((z + 0.1 * rs.standard_normal(z.shape)).astype(np.float32)).to(dev)
+        gs = torch.from_numpy(rs.standard_normal(z.shape).astype(np.float32)).to(dev)
+        ze = zs.clone().requires_grad_(True)
+        st, zq, idx, stats = qe(ze, do_ema_update=True)
+        torch.autograd.backward([st, qe.last_commit], [gs, torch.full((), 0.3, device=dev)])
+        st2, zq2, idx2, stats2, commit2, grad2 = g(zs, gs, 0.3)
+        # the EMA update after every level moves the codebook by the atomics' summation noise, so the two runs'
+        # codebooks (and with them z_q) agree to ~1e-6, not bit for bit
+        assert torch.equal(idx, idx2)
+        assert torch.allclose(zq, zq2, rtol=1e-4, atol=1e-5) and torch.allclose(st.detach(), st2.detach(), rtol=1e-4, atol=1e-5)
+        assert torch.allclose(stats, stats2) and torch.allclose(qe.last_commit, commit2)
+        assert torch.allclose(ze.grad, grad2, rtol=1e-6, atol=1e-8)
+        # atomics order differs run to run: EMA buffers agree to summation noise
+        assert torch.allclose(qe.ema_embedding, qg.ema_embedding, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(qe.embedding, qg.embedding, rtol=1e-3, atol=1e-5)
+
+
+def test_forward_host_empty_and_ragged(vq):
+    dev = torch.device("cuda:0")
+    q = vq.VectorQuantizerEMA(512, 64, print_init=False).to(dev).eval()
+    st, zq, idx, stats = q.forward_host(torch.empty(0, 64, 64))
+    assert idx.numel() == 0 and zq.shape == (0, 64, 64)
+    z = torch.randn(70, 64, 64)                                   # 4480 rows: one full chunk of 4096 + a ragged tail
+    with torch.no_grad():
+        ref = q(z.to(dev), do_ema_update=False)
+    out = q.forward_host(z, chunk_rows=4096)
+    assert torch.equal(out[2], ref[2].cpu()) and torch.equal(out[1], ref[1]) and torch.equal(out[0], ref[0])
