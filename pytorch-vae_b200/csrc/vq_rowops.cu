@@ -21,6 +21,7 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int D4 = D >> 2;
+  __shared__ int s_red[8][6];
   if (row < K_total) {
   constexpr bool EMA = MODE == 1;
   float denom = 1.f;
@@ -98,22 +99,45 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
   if (lane == 0) {
     ee_half[row] = static_cast<float>(0.5 * acc);
     ee_half[K_total + row] = static_cast<float>(0.5 * accb);
-    float* meta = level_meta + (row / K_per) * VQB200_LEVEL_META_FLOATS;
-    // round the norms UP a hair: they feed an error bound
+    // level norms (rounded UP a hair: they feed an error bound), dead-code marker, non-finite flag
+    const float kInfF = __int_as_float(0x7f800000);
     const float n0 = static_cast<float>(sqrt(acc)) * 1.0000002f, n1 = static_cast<float>(sqrt(accb)) * 1.0000002f;
-    if (n0 == n0 && n0 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 0), __float_as_int(n0));
-    if (n1 == n1 && n1 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 2), __float_as_int(n1));
     const float n3 = static_cast<float>(sqrt(accd)) * 1.0000002f;          // max_k |e_k - bf16(e_k)|
-    if (n3 == n3 && n3 < __int_as_float(0x7f800000)) atomicMax(reinterpret_cast<int*>(meta + 3), __float_as_int(n3));
     // fp16 plane: an overflowed element makes these +inf, which the pre-pass turns into "exact path for every row"
     const float n4 = static_cast<float>(sqrt(acch)) * 1.0000002f, n5 = static_cast<float>(sqrt(accdh)) * 1.0000002f;
-    if (n4 == n4) atomicMax(reinterpret_cast<int*>(meta + 4), __float_as_int(n4));
-    if (n5 == n5) atomicMax(reinterpret_cast<int*>(meta + 5), __float_as_int(n5));
-    // an all-zero row (a dead code after an EMA update from zeroed buffers, models/vq_vae.py:52-53,88): remember
-    // the LOWEST such index of the level as K_per - local index (0 = none) for the de-duplication below
-    if (acc == 0.0) atomicMax(reinterpret_cast<int*>(meta + 7), K_per - (row % K_per));
-    if (bad || !(acc == acc) || isinf(static_cast<float>(acc))) meta[1] = 1.0f;
+    int v[6];
+    v[0] = (n0 == n0 && n0 < kInfF) ? __float_as_int(n0) : 0;
+    v[1] = (n1 == n1 && n1 < kInfF) ? __float_as_int(n1) : 0;
+    v[2] = (n3 == n3 && n3 < kInfF) ? __float_as_int(n3) : 0;
+    v[3] = (n4 == n4) ? __float_as_int(n4) : 0;
+    v[4] = (n5 == n5) ? __float_as_int(n5) : 0;
+    // an all-zero row (a dead code after an EMA update from zeroed buffers, models/vq_vae.py:52-53,88): the LOWEST
+    // such index of the level is remembered as K_per - local index (0 = none) for the de-duplication below
+    v[5] = (acc == 0.0) ? K_per - (row % K_per) : 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s_red[threadIdx.x >> 5][i] = v[i];
+    if (bad || !(acc == acc) || isinf(static_cast<float>(acc)))
+      level_meta[(row / K_per) * VQB200_LEVEL_META_FLOATS + 1] = 1.0f;
   }
+  }
+  // one atomicMax per block and word instead of one per row (K_total x 6 atomics on a handful of L2 lines);
+  // positive floats order like their bit patterns.  A block whose rows straddle two levels reduces per row.
+  __syncthreads();
+  {
+    const int wpb = blockDim.x >> 5, row0 = blockIdx.x * wpb;
+    const int rows_here = K_total - row0 < wpb ? K_total - row0 : wpb;
+    const int slot[6] = {0, 2, 3, 4, 5, 7};
+    if (rows_here > 0 && threadIdx.x < 6) {
+      const bool one_level = row0 / K_per == (row0 + rows_here - 1) / K_per;
+      int m = 0;
+      for (int w = 0; w < rows_here; ++w) {
+        const int x = s_red[w][threadIdx.x];
+        if (one_level) m = x > m ? x : m;
+        else if (x) atomicMax(reinterpret_cast<int*>(level_meta + ((row0 + w) / K_per) * VQB200_LEVEL_META_FLOATS + slot[threadIdx.x]), x);
+      }
+      if (one_level && m)
+        atomicMax(reinterpret_cast<int*>(level_meta + (row0 / K_per) * VQB200_LEVEL_META_FLOATS + slot[threadIdx.x]), m);
+    }
   }
   // De-duplicate dead codes.  Every all-zero row of a level has the same distance to any latent, and arg-min
   // takes the lowest index, so all but the first can never be chosen: their |e|^2/2 becomes +inf (score -inf).
@@ -387,6 +411,8 @@ __device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
                : "memory");
 }
 
+constexpr int SCATTER_SLICES = 4;   // float4 slices per lane held in registers: D <= 512
+
 __global__ void __launch_bounds__(256)
 scatter_add_kernel(const float4* __restrict__ z, const int64_t* __restrict__ idx,
                    const uint8_t* __restrict__ row_mask, int64_t N, int D4, int K_total, int rpw,
@@ -406,12 +432,49 @@ scatter_add_kernel(const float4* __restrict__ z, const int64_t* __restrict__ idx
     }
     const unsigned peers = __match_any_sync(0xffffffffu, my_k);
     if (my_k >= 0 && lane == (__ffs(peers) - 1)) atomicAdd(seg_cnt + my_k, static_cast<float>(__popc(peers)));
-    for (int r = 0; r < rpw; ++r) {
-      const int64_t k = __shfl_sync(0xffffffffu, my_k, r);
-      if (k < 0) continue;
-      const float4* src = z + (base + r) * D4;
-      float* dst = seg_sum + k * (static_cast<int64_t>(D4) * 4);
-      for (int c = lane; c < D4; c += 32) red_add_v4(dst + c * 4, ld_stream(src + c));
+    if (D4 <= 32 * SCATTER_SLICES) {
+      // runs of consecutive rows with the same code are summed in registers and cost ONE set of reductions:
+      // early in training, and on every level of a collapsed residual codebook, most rows share a code, and
+      // thousands of atomics on the same 128 addresses serialise in L2 (measured 68 us -> 36 us -> see profiles/)
+      float4 run[SCATTER_SLICES];
+      int64_t run_k = -1;
+      auto flush = [&]() {
+        if (run_k < 0) return;
+        float* dst = seg_sum + run_k * (static_cast<int64_t>(D4) * 4);
+#pragma unroll
+        for (int j = 0; j < SCATTER_SLICES; ++j) {
+          const int c = lane + 32 * j;
+          if (c < D4) red_add_v4(dst + c * 4, run[j]);
+        }
+      };
+      for (int r = 0; r < rpw; ++r) {
+        const int64_t k = __shfl_sync(0xffffffffu, my_k, r);
+        if (k < 0) continue;
+        if (k != run_k) {
+          flush();
+          run_k = k;
+#pragma unroll
+          for (int j = 0; j < SCATTER_SLICES; ++j) run[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float4* src = z + (base + r) * D4;
+#pragma unroll
+        for (int j = 0; j < SCATTER_SLICES; ++j) {
+          const int c = lane + 32 * j;
+          if (c < D4) {
+            const float4 v = ld_stream(src + c);
+            run[j].x += v.x; run[j].y += v.y; run[j].z += v.z; run[j].w += v.w;
+          }
+        }
+      }
+      flush();
+    } else {
+      for (int r = 0; r < rpw; ++r) {
+        const int64_t k = __shfl_sync(0xffffffffu, my_k, r);
+        if (k < 0) continue;
+        const float4* src = z + (base + r) * D4;
+        float* dst = seg_sum + k * (static_cast<int64_t>(D4) * 4);
+        for (int c = lane; c < D4; c += 32) red_add_v4(dst + c * 4, ld_stream(src + c));
+      }
     }
   }
 }
@@ -419,8 +482,8 @@ scatter_add_kernel(const float4* __restrict__ z, const int64_t* __restrict__ idx
 int launch_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
                        float* seg_sum, float* seg_cnt, cudaStream_t s) {
   if (N == 0) return VQB200_OK;
-  int rpw = 32;                                            // rows per warp step: keep >= ~4K warps in flight
-  while (rpw > 1 && N / rpw < 4096) rpw >>= 1;
+  int rpw = 32;                                            // rows per warp step: ~4K warps in flight when N allows,
+  while (rpw > 8 && N / rpw < 4096) rpw >>= 1;             // but >= 8 rows so that runs of one code aggregate
   int64_t warps = (N + rpw - 1) / rpw;
   int64_t blocks = (warps + 7) / 8;
   const int64_t cap = static_cast<int64_t>(kNumSMs) * 8;
