@@ -30,7 +30,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 4
+#define VQB200_ABI_VERSION 5
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -161,6 +161,16 @@ VQB200_API int vqb200_ema_finalize(const float* seg_sum, const float* seg_cnt, f
  * keeps its centroid; the derived cache is refreshed in the same pass.  seg_* come from vqb200_scatter_add. */
 VQB200_API int vqb200_kmeans_finalize(const float* seg_sum, const float* seg_cnt, int K_total, int D, int K_per,
                            float* E, uint16_t* E_bf16, float* ee_half, float* level_meta, void* stream);
+
+/* Residual-VQ tail in one pass (eval mode, <= 8 levels): from the level-major GLOBAL ids
+ * idx[l*level_stride + n] (level_stride = N for a packed [L*N] array),
+ *   zq_out = ((E[i_0] + E[i_1]) + ...) in level order (models/vq_vae.py:261), zq_st_out = fl(z + fl(zq - z)) (:263),
+ *   sqerr_sum += sum (zq - z)^2 (:1293), hist[i_l] += 1 for every level (:266).  Every output is optional.
+ * Replaces the per-level z_q accumulation of vqb200_gather plus vqb200_st_loss when the codebook does not change
+ * between levels (no EMA update): z_q is written once instead of being re-read and re-written per level. */
+VQB200_API int vqb200_rvq_finalize(const float* z, const int64_t* idx_level_major, int64_t level_stride,
+                        int64_t N, int D, int L, const float* E, int K_total, float* zq_out, float* zq_st_out, double* sqerr_sum,
+                        int32_t* hist, void* stream);
 
 /* Soft assignment of the soft-VQ training path (models/vq_vae.py:838-843, single-level codebooks):
  *   z_soft[n] = sum_k softmax_k(-|z_n - e_k|^2 / max(1e-8, tau)) e_k

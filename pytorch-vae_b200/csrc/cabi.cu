@@ -261,6 +261,17 @@ int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok,
                                   static_cast<cudaStream_t>(stream));
 }
 
+int vqb200_rvq_finalize(const float* z, const int64_t* idx_level_major, int64_t level_stride, int64_t N, int D, int L,
+                        const float* E, int K_total, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                        void* stream) {
+  VQ_REQUIRE(N >= 0 && L >= 1 && K_total > 0 && level_stride >= N, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && idx_level_major && E), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D) && L <= 8, VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(zq_out) && aligned16(zq_st_out), VQB200_EALIGN);
+  return launch_rvq_finalize(z, idx_level_major, level_stride, N, D, L, E, K_total, zq_out, zq_st_out, sqerr_sum, hist,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_soft_assign(const float* z, int64_t N, int D, const float* E, int K, float tau, float* z_soft_out,
                        void* stream) {
   VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);

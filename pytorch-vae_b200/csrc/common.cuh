@@ -145,6 +145,9 @@ int launch_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_ma
 int launch_commit_backward(const float* g, const float* gc, const float* z, const float* zq, int64_t n_elems,
                            float scale, float* out, cudaStream_t s);
 int launch_relayout(const int64_t* in, int Q, int64_t B, int64_t M, void* out, int bytes, cudaStream_t s);
+int launch_rvq_finalize(const float* z, const int64_t* idx, int64_t lstride, int64_t N, int D, int L, const float* E,
+                        int K_total,
+                        float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist, cudaStream_t s);
 int launch_soft_assign(const float* z, int64_t N, int D, const float* E, int K, float tau, float* z_soft,
                        cudaStream_t s);
 int launch_indices_to_latent(const void* idx, int bytes, int64_t n_tok, int Q, const float* E, int K_total, int D,

@@ -347,6 +347,73 @@ int launch_st_loss(const float* z, const float* zq, int64_t n_elems, float* st, 
 }
 
 // --------------------------------------------------------------------------------------------
+// residual-VQ tail in ONE pass (eval mode): z_q = ((E[i_0] + E[i_1]) + ...) summed in level order
+// (models/vq_vae.py:261), z_q_st = fl(z + fl(z_q - z)) (:263), sum (z_q - z)^2 (:1293) and the usage histogram
+// of every level (:266), straight from the level-major indices.  The per-level path keeps z_q in HBM and
+// re-reads / re-writes it on every level (3 x 8 D bytes per latent more at four levels) and reads it once more
+// for the straight-through pass; here the codebook rows come from L2 and each output is written once.
+// Not usable while the EMA update mutates the codebook between levels (:251 then :248 of the next level).
+// --------------------------------------------------------------------------------------------
+constexpr int RVQ_MAX_LEVELS = 8;
+
+__global__ void __launch_bounds__(ROW_THREADS)
+rvq_finalize_kernel(const float4* __restrict__ z, const int64_t* __restrict__ idx, int64_t lstride, int64_t N, int D4,
+                    int d4_shift, int L, const float4* __restrict__ E, int K_total, float4* __restrict__ zq_out,
+                    float4* __restrict__ zq_st_out, double* sqerr_sum, int32_t* __restrict__ hist) {
+  const int64_t total = N * D4;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  float err = 0.f;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t row;
+    int c;
+    if (d4_shift >= 0) { row = i >> d4_shift; c = static_cast<int>(i & ((1 << d4_shift) - 1)); }
+    else { row = i / D4; c = static_cast<int>(i - row * D4); }
+    int k[RVQ_MAX_LEVELS];
+#pragma unroll
+    for (int l = 0; l < RVQ_MAX_LEVELS; ++l) {
+      if (l < L) {
+        const int64_t kk = idx[static_cast<int64_t>(l) * lstride + row];
+        k[l] = (kk >= 0 && kk < K_total) ? static_cast<int>(kk) : -1;
+      }
+    }
+    const float4 v = ld_stream(z + i);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < RVQ_MAX_LEVELS; ++l) {
+      if (l < L && k[l] >= 0) {
+        const float4 e = __ldg(E + static_cast<int64_t>(k[l]) * D4 + c);
+        if (l == 0) q = e;
+        else { q.x = __fadd_rn(q.x, e.x); q.y = __fadd_rn(q.y, e.y); q.z = __fadd_rn(q.z, e.z); q.w = __fadd_rn(q.w, e.w); }
+        if (hist && c == 0) atomicAdd(hist + k[l], 1);
+      }
+    }
+    float4 df;
+    df.x = __fsub_rn(q.x, v.x); df.y = __fsub_rn(q.y, v.y); df.z = __fsub_rn(q.z, v.z); df.w = __fsub_rn(q.w, v.w);
+    if (zq_out) st_stream(zq_out + i, q);
+    if (zq_st_out)
+      st_stream(zq_st_out + i, make_float4(__fadd_rn(v.x, df.x), __fadd_rn(v.y, df.y), __fadd_rn(v.z, df.z),
+                                           __fadd_rn(v.w, df.w)));
+    err = fmaf(df.x, df.x, err); err = fmaf(df.y, df.y, err);
+    err = fmaf(df.z, df.z, err); err = fmaf(df.w, df.w, err);
+  }
+  if (sqerr_sum) block_add_double(static_cast<double>(err), sqerr_sum);
+}
+
+int launch_rvq_finalize(const float* z, const int64_t* idx, int64_t lstride, int64_t N, int D, int L, const float* E,
+                        int K_total,
+                        float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist, cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  if (L < 1 || L > RVQ_MAX_LEVELS) return VQB200_ESHAPE;
+  const int D4 = D >> 2;
+  int shift = -1;
+  if ((D4 & (D4 - 1)) == 0) { shift = 0; while ((1 << shift) < D4) ++shift; }
+  rvq_finalize_kernel<<<stream_grid(N * D4), ROW_THREADS, 0, s>>>(
+      reinterpret_cast<const float4*>(z), idx, lstride, N, D4, shift, L, reinterpret_cast<const float4*>(E), K_total,
+      reinterpret_cast<float4*>(zq_out), reinterpret_cast<float4*>(zq_st_out), sqerr_sum, hist);
+  return status_of(cudaGetLastError());
+}
+
+// --------------------------------------------------------------------------------------------
 // statistics: one CTA over the K_total-bin histogram
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)

@@ -179,6 +179,17 @@ def kmeans_finalize(seg_sum, seg_cnt, E, cache: CodebookCache):
     _count(1)
 
 
+def rvq_finalize(z, idx_level0, level_stride, L, E, zq_out=None, zq_st_out=None, sqerr_sum=None, hist=None):
+    """Residual-VQ tail in one pass: z_q (level-order sum), z_q_st, squared error and histogram from the indices.
+    ``idx_level0`` is level 0's id vector; level l's starts ``l * level_stride`` elements further on."""
+    _need_cuda(z, idx_level0, E)
+    _f32c(z, "z")
+    N, D = z.shape
+    check(lib.vqb200_rvq_finalize(ptr(z), ptr(idx_level0), level_stride, N, D, L, ptr(E), E.shape[0], ptr(zq_out),
+                                  ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), stream_ptr()), "vqb200_rvq_finalize")
+    _count(1)
+
+
 def soft_assign(z, E, tau: float, out=None):
     """z_soft = softmax(-|z - e|^2 / tau) @ E (models/vq_vae.py:838-843), online softmax, nothing materialised."""
     _need_cuda(z, E)

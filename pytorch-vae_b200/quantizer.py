@@ -329,6 +329,20 @@ class VectorQuantizerEMA(nn.Module):
             return
         residual = flat
         spare = [torch.empty(n, D, dtype=torch.float32, device=flat.device) for _ in range(min(2, L - 1))]
+        lstride = (idx_levels[1].data_ptr() - idx_levels[0].data_ptr()) // 8 if L > 1 else n
+        even = all(idx_levels[l].data_ptr() == idx_levels[0].data_ptr() + 8 * l * lstride for l in range(L))
+        if not do_ema and L <= 8 and even and lstride >= n:
+            # the codebook does not move between levels: the levels only carry the residual forward, and ONE
+            # pass at the end forms z_q (level-order sum), z_q_st, the loss partial sum and the histogram from
+            # the indices -- z_q is not re-read and re-written on every level
+            for level in range(L):
+                ops.search(residual, E, cache, level, mode, idx_levels[level])
+                if level < L - 1:
+                    ops.gather(residual, E, idx_levels[level], residual_out=spare[level % 2])
+                    residual = spare[level % 2]
+            ops.rvq_finalize(flat, idx_levels[0], lstride, L, E, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
+                             hist=hist)
+            return
         for level in range(L):
             idx_l = idx_levels[level]
             if level > 0 and do_ema:
