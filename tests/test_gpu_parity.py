@@ -410,3 +410,35 @@ def test_full_size_properties(vq, dev, K, D, N, mode):
     ref = O.nearest_code64(zs, E.cpu().numpy())
     mm, outside = O.near_tie_rows(zs, E.cpu().numpy(), npy(idx.view(-1)[rows.to(dev)]), ref)
     assert outside.size == 0 and mm.size <= 2
+
+
+@pytest.mark.parametrize("K_per,D,L,N,lstride_pad", [(64, 48, 5, 333, 0), (100, 20, 8, 1, 7), (1024, 512, 4, 2048, 0),
+                                                     (32, 64, 1, 100, 0), (16, 36, 3, 4097, 100)])
+def test_rvq_finalize_matches_level_order_sum(vq, dev, K_per, D, L, N, lstride_pad):
+    """vqb200_rvq_finalize: z_q = ((E[i0] + E[i1]) + ...) in level order, bit for bit what stack().sum(0) gives
+    (models/vq_vae.py:261); z_q_st, squared error and histogram as the per-level path produces them.  Odd sizes:
+    D/4 not a power of two, one row, a padded level stride."""
+    rs = np.random.RandomState(K_per + N)
+    E = rs.standard_normal((K_per * L, D)).astype(np.float32)
+    z = rs.standard_normal((N, D)).astype(np.float32)
+    stride = N + lstride_pad
+    ids = np.full((L, stride), -7, dtype=np.int64)
+    for l in range(L):
+        ids[l, :N] = rs.randint(0, K_per, N) + l * K_per
+    want = E[ids[0, :N]].copy()
+    for l in range(1, L):
+        want = (want + E[ids[l, :N]]).astype(np.float32)
+    want_st = (z + (want - z).astype(np.float32)).astype(np.float32)
+    zq = torch.empty(N, D, device=dev)
+    st = torch.empty(N, D, device=dev)
+    scratch = torch.zeros(2 + K_per * L, dtype=torch.int32, device=dev)
+    idt = T(ids, dev)
+    vq.ops.rvq_finalize(T(z, dev), idt.view(-1), stride, L, T(E, dev), zq_out=zq, zq_st_out=st,
+                        sqerr_sum=scratch[:2].view(torch.float64), hist=scratch[2:])
+    assert np.array_equal(npy(zq), want) and np.array_equal(npy(st), want_st)
+    assert np.array_equal(npy(scratch[2:]), np.bincount(ids[:, :N].reshape(-1), minlength=K_per * L))
+    np.testing.assert_allclose(float(scratch[:2].view(torch.float64)[0]), float(((want.astype(np.float64) - z) ** 2).sum()),
+                               rtol=1e-5)
+    # optional outputs may be absent
+    vq.ops.rvq_finalize(T(z, dev), idt.view(-1), stride, L, T(E, dev), zq_out=zq)
+    assert np.array_equal(npy(zq), want)
