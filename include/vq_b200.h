@@ -30,7 +30,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 5
+#define VQB200_ABI_VERSION 6
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -86,6 +86,21 @@ VQB200_API int vqb200_search(const float* z, int64_t N, int D, const float* E, c
                   const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K,
                   int mode, int64_t idx_offset, int64_t* idx_out, void* workspace,
                   size_t workspace_bytes, void* stream);
+
+/* Residual VQ, between two levels (models/vq_vae.py:258 then :238 of the next level), in ONE read of the rows:
+ *   residual_out = fl(z - E_full[idx])   [N, D] fp32
+ *   z16_out      = the 16-bit tensor-core operand copy of residual_out for `mode` (fp16 / bf16)   [N, D]
+ *   margin_out   = the admission margins of the NEXT level's search for those rows (next_level_meta)   [N]
+ * vqb200_search_prepped is vqb200_search given that copy and those margins (it skips its own pre-pass); it exists
+ * for shapes vqb200_search_path() sends to the tensor kernel and returns VQB200_ESHAPE otherwise. */
+VQB200_API int vqb200_residual_prep(const float* z, const float* E_full, const int64_t* idx, int64_t N, int D,
+                         int K_total, int mode, const float* next_level_meta, float* residual_out,
+                         uint16_t* z16_out, float* margin_out, void* stream);
+VQB200_API int vqb200_search_prepped(const float* z, const uint16_t* z16, const float* margin, int64_t N, int D,
+                          const float* E, const uint16_t* E_bf16, const float* ee_half,
+                          const float* ee_half_bf16, const float* level_meta, int K, int mode,
+                          int64_t idx_offset, int64_t* idx_out, void* workspace, size_t workspace_bytes,
+                          void* stream);
 
 /* Measurement hook (bench.py): while enabled, vqb200_search brackets every launch of its dominant kernel (the
  * tcgen05 search kernel; the SIMT kernel on shapes that take the SIMT path) with CUDA events on the launching

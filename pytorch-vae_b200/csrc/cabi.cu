@@ -96,6 +96,34 @@ int vqb200_search_launches(int64_t N, int K, int D, int mode) {
   return tc_supported(N, K, D) ? tc_launches(N, K, D) : 1;
 }
 
+int vqb200_residual_prep(const float* z, const float* E_full, const int64_t* idx, int64_t N, int D, int K_total,
+                         int mode, const float* next_level_meta, float* residual_out, uint16_t* z16_out,
+                         float* margin_out, void* stream) {
+  VQ_REQUIRE(N >= 0 && K_total > 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && E_full && idx && next_level_meta && residual_out && z16_out && margin_out), VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E_full) && aligned16(residual_out) && aligned16(z16_out), VQB200_EALIGN);
+  return launch_residual_prep(z, E_full, idx, N, D, K_total, mode, next_level_meta, residual_out, z16_out, margin_out,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_search_prepped(const float* z, const uint16_t* z16, const float* margin, int64_t N, int D, const float* E,
+                          const uint16_t* E_bf16, const float* ee_half, const float* ee_half_bf16,
+                          const float* level_meta, int K, int mode, int64_t idx_offset, int64_t* idx_out,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  VQ_REQUIRE(N > 0 && K > 0 && z && z16 && margin && idx_out, VQB200_EINVAL);
+  VQ_REQUIRE(E && E_bf16 && ee_half && ee_half_bf16 && level_meta, VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D) && tc_supported(N, K, D), VQB200_ESHAPE);      // the prepared copy only feeds the tensor path
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(E_bf16) && (reinterpret_cast<uintptr_t>(z16) & 127u) == 0 &&
+                 (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, VQB200_EALIGN);
+  VQ_REQUIRE(workspace_bytes >= vqb200_search_workspace_bytes(N, K, D, mode) && workspace, VQB200_EWORKSPACE);
+  PrepArgs prep{z16, margin};
+  return launch_search_tc(z, N, D, E, E_bf16, ee_half, ee_half_bf16, level_meta, K, mode, idx_offset, idx_out,
+                          workspace, workspace_bytes, static_cast<cudaStream_t>(stream), nullptr, &prep);
+}
+
 int vqb200_search(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                   const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                   int64_t* idx_out, void* workspace, size_t workspace_bytes, void* stream) {

@@ -121,10 +121,18 @@ struct GatherArgs {
   int32_t* hist;
   const uint8_t* row_mask;
 };
+// optional: the 16-bit copy and the admission margins of the rows were already produced (vqb200_residual_prep)
+struct PrepArgs {
+  const uint16_t* z16;      // [N, D]
+  const float* margin;      // [N]
+};
+int launch_residual_prep(const float* z, const float* E_full, const int64_t* idx, int64_t N, int D, int K_total,
+                         int mode, const float* next_level_meta, float* residual_out, uint16_t* z16_out,
+                         float* margin_out, cudaStream_t s);
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                      int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s,
-                     const GatherArgs* ga = nullptr);
+                     const GatherArgs* ga = nullptr, const PrepArgs* prep = nullptr);
 bool fused_supported(int64_t N, int K, int D);
 size_t fused_workspace_bytes(int64_t N);
 int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,

@@ -33,9 +33,13 @@ constexpr int TC_SLOTS = TC_CAND + 1;
 // ------------------------------------------------------------------------------------ z pre-pass
 // z fp32 -> 16-bit tensor-core operand (fp16 in fp32 mode, bf16 in bf16_input mode; RN) plus the per-row
 // admission margin.  One warp per row.
+// With E_sub / idx_sub / residual_out the row is first replaced by the residual fl(z - E_sub[idx_sub[row]])
+// (models/vq_vae.py:258), which is also written out in fp32: the residual update of one RVQ level and the
+// pre-pass of the next in ONE read of the row.
 __global__ void __launch_bounds__(256)
 zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const float* __restrict__ level_meta,
-             __nv_bfloat16* __restrict__ zb, float* __restrict__ margin) {
+             __nv_bfloat16* __restrict__ zb, float* __restrict__ margin, const float* __restrict__ E_sub,
+             const int64_t* __restrict__ idx_sub, int K_sub, float* __restrict__ residual_out) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -49,8 +53,20 @@ zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const floa
   const float coef = 2.f * static_cast<float>(D + 32) * 1.1920929e-7f;
   for (int64_t row = warp; row < n; row += nwarps) {
     float ss = 0.f, sse = 0.f;
+    int64_t ksub = -1;
+    if (E_sub) {
+      ksub = idx_sub[row];
+      if (ksub < 0 || ksub >= K_sub) ksub = -1;           // never produced by vqb200_search; leaves the row as is
+    }
     for (int c = lane; c < D4; c += 32) {
-      const float4 v = ld_stream(reinterpret_cast<const float4*>(z) + row * D4 + c);
+      float4 v = ld_stream(reinterpret_cast<const float4*>(z) + row * D4 + c);
+      if (E_sub) {
+        if (ksub >= 0) {
+          const float4 e = __ldg(reinterpret_cast<const float4*>(E_sub) + ksub * D4 + c);
+          v.x = __fsub_rn(v.x, e.x); v.y = __fsub_rn(v.y, e.y); v.z = __fsub_rn(v.z, e.z); v.w = __fsub_rn(v.w, e.w);
+        }
+        st_stream(reinterpret_cast<float4*>(residual_out) + row * D4 + c, v);
+      }
       uint16_t b0, b1, b2, b3;
       float f0, f1, f2, f3;
       if (bfm) {
@@ -86,6 +102,18 @@ zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const floa
       margin[row] = m;
     }
   }
+}
+
+int launch_residual_prep(const float* z, const float* E_full, const int64_t* idx, int64_t N, int D, int K_total,
+                         int mode, const float* next_level_meta, float* residual_out, uint16_t* z16_out,
+                         float* margin_out, cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  int64_t blocks = (N + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  zprep_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(z, N, D, mode, next_level_meta,
+                                                             reinterpret_cast<__nv_bfloat16*>(z16_out), margin_out, E_full,
+                                                             idx, K_total, residual_out);
+  return status_of(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------ the tensor kernel
@@ -917,7 +945,8 @@ static TcSet carve(uint8_t* w, int64_t cap, int D, int BM) {
 // SM, so they co-reside.  Everything is joined back into the caller's stream before returning.
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
-                     int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s, const GatherArgs* ga) {
+                     int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s, const GatherArgs* ga,
+                     const PrepArgs* prep) {
   TcPlan pl;
   if (!tc_plan(N, K, D, &pl)) return VQB200_ESHAPE;
   if (workspace_bytes < tc_workspace_bytes(N, K, D)) return VQB200_EWORKSPACE;
@@ -988,8 +1017,12 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     VQ_CUDA(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int), s_prep));
     int64_t blocks = (rows + 7) / 8;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    zprep_kernel<<<static_cast<unsigned>(blocks), 256, 0, s_prep>>>(zc, rows, D, mode, level_meta, w.zb, w.margin);
+    if (!prep)
+      zprep_kernel<<<static_cast<unsigned>(blocks), 256, 0, s_prep>>>(zc, rows, D, mode, level_meta, w.zb, w.margin,
+                                                                      nullptr, nullptr, 0, nullptr);
     VQ_CUDA(cudaGetLastError());
+    const __nv_bfloat16* zb_c = prep ? reinterpret_cast<const __nv_bfloat16*>(prep->z16) + r0 * D : w.zb;
+    const float* mg_c = prep ? prep->margin + r0 : w.margin;
     if (piped) {
       VQ_CUDA(cudaEventRecord(pipe->prep[b], s_prep));
       VQ_CUDA(cudaStreamWaitEvent(s_tc, pipe->prep[b], 0));
@@ -1000,11 +1033,11 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     TcParams p;
     p.n_rows = rows; p.D = D; p.K = K;
     p.ee_half = bf ? ee_half_bf16 : ee_half;
-    p.margin = w.margin; p.cand = w.cand; p.cnt = w.cnt; p.best = w.best;
+    p.margin = mg_c; p.cand = w.cand; p.cnt = w.cnt; p.best = w.best;
     const bool pair_now = use2 && rows >= static_cast<int64_t>(kNumSMs / 2) * 2 * P2_ROWS;
     int nsub;
     if (pair_now) {
-      if (!make_map(&map_z, w.zb, rows, D, P2_ROWS, !bf)) return VQB200_EDRIVER;
+      if (!make_map(&map_z, zb_c, rows, D, P2_ROWS, !bf)) return VQB200_EDRIVER;
       p.idesc = bf ? kIdescPair : kIdescPairF16;
       p.row_tiles = static_cast<int>((rows + 2 * P2_ROWS - 1) / (2 * P2_ROWS));
       p.ksplit = 1; p.tiles_per_split = (K + P2_BN - 1) / P2_BN;
@@ -1018,7 +1051,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
       else search_tc2_kernel<168><<<2 * pairs, 64 + P2_NEPI * 32, smem2, s_tc>>>(map_z, map_e, p);
       timing_mark_end(s_tc);
     } else {
-    if (!make_map(&map_z, w.zb, rows, D, pl.BM, !bf)) return VQB200_EDRIVER;
+    if (!make_map(&map_z, zb_c, rows, D, pl.BM, !bf)) return VQB200_EDRIVER;
     p.idesc = bf ? kIdesc : kIdescF16;
     p.row_tiles = static_cast<int>((rows + pl.BM - 1) / pl.BM);
     p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, pl.ksplit_max, &p.tiles_per_split);
@@ -1048,11 +1081,11 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
     if (bf)
-      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s_rr>>>(zc, w.zb, E, Eb, rows, D, nsub, rpw, w.margin,
+      rerank_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, s_rr>>>(zc, zb_c, E, Eb, rows, D, nsub, rpw, mg_c,
                                                                           w.cand, w.cnt, w.best, idx_offset, idx_out + r0,
                                                                           w.fb_rows, w.fb_packed, w.counters);
     else
-      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s_rr>>>(zc, w.zb, E, Eb, rows, D, nsub, rpw, w.margin,
+      rerank_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, s_rr>>>(zc, zb_c, E, Eb, rows, D, nsub, rpw, mg_c,
                                                                            w.cand, w.cnt, w.best, idx_offset, idx_out + r0,
                                                                            w.fb_rows, w.fb_packed, w.counters);
     VQ_CUDA(cudaGetLastError());

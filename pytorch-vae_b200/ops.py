@@ -83,6 +83,40 @@ def search(z: torch.Tensor, E: torch.Tensor, cache: CodebookCache, level: int, m
     _count(search_launches(N, K, D, mode))
 
 
+def residual_prep(z, E, idx, cache: CodebookCache, next_level: int, mode: int, residual_out, z16_out, margin_out):
+    """residual_out = z - E[idx] together with the next level's 16-bit operand copy and admission margins."""
+    _need_cuda(z, E, idx, residual_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    check(lib.vqb200_residual_prep(ptr(z), ptr(E), ptr(idx), N, D, E.shape[0], mode,
+                                   cache.level_meta.data_ptr() + next_level * _cabi.LEVEL_META_FLOATS * 4,
+                                   ptr(residual_out), ptr(z16_out), ptr(margin_out), stream_ptr()),
+          "vqb200_residual_prep")
+    _count(1)
+
+
+def search_prepped(z, z16, margin, E, cache: CodebookCache, level: int, mode: int, idx_out):
+    """``search`` for rows whose operand copy and margins ``residual_prep`` already produced (tensor path only)."""
+    _need_cuda(z, E, idx_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    K = cache.K_per
+    s = level * K
+    ws_bytes = lib.vqb200_search_workspace_bytes(N, K, D, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    check(lib.vqb200_search_prepped(ptr(z), ptr(z16), ptr(margin), N, D, E.data_ptr() + s * D * E.element_size(),
+                                    cache.operand_ptr(mode, s), cache.ee_half.data_ptr() + s * 4,
+                                    cache.ee_half.data_ptr() + (cache.K_total + s) * 4,
+                                    cache.level_meta.data_ptr() + level * _cabi.LEVEL_META_FLOATS * 4, K, mode, s,
+                                    ptr(idx_out), ptr(ws), ws_bytes, stream_ptr()), "vqb200_search_prepped")
+    _count(search_launches(N, K, D, mode) - tc_chunks(N, K, D, mode))
+
+
+def tc_chunks(N, K, D, mode) -> int:
+    """Chunks the tensor-path search splits N rows into (one pre-pass launch each)."""
+    return max(1, search_launches(N, K, D, mode) // 5) if lib.vqb200_search_path(N, K, D, mode) else 0
+
+
 def search_launches(N, K, D, mode) -> int:
     return lib.vqb200_search_launches(N, K, D, mode)
 

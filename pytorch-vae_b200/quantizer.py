@@ -335,10 +335,21 @@ class VectorQuantizerEMA(nn.Module):
             # the codebook does not move between levels: the levels only carry the residual forward, and ONE
             # pass at the end forms z_q (level-order sum), z_q_st, the loss partial sum and the histogram from
             # the indices -- z_q is not re-read and re-written on every level
+            # ... and, on the tensor path, the residual update of a level and the pre-pass of the next (16-bit
+            # operand copy + admission margins) are one kernel, one read of the rows
+            on_tc = bool(_cabi.lib.vqb200_search_path(n, self.K_per, D, mode)) and L > 1
+            z16 = torch.empty(n, D, dtype=torch.bfloat16, device=flat.device) if on_tc else None
+            mg = torch.empty(n, dtype=torch.float32, device=flat.device) if on_tc else None
             for level in range(L):
-                ops.search(residual, E, cache, level, mode, idx_levels[level])
+                if on_tc and level > 0:
+                    ops.search_prepped(residual, z16, mg, E, cache, level, mode, idx_levels[level])
+                else:
+                    ops.search(residual, E, cache, level, mode, idx_levels[level])
                 if level < L - 1:
-                    ops.gather(residual, E, idx_levels[level], residual_out=spare[level % 2])
+                    if on_tc:
+                        ops.residual_prep(residual, E, idx_levels[level], cache, level + 1, mode, spare[level % 2], z16, mg)
+                    else:
+                        ops.gather(residual, E, idx_levels[level], residual_out=spare[level % 2])
                     residual = spare[level % 2]
             ops.rvq_finalize(flat, idx_levels[0], lstride, L, E, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
                              hist=hist)
