@@ -30,7 +30,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 6
+#define VQB200_ABI_VERSION 7
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -101,6 +101,18 @@ VQB200_API int vqb200_search_prepped(const float* z, const uint16_t* z16, const 
                           const float* ee_half_bf16, const float* level_meta, int K, int mode,
                           int64_t idx_offset, int64_t* idx_out, void* workspace, size_t workspace_bytes,
                           void* stream);
+
+/* The whole eval-mode residual forward (models/vq_vae.py:226-263 without the EMA branch) in ONE call: per level
+ * search -> residual update fused with the next level's pre-pass, then vqb200_rvq_finalize.  Same results as the
+ * per-level entry points; it exists because at the stage-2 shape (N = 8192) the ~20 separate calls cost more host
+ * time than their kernels cost GPU time.  E, E_lp (operand plane of the mode), ee_half (plane 0), ee_half_bf16
+ * (plane 1) and level_meta are the WHOLE cache arrays ([K_per * L, ...]); idx_out [L * N] level-major global ids. */
+VQB200_API size_t vqb200_rvq_forward_workspace_bytes(int64_t N, int K_per, int D, int L, int mode);
+VQB200_API int vqb200_rvq_forward_launches(int64_t N, int K_per, int D, int L, int mode);
+VQB200_API int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp,
+                       const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K_per, int L,
+                       int mode, int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum,
+                       int32_t* hist, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Measurement hook (bench.py): while enabled, vqb200_search brackets every launch of its dominant kernel (the
  * tcgen05 search kernel; the SIMT kernel on shapes that take the SIMT path) with CUDA events on the launching

@@ -96,6 +96,80 @@ int vqb200_search_launches(int64_t N, int K, int D, int mode) {
   return tc_supported(N, K, D) ? tc_launches(N, K, D) : 1;
 }
 
+// ---- the whole eval-mode residual forward in ONE call (host overhead: one ctypes call instead of ~20) ----
+static size_t rvq_align(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t vqb200_rvq_forward_workspace_bytes(int64_t N, int K_per, int D, int L, int mode) {
+  (void)L;                                               // two residual buffers whatever the number of levels
+  const size_t rows = static_cast<size_t>(N > 0 ? N : 0);
+  return rvq_align(vqb200_search_workspace_bytes(N, K_per, D, mode)) + 2 * rvq_align(rows * D * 4) +
+         rvq_align(rows * D * 2) + rvq_align(rows * 4);
+}
+
+int vqb200_rvq_forward_launches(int64_t N, int K_per, int D, int L, int mode) {
+  if (N <= 0 || L < 1) return 0;
+  const int per_search = vqb200_search_launches(N, K_per, D, mode);
+  const bool tc = tc_supported(N, K_per, D);
+  const int chunks = tc ? per_search / 5 : 0;
+  // level 0: full search; levels > 0 on the tensor path skip their pre-pass; L-1 residual kernels; one finalize
+  return per_search + (L - 1) * (per_search - chunks) + (L - 1) + 1;
+}
+
+int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
+                       const float* ee_half_bf16, const float* level_meta, int K_per, int L, int mode,
+                       int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  VQ_REQUIRE(N >= 0 && K_per > 0 && L >= 1 && L <= 8, VQB200_EINVAL);
+  if (N == 0) return VQB200_OK;
+  VQ_REQUIRE(z && idx_out && E && E_lp && ee_half && ee_half_bf16 && level_meta && workspace, VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(E_lp) && aligned16(zq_out) && aligned16(zq_st_out) &&
+                 (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, VQB200_EALIGN);
+  VQ_REQUIRE(workspace_bytes >= vqb200_rvq_forward_workspace_bytes(N, K_per, D, L, mode), VQB200_EWORKSPACE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  const bool tc = tc_supported(N, K_per, D);
+  const int K_total = K_per * L;
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  void* ws_search = w;
+  const size_t ws_search_bytes = vqb200_search_workspace_bytes(N, K_per, D, mode);
+  w += rvq_align(ws_search_bytes);
+  float* res[2];
+  res[0] = reinterpret_cast<float*>(w); w += rvq_align(static_cast<size_t>(N) * D * 4);
+  res[1] = reinterpret_cast<float*>(w); w += rvq_align(static_cast<size_t>(N) * D * 4);
+  uint16_t* z16 = reinterpret_cast<uint16_t*>(w); w += rvq_align(static_cast<size_t>(N) * D * 2);
+  float* margin = reinterpret_cast<float*>(w);
+
+  const float* residual = z;
+  for (int l = 0; l < L; ++l) {
+    const int64_t s0 = static_cast<int64_t>(l) * K_per;
+    const float* El = E + s0 * D;
+    const uint16_t* Elp = E_lp + s0 * D;
+    const float* meta = level_meta + l * VQB200_LEVEL_META_FLOATS;
+    int64_t* idx_l = idx_out + static_cast<int64_t>(l) * N;
+    int st;
+    if (tc) {
+      PrepArgs prep{z16, margin};
+      st = launch_search_tc(residual, N, D, El, Elp, ee_half + s0, ee_half_bf16 + s0, meta, K_per, mode, s0, idx_l,
+                            ws_search, ws_search_bytes, s, nullptr, l > 0 ? &prep : nullptr);
+    } else {
+      st = launch_search_simt(residual, nullptr, N, D, El, (bf ? ee_half_bf16 : ee_half) + s0, K_per, bf ? 1 : 0, s0,
+                              idx_l, nullptr, s);
+    }
+    if (st != VQB200_OK) return st;
+    if (l + 1 < L) {
+      float* nxt = res[l & 1];
+      st = tc ? launch_residual_prep(residual, E, idx_l, N, D, K_total, mode, meta + VQB200_LEVEL_META_FLOATS, nxt, z16,
+                                     margin, s)
+              : launch_gather(residual, E, idx_l, N, D, K_total, nullptr, 0, nullptr, nxt, nullptr, nullptr, nullptr, s);
+      if (st != VQB200_OK) return st;
+      residual = nxt;
+    }
+  }
+  return launch_rvq_finalize(z, idx_out, N, N, D, L, E, K_total, zq_out, zq_st_out, sqerr_sum, hist, s);
+}
+
 int vqb200_residual_prep(const float* z, const float* E_full, const int64_t* idx, int64_t N, int D, int K_total,
                          int mode, const float* next_level_meta, float* residual_out, uint16_t* z16_out,
                          float* margin_out, void* stream) {

@@ -83,6 +83,22 @@ def search(z: torch.Tensor, E: torch.Tensor, cache: CodebookCache, level: int, m
     _count(search_launches(N, K, D, mode))
 
 
+def rvq_forward(z, E, cache: CodebookCache, mode: int, idx_out, zq_out=None, zq_st_out=None, sqerr_sum=None,
+                hist=None):
+    """Eval-mode residual forward (all levels, finalize included) in one library call."""
+    _need_cuda(z, E, idx_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    K, L = cache.K_per, cache.levels
+    ws_bytes = lib.vqb200_rvq_forward_workspace_bytes(N, K, D, L, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    check(lib.vqb200_rvq_forward(ptr(z), N, D, ptr(E), cache.operand_ptr(mode, 0), cache.ee_half.data_ptr(),
+                                 cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, L, mode,
+                                 ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws),
+                                 ws_bytes, stream_ptr()), "vqb200_rvq_forward")
+    _count(lib.vqb200_rvq_forward_launches(N, K, D, L, mode))
+
+
 def residual_prep(z, E, idx, cache: CodebookCache, next_level: int, mode: int, residual_out, z16_out, margin_out):
     """residual_out = z - E[idx] together with the next level's 16-bit operand copy and admission margins."""
     _need_cuda(z, E, idx, residual_out)

@@ -336,7 +336,13 @@ class VectorQuantizerEMA(nn.Module):
             # pass at the end forms z_q (level-order sum), z_q_st, the loss partial sum and the histogram from
             # the indices -- z_q is not re-read and re-written on every level
             # ... and, on the tensor path, the residual update of a level and the pre-pass of the next (16-bit
-            # operand copy + admission margins) are one kernel, one read of the rows
+            # operand copy + admission margins) are one kernel, one read of the rows.  With the ids packed
+            # [L * n] the whole loop is ONE library call (at N = 8192 the separate calls cost more host time
+            # than their kernels cost GPU time).
+            if lstride == n:
+                ops.rvq_forward(flat, E, cache, mode, idx_levels[0], zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
+                                hist=hist)
+                return
             on_tc = bool(_cabi.lib.vqb200_search_path(n, self.K_per, D, mode)) and L > 1
             z16 = torch.empty(n, D, dtype=torch.bfloat16, device=flat.device) if on_tc else None
             mg = torch.empty(n, dtype=torch.float32, device=flat.device) if on_tc else None
