@@ -30,7 +30,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 7
+#define VQB200_ABI_VERSION 8
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -113,6 +113,19 @@ VQB200_API int vqb200_rvq_forward(const float* z, int64_t N, int D, const float*
                        const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K_per, int L,
                        int mode, int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum,
                        int32_t* hist, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The training-mode residual forward with the EMA update after every level (models/vq_vae.py:226-263 incl. :251,
+ * each rank updating from its own rows, no mask) in ONE call: per level search -> gather (z_q accumulated BEFORE the
+ * codebook moves, residual, histogram) -> scatter-add -> EMA finalize + cache refresh; then the straight-through /
+ * loss pass.  E, E_lp_planes ([2, K_total, D]), ee_half ([2, K_total]), level_meta, ema_* are the whole arrays and
+ * are UPDATED in place.  Same results as the per-level entry points. */
+VQB200_API size_t vqb200_rvq_train_workspace_bytes(int64_t N, int K_per, int D, int L, int mode);
+VQB200_API int vqb200_rvq_train_launches(int64_t N, int K_per, int D, int L, int mode);
+VQB200_API int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes,
+                             float* ee_half, float* level_meta, int K_per, int L, int mode, float decay,
+                             float one_minus_decay, float eps, float* ema_cluster_size, float* ema_embedding,
+                             int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Measurement hook (bench.py): while enabled, vqb200_search brackets every launch of its dominant kernel (the
  * tcgen05 search kernel; the SIMT kernel on shapes that take the SIMT path) with CUDA events on the launching

@@ -170,6 +170,75 @@ int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const u
   return launch_rvq_finalize(z, idx_out, N, N, D, L, E, K_total, zq_out, zq_st_out, sqerr_sum, hist, s);
 }
 
+// ---- the training-mode residual forward with a LOCAL EMA update after every level, in ONE call ----
+size_t vqb200_rvq_train_workspace_bytes(int64_t N, int K_per, int D, int L, int mode) {
+  const size_t rows = static_cast<size_t>(N > 0 ? N : 0), Kt = static_cast<size_t>(K_per) * L;
+  return rvq_align(vqb200_search_workspace_bytes(N, K_per, D, mode)) + 2 * rvq_align(rows * D * 4) +
+         rvq_align((Kt * D + Kt) * 4);
+}
+
+int vqb200_rvq_train_launches(int64_t N, int K_per, int D, int L, int mode) {
+  if (N <= 0 || L < 1) return 0;
+  return L * (vqb200_search_launches(N, K_per, D, mode) + 3) + 1;      // + gather, scatter-add, EMA finalize; st_loss
+}
+
+int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                             float* level_meta, int K_per, int L, int mode, float decay, float one_minus_decay,
+                             float eps, float* ema_cluster_size, float* ema_embedding, int64_t* idx_out,
+                             float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  VQ_REQUIRE(N >= 0 && K_per > 0 && L >= 1 && L <= VQB200_MAX_LEVELS, VQB200_EINVAL);
+  if (N == 0) return VQB200_OK;
+  VQ_REQUIRE(z && idx_out && E && E_lp_planes && ee_half && level_meta && ema_cluster_size && ema_embedding &&
+                 zq_out && workspace, VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(E_lp_planes) && aligned16(zq_out) && aligned16(zq_st_out) &&
+                 aligned16(ema_embedding) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, VQB200_EALIGN);
+  VQ_REQUIRE(workspace_bytes >= vqb200_rvq_train_workspace_bytes(N, K_per, D, L, mode), VQB200_EWORKSPACE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  const bool tc = tc_supported(N, K_per, D);
+  const int K_total = K_per * L;
+  const uint16_t* plane = E_lp_planes + (bf ? 0 : static_cast<size_t>(K_total) * D);   // operand plane of the mode
+  const float* ee_bf = ee_half + K_total;
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  void* ws_search = w;
+  const size_t ws_search_bytes = vqb200_search_workspace_bytes(N, K_per, D, mode);
+  w += rvq_align(ws_search_bytes);
+  float* res[2];
+  res[0] = reinterpret_cast<float*>(w); w += rvq_align(static_cast<size_t>(N) * D * 4);
+  res[1] = reinterpret_cast<float*>(w); w += rvq_align(static_cast<size_t>(N) * D * 4);
+  float* seg_sum = reinterpret_cast<float*>(w);
+  float* seg_cnt = seg_sum + static_cast<size_t>(K_total) * D;
+  const size_t seg_bytes = (static_cast<size_t>(K_total) * D + K_total) * 4;
+
+  const float* residual = z;
+  for (int l = 0; l < L; ++l) {
+    const int64_t s0 = static_cast<int64_t>(l) * K_per;
+    int64_t* idx_l = idx_out + static_cast<int64_t>(l) * N;
+    const float* meta = level_meta + l * VQB200_LEVEL_META_FLOATS;
+    int st = tc ? launch_search_tc(residual, N, D, E + s0 * D, plane + s0 * D, ee_half + s0, ee_bf + s0, meta, K_per, mode,
+                                   s0, idx_l, ws_search, ws_search_bytes, s)
+                : launch_search_simt(residual, nullptr, N, D, E + s0 * D, (bf ? ee_bf : ee_half) + s0, K_per, bf ? 1 : 0, s0,
+                                     idx_l, nullptr, s);
+    if (st != VQB200_OK) return st;
+    float* nxt = l + 1 < L ? res[l & 1] : nullptr;
+    // z_q is gathered BEFORE this level's EMA update moves the codebook (models/vq_vae.py:248 -> :251)
+    st = launch_gather(residual, E, idx_l, N, D, K_total, zq_out, l > 0, nullptr, nxt, nullptr, hist, nullptr, s);
+    if (st != VQB200_OK) return st;
+    cudaError_t e = cudaMemsetAsync(seg_sum, 0, seg_bytes, s);
+    if (e != cudaSuccess) return status_of(e);
+    st = launch_scatter_add(residual, idx_l, nullptr, N, D, K_total, seg_sum, seg_cnt, s);
+    if (st != VQB200_OK) return st;
+    st = launch_codebook_refresh(1, seg_sum, seg_cnt, decay, one_minus_decay, eps, K_total, D, K_per, ema_cluster_size,
+                                 ema_embedding, E, E_lp_planes, ee_half, level_meta, s);
+    if (st != VQB200_OK) return st;
+    if (nxt) residual = nxt;
+  }
+  return launch_st_loss(z, zq_out, N * D, zq_st_out, sqerr_sum, s);
+}
+
 int vqb200_residual_prep(const float* z, const float* E_full, const int64_t* idx, int64_t N, int D, int K_total,
                          int mode, const float* next_level_meta, float* residual_out, uint16_t* z16_out,
                          float* margin_out, void* stream) {

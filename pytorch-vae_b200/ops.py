@@ -99,6 +99,23 @@ def rvq_forward(z, E, cache: CodebookCache, mode: int, idx_out, zq_out=None, zq_
     _count(lib.vqb200_rvq_forward_launches(N, K, D, L, mode))
 
 
+def rvq_train_forward(z, E, cache: CodebookCache, mode, decay, eps, ema_cluster_size, ema_embedding, idx_out, zq_out,
+                      zq_st_out=None, sqerr_sum=None, hist=None):
+    """Training-mode residual forward with a local EMA update after every level, in one library call."""
+    _need_cuda(z, E, idx_out, zq_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    K, L = cache.K_per, cache.levels
+    ws_bytes = lib.vqb200_rvq_train_workspace_bytes(N, K, D, L, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    check(lib.vqb200_rvq_train_forward(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), ptr(cache.ee_half),
+                                       ptr(cache.level_meta), K, L, mode, float(decay), float(1 - decay), float(eps),
+                                       ptr(ema_cluster_size), ptr(ema_embedding), ptr(idx_out), ptr(zq_out),
+                                       ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws), ws_bytes, stream_ptr()),
+          "vqb200_rvq_train_forward")
+    _count(lib.vqb200_rvq_train_launches(N, K, D, L, mode))
+
+
 def residual_prep(z, E, idx, cache: CodebookCache, next_level: int, mode: int, residual_out, z16_out, margin_out):
     """residual_out = z - E[idx] together with the next level's 16-bit operand copy and admission margins."""
     _need_cuda(z, E, idx, residual_out)

@@ -360,6 +360,14 @@ class VectorQuantizerEMA(nn.Module):
             ops.rvq_finalize(flat, idx_levels[0], lstride, L, E, zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
                              hist=hist)
             return
+        if ema_ok and valid_u8 is None and lstride == n and \
+                not (self.ema_sync == "allreduce" and sharding.dist_ready()):
+            # training, every rank updating from its own rows: all levels, their EMA updates and the
+            # straight-through / loss pass in ONE library call
+            ops.rvq_train_forward(flat, E, cache, mode, self.decay, self.eps, self.ema_cluster_size,
+                                  self.ema_embedding, idx_levels[0], z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist)
+            cache.key = (self.embedding.data_ptr(), self.embedding._version)
+            return
         for level in range(L):
             idx_l = idx_levels[level]
             if level > 0 and do_ema:
