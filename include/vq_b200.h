@@ -30,7 +30,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 8
+#define VQB200_ABI_VERSION 9
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -211,6 +211,18 @@ VQB200_API int vqb200_kmeans_finalize(const float* seg_sum, const float* seg_cnt
 VQB200_API int vqb200_rvq_finalize(const float* z, const int64_t* idx_level_major, int64_t level_stride,
                         int64_t N, int D, int L, const float* E, int K_total, float* zq_out, float* zq_st_out, double* sqerr_sum,
                         int32_t* hist, void* stream);
+
+/* Usage-entropy regulariser (models/vq_vae.py:1298-1309): the code-usage distribution
+ *   p_code[k] = (1/N) sum_n softmax_k(z_n . e_k)
+ * without the [N, K] logits / probabilities.  vqb200_usage_probs ADDS sum_n P_nk to p_sum [K] (caller zeroes; divide
+ * by N) and stores the per-row (max logit, 1 / sum exp) in row_stats [N, 2] for the backward.
+ * vqb200_usage_probs_backward: grad_z_n = scale * sum_j P_nj (g_j - sum_k P_nk g_k) e_j with g = dLoss/dp_code
+ * (pass scale = 1 / N).  D <= 512. */
+VQB200_API int vqb200_usage_probs(const float* z, int64_t N, int D, const float* E, int K, float* p_sum,
+                       float* row_stats, void* stream);
+VQB200_API int vqb200_usage_probs_backward(const float* z, int64_t N, int D, const float* E, int K,
+                                const float* row_stats, const float* grad_p, float scale, float* grad_z_out,
+                                void* stream);
 
 /* Soft assignment of the soft-VQ training path (models/vq_vae.py:838-843, single-level codebooks):
  *   z_soft[n] = sum_k softmax_k(-|z_n - e_k|^2 / max(1e-8, tau)) e_k

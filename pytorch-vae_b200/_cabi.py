@@ -16,7 +16,7 @@ MODE_FP32_EXACT = 0
 MODE_BF16_INPUT = 1
 MAX_LEVELS = 32
 LEVEL_META_FLOATS = 8
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _p = C.c_void_p
 _i = C.c_int
@@ -56,6 +56,8 @@ SIGNATURES = {
     "vqb200_ema_finalize": (_i, [_p, _p, _f, _f, _f, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "vqb200_kmeans_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "vqb200_rvq_finalize": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _i, _p, _p, _p, _p, _p]),
+    "vqb200_usage_probs": (_i, [_p, _i64, _i, _p, _i, _p, _p, _p]),
+    "vqb200_usage_probs_backward": (_i, [_p, _i64, _i, _p, _i, _p, _p, _f, _p, _p]),
     "vqb200_soft_assign": (_i, [_p, _i64, _i, _p, _i, _f, _p, _p]),
     "vqb200_commit_backward": (_i, [_p, _p, _p, _p, _i64, _f, _p, _p]),
     "vqb200_relayout_indices": (_i, [_p, _i, _i64, _i64, _p, _i, _p]),

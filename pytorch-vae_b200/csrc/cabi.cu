@@ -443,6 +443,26 @@ int vqb200_rvq_finalize(const float* z, const int64_t* idx_level_major, int64_t 
                              static_cast<cudaStream_t>(stream));
 }
 
+int vqb200_usage_probs(const float* z, int64_t N, int D, const float* E, int K, float* p_sum, float* row_stats,
+                       void* stream) {
+  VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && E && p_sum && row_stats), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && (reinterpret_cast<uintptr_t>(row_stats) & 7u) == 0, VQB200_EALIGN);
+  return launch_usage_probs(z, N, D, E, K, p_sum, row_stats, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_usage_probs_backward(const float* z, int64_t N, int D, const float* E, int K, const float* row_stats,
+                                const float* grad_p, float scale, float* grad_z_out, void* stream) {
+  VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && E && row_stats && grad_p && grad_z_out), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(grad_z_out) && (reinterpret_cast<uintptr_t>(row_stats) & 7u) == 0,
+             VQB200_EALIGN);
+  return launch_usage_probs_backward(z, N, D, E, K, row_stats, grad_p, scale, grad_z_out,
+                                     static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_soft_assign(const float* z, int64_t N, int D, const float* E, int K, float tau, float* z_soft_out,
                        void* stream) {
   VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);

@@ -156,6 +156,10 @@ int launch_relayout(const int64_t* in, int Q, int64_t B, int64_t M, void* out, i
 int launch_rvq_finalize(const float* z, const int64_t* idx, int64_t lstride, int64_t N, int D, int L, const float* E,
                         int K_total,
                         float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist, cudaStream_t s);
+int launch_usage_probs(const float* z, int64_t N, int D, const float* E, int K, float* p_sum, float* row_stats,
+                       cudaStream_t s);
+int launch_usage_probs_backward(const float* z, int64_t N, int D, const float* E, int K, const float* row_stats,
+                                const float* g, float scale, float* grad_z, cudaStream_t s);
 int launch_soft_assign(const float* z, int64_t N, int D, const float* E, int K, float tau, float* z_soft,
                        cudaStream_t s);
 int launch_indices_to_latent(const void* idx, int bytes, int64_t n_tok, int Q, const float* E, int K_total, int D,

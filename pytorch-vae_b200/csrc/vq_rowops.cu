@@ -752,4 +752,136 @@ int launch_soft_assign(const float* z, int64_t N, int D, const float* E, int K, 
   return status_of(cudaGetLastError());
 }
 
+// --------------------------------------------------------------------------------------------
+// usage-entropy regulariser (models/vq_vae.py:1298-1309): p_code = mean_n softmax_k(z_n . e_k).
+// Forward: one warp per row, two sweeps over the codes (online max / sum, then the probabilities, added to
+// p_sum[k] with one atomic per (row, code)); the per-row (max, sum) is kept for the backward.
+// Backward: given g_k = dLoss/dp_code[k],  dLoss/dlogit_nj = P_nj (g_j - sum_k P_nk g_k) / N  and
+// dLoss/dz_n = sum_j dLoss/dlogit_nj e_j: two more sweeps per row.  The reference materialises [N, K] logits
+// and probabilities and runs two GEMMs.  SIMT fp32: a training-time, small-N path like soft_assign.
+// --------------------------------------------------------------------------------------------
+template <typename F>
+__device__ __forceinline__ void usage_sweep(const float4 (&zr)[SOFT_SLICES], const float4* __restrict__ E, int K, int D4,
+                                            int lane, F&& f) {
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    float4 ev[4][SOFT_SLICES];
+    float part[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      part[u] = 0.f;
+      const bool live = k0 + u < K;
+#pragma unroll
+      for (int j = 0; j < SOFT_SLICES; ++j) {
+        const int c = lane + 32 * j;
+        ev[u][j] = (live && c < D4) ? __ldg(E + static_cast<int64_t>(k0 + u) * D4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        part[u] += zr[j].x * ev[u][j].x + zr[j].y * ev[u][j].y + zr[j].z * ev[u][j].z + zr[j].w * ev[u][j].w;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) part[u] += __shfl_xor_sync(0xffffffffu, part[u], o);
+    }
+    f(k0, part, ev);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+usage_probs_kernel(const float4* __restrict__ z, const float4* __restrict__ E, int64_t N, int K, int D4,
+                   float* __restrict__ p_sum, float2* __restrict__ row_stats) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const float kNegInf = __int_as_float(0xff800000);
+  for (int64_t row = warp0; row < N; row += nwarps) {
+    float4 zr[SOFT_SLICES];
+#pragma unroll
+    for (int j = 0; j < SOFT_SLICES; ++j) {
+      const int c = lane + 32 * j;
+      zr[j] = c < D4 ? z[row * D4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float m = kNegInf, ssum = 0.f;
+    usage_sweep(zr, E, K, D4, lane, [&](int k0, const float (&lg)[4], const float4 (&)[4][SOFT_SLICES]) {
+      float mx = m;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (k0 + u < K) mx = fmaxf(mx, lg[u]);
+      ssum *= expf(m - mx);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (k0 + u < K) ssum += expf(lg[u] - mx);
+      m = mx;
+    });
+    const float inv = 1.f / ssum;
+    usage_sweep(zr, E, K, D4, lane, [&](int k0, const float (&lg)[4], const float4 (&)[4][SOFT_SLICES]) {
+      if (lane < 4 && k0 + lane < K) atomicAdd(p_sum + k0 + lane, expf(lg[lane] - m) * inv);
+    });
+    if (lane == 0) row_stats[row] = make_float2(m, inv);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+usage_probs_backward_kernel(const float4* __restrict__ z, const float4* __restrict__ E, int64_t N, int K, int D4,
+                            const float2* __restrict__ row_stats, const float* __restrict__ g, float scale,
+                            float4* __restrict__ grad_z) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < N; row += nwarps) {
+    float4 zr[SOFT_SLICES], acc[SOFT_SLICES];
+#pragma unroll
+    for (int j = 0; j < SOFT_SLICES; ++j) {
+      const int c = lane + 32 * j;
+      zr[j] = c < D4 ? z[row * D4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float2 st = row_stats[row];
+    float t = 0.f;                                        // sum_k P_nk g_k
+    usage_sweep(zr, E, K, D4, lane, [&](int k0, const float (&lg)[4], const float4 (&)[4][SOFT_SLICES]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (k0 + u < K) t = fmaf(expf(lg[u] - st.x) * st.y, g[k0 + u], t);
+    });
+    usage_sweep(zr, E, K, D4, lane, [&](int k0, const float (&lg)[4], const float4 (&ev)[4][SOFT_SLICES]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k0 + u >= K) continue;
+        const float w = expf(lg[u] - st.x) * st.y * (g[k0 + u] - t);
+#pragma unroll
+        for (int j = 0; j < SOFT_SLICES; ++j) {
+          acc[j].x = fmaf(w, ev[u][j].x, acc[j].x); acc[j].y = fmaf(w, ev[u][j].y, acc[j].y);
+          acc[j].z = fmaf(w, ev[u][j].z, acc[j].z); acc[j].w = fmaf(w, ev[u][j].w, acc[j].w);
+        }
+      }
+    });
+#pragma unroll
+    for (int j = 0; j < SOFT_SLICES; ++j) {
+      const int c = lane + 32 * j;
+      if (c < D4)
+        grad_z[row * D4 + c] = make_float4(acc[j].x * scale, acc[j].y * scale, acc[j].z * scale, acc[j].w * scale);
+    }
+  }
+}
+
+int launch_usage_probs(const float* z, int64_t N, int D, const float* E, int K, float* p_sum, float* row_stats,
+                       cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  if (D > 128 * SOFT_SLICES) return VQB200_ESHAPE;
+  int64_t blocks = (N + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  usage_probs_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(reinterpret_cast<const float4*>(z),
+                                                                  reinterpret_cast<const float4*>(E), N, K, D >> 2, p_sum,
+                                                                  reinterpret_cast<float2*>(row_stats));
+  return status_of(cudaGetLastError());
+}
+
+int launch_usage_probs_backward(const float* z, int64_t N, int D, const float* E, int K, const float* row_stats,
+                                const float* g, float scale, float* grad_z, cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  if (D > 128 * SOFT_SLICES) return VQB200_ESHAPE;
+  int64_t blocks = (N + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  usage_probs_backward_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(E), N, K, D >> 2,
+      reinterpret_cast<const float2*>(row_stats), g, scale, reinterpret_cast<float4*>(grad_z));
+  return status_of(cudaGetLastError());
+}
+
 }  // namespace vqb

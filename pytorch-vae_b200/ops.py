@@ -257,6 +257,29 @@ def rvq_finalize(z, idx_level0, level_stride, L, E, zq_out=None, zq_st_out=None,
     _count(1)
 
 
+def usage_probs(z, E):
+    """(p_code [K], row_stats [N, 2]): p_code = mean_n softmax_k(z_n . e_k) (models/vq_vae.py:1305-1307)."""
+    _need_cuda(z, E)
+    _f32c(z, "z")
+    _f32c(E, "embedding")
+    N, D = z.shape
+    p_sum = torch.zeros(E.shape[0], dtype=torch.float32, device=z.device)
+    row_stats = torch.empty(N, 2, dtype=torch.float32, device=z.device)
+    check(lib.vqb200_usage_probs(ptr(z), N, D, ptr(E), E.shape[0], ptr(p_sum), ptr(row_stats), stream_ptr()),
+          "vqb200_usage_probs")
+    _count(1)
+    return p_sum / max(N, 1), row_stats
+
+
+def usage_probs_backward(z, E, row_stats, grad_p):
+    N, D = z.shape
+    out = torch.empty_like(z)
+    check(lib.vqb200_usage_probs_backward(ptr(z), N, D, ptr(E), E.shape[0], ptr(row_stats), ptr(grad_p),
+                                          1.0 / max(N, 1), ptr(out), stream_ptr()), "vqb200_usage_probs_backward")
+    _count(1)
+    return out
+
+
 def soft_assign(z, E, tau: float, out=None):
     """z_soft = softmax(-|z - e|^2 / tau) @ E (models/vq_vae.py:838-843), online softmax, nothing materialised."""
     _need_cuda(z, E)

@@ -264,6 +264,14 @@ class VectorQuantizerEMA(nn.Module):
         ops.stats_finalize(hist, float(N), sqerr, 1.0 / max(N * D, 1), spare[: self.K], spare[self.K:], stats3)
         return z_soft.view(B, M, D), z_q.view(B, M, D), idx.view(B, M), stats3[:2]
 
+    def usage_code_probs(self, z_e: Tensor) -> Tensor:
+        """``softmax(z_e @ E^T).mean(0)`` [K_total] -- the soft code-usage distribution of the usage-entropy
+        regulariser (models/vq_vae.py:1298-1309), differentiable w.r.t. ``z_e`` (the codebook is detached there);
+        no [N, K] matrix is formed in either direction."""
+        if not z_e.is_cuda or z_e.dtype != torch.float32 or z_e.shape[-1] != self.D:
+            raise RuntimeError("usage_code_probs needs float32 CUDA latents whose last dim matches the codebook")
+        return _UsageProbsFn.apply(z_e.reshape(-1, self.D), self.embedding)
+
     def commitment_loss(self, z_q: Tensor, z_e: Tensor) -> Tensor:
         """``F.mse_loss(z_q.detach(), z_e)`` (models/vq_vae.py:1293).  When called with the pair the
         last forward produced, returns the value the gather pass already accumulated (its backward is
@@ -508,6 +516,23 @@ class VectorQuantizerEMA(nn.Module):
             sqerr, hist = sharding.allreduce_stats(sqerr, n_elems, hist)    # sqerr is now the global mean
             inv = 1.0
         ops.stats_finalize(hist, count_add, sqerr, inv, self._ep_usage, self._ep_cnt, stats3)
+
+
+class _UsageProbsFn(torch.autograd.Function):
+    """p_code = softmax(z @ E^T).mean(0) with the codebook detached (models/vq_vae.py:1303-1307)."""
+
+    @staticmethod
+    def forward(ctx, z_flat, E):
+        z = z_flat.detach().contiguous()
+        Ed = E.detach().contiguous()
+        p_code, row_stats = ops.usage_probs(z, Ed)
+        ctx.save_for_backward(z, Ed, row_stats)
+        return p_code
+
+    @staticmethod
+    def backward(ctx, g):
+        z, Ed, row_stats = ctx.saved_tensors
+        return ops.usage_probs_backward(z, Ed, row_stats, g.to(torch.float32).contiguous()), None
 
 
 class _CommitFn(torch.autograd.Function):

@@ -277,9 +277,8 @@ class VQVAE(nn.Module):
             if float(kwargs.get(name, 0.0)) != 0.0:
                 raise NotImplementedError(f"{name} != 0: the geometry regularisers are outside the hot path; train with "
                                           "the reference VQVAE and pytorch_vae_b200.install()")
-        if self.xyz_align_alpha != 0.0 or self.usage_entropy_lambda > 0.0:
-            raise NotImplementedError("Kabsch-aligned xyz loss / usage-entropy regulariser: use the reference VQVAE "
-                                      "with pytorch_vae_b200.install()")
+        if self.xyz_align_alpha != 0.0:
+            raise NotImplementedError("Kabsch-aligned xyz loss: use the reference VQVAE with pytorch_vae_b200.install()")
         ss_weight, rmsd_weight = float(kwargs.get("ss_weight", 1.0)), float(kwargs.get("rmsd_weight", 1.0))
         dev = recons.device
         zero = torch.tensor(0.0, device=dev)
@@ -326,7 +325,13 @@ class VQVAE(nn.Module):
         else:
             vq_loss = zero
 
-        total = rmsd_weight * loss_xyz + ss_weight * loss_ss + vq_loss + self.ss_tv_lambda * ss_tv
+        usage_reg = zero                                     # models/vq_vae.py:1298-1309
+        if self.usage_entropy_lambda > 0.0 and ze_raw.numel() > 0 and self.quantizer is not None:
+            p_code = self.quantizer.usage_code_probs(ze_raw)
+            entropy = -(p_code * p_code.clamp_min(1e-12).log()).sum()
+            usage_reg = -self.usage_entropy_lambda * entropy
+
+        total = rmsd_weight * loss_xyz + ss_weight * loss_ss + vq_loss + self.ss_tv_lambda * ss_tv + usage_reg
         with torch.no_grad():
             hit = logits.argmax(-1) == labels
             acc = (hit & mask).sum().float() / mask.sum().float().clamp_min(1.0) if mask is not None else hit.float().mean()
@@ -335,7 +340,7 @@ class VQVAE(nn.Module):
                 "XYZ_MSE_Aligned": det(loss_xyz), "Reconstruction_Loss_SS": det(loss_ss), "SS_Accuracy": det(acc),
                 "VQ_Loss": det(vq_loss), "Geom_BondLength_Loss": zero, "Geom_BondAngle_Loss": zero,
                 "Geom_Direction_Loss": zero, "Geom_Dihedral_Loss": zero, "Geom_Loss": zero, "SS_TV": det(ss_tv),
-                "Usage_Reg": zero, "XYZ_TV2": zero, "VQ_Perplexity": det(ppl), "VQ_DeadRatio": det(dead),
+                "Usage_Reg": det(usage_reg), "XYZ_TV2": zero, "VQ_Perplexity": det(ppl), "VQ_DeadRatio": det(dead),
                 "RMSD_Raw": rmsd, "RMSD_Aligned": rmsd}
 
     @torch.no_grad()

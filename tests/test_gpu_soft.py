@@ -71,3 +71,45 @@ def test_soft_assign_edges(vq):
         q.soft_forward(torch.randn(2, 4, 32, device=dev), 1.0)
     with pytest.raises(Exception):
         vq.ops.soft_assign(torch.randn(4, 1024, device=dev), torch.randn(8, 1024, device=dev), 1.0)   # D > 512
+
+
+USAGE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "usage_golden.npz")
+
+
+@pytest.mark.parametrize("tag", ["single", "sharp", "rvq"])
+def test_usage_entropy_matches_live_reference(vq, tag):
+    """The usage-entropy regulariser (forward value and gradient to z_e) against the reference's own
+    loss_function (tests/golden/usage_golden.npz) and the float64 oracle."""
+    dev = torch.device("cuda:0")
+    g = np.load(USAGE)
+    E, z, lam = g[f"{tag}/E"], g[f"{tag}/z_e"], float(g[f"{tag}/lambda"])
+    q = vq.VectorQuantizerEMA(E.shape[0], E.shape[1], print_init=False).to(dev)      # K_total codes, one flat table
+    q.embedding.copy_(torch.from_numpy(E))
+    ze = torch.from_numpy(z).to(dev).requires_grad_(True)
+    p_code = q.usage_code_probs(ze)
+    entropy = -(p_code * p_code.clamp_min(1e-12).log()).sum()                         # the reference's own expression
+    reg = -lam * entropy
+    reg.backward()
+    np.testing.assert_allclose(float(reg.detach()), float(g[f"{tag}/usage_reg"]), rtol=1e-5)
+    scale = np.abs(g[f"{tag}/grad"]).max()
+    np.testing.assert_allclose(ze.grad.cpu().numpy(), g[f"{tag}/grad"], rtol=2e-3, atol=2e-4 * scale)
+    oreg, op, ograd = O.usage_entropy(z, E, lam)
+    np.testing.assert_allclose(p_code.detach().cpu().numpy(), op, rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(ze.grad.cpu().numpy(), ograd, rtol=1e-3, atol=1e-4 * scale)
+
+
+@pytest.mark.parametrize("K,D,N", [(512, 64, 2048), (100, 48, 333), (1024, 512, 256), (37, 20, 65)])
+def test_usage_probs_matches_oracle(vq, K, D, N):
+    dev = torch.device("cuda:0")
+    rs = np.random.RandomState(K + N)
+    E = (rs.standard_normal((K, D)) * (2.0 / np.sqrt(D))).astype(np.float32)
+    z = (rs.standard_normal((N, D)) * 1.5).astype(np.float32)
+    zt = torch.from_numpy(z).to(dev).requires_grad_(True)
+    q = vq.VectorQuantizerEMA(K, D, print_init=False).to(dev)
+    q.embedding.copy_(torch.from_numpy(E))
+    p = q.usage_code_probs(zt.view(1, N, D))
+    (-(p * p.clamp_min(1e-12).log()).sum() * -0.3).backward()
+    oreg, op, ograd = O.usage_entropy(z, E, 0.3)
+    np.testing.assert_allclose(p.detach().cpu().numpy(), op, rtol=2e-5, atol=1e-8)
+    scale = np.abs(ograd).max()
+    np.testing.assert_allclose(zt.grad.cpu().numpy(), ograd, rtol=1e-3, atol=1e-4 * scale)

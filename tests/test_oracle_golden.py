@@ -216,3 +216,15 @@ def test_oracle_soft_vq_matches_live_reference():
         assert np.array_equal(idx, g[f"step{s}/idx"])
         assert np.array_equal(hard, g[f"step{s}/zq_hard"])
         np.testing.assert_allclose(out, g[f"step{s}/z_dec"], rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_usage_entropy_matches_live_reference():
+    """tests/golden/usage_golden.npz: Usage_Reg and d(Usage_Reg)/d(z_e) out of the reference's own loss_function."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "usage_golden.npz"))
+    for tag in ("single", "sharp", "rvq"):
+        reg, p, grad = O.usage_entropy(g[f"{tag}/z_e"], g[f"{tag}/E"], float(g[f"{tag}/lambda"]))
+        np.testing.assert_allclose(reg, float(g[f"{tag}/usage_reg"]), rtol=1e-5)
+        np.testing.assert_allclose(p.sum(), 1.0, rtol=1e-5)
+        scale = np.abs(g[f"{tag}/grad"]).max()
+        np.testing.assert_allclose(grad, g[f"{tag}/grad"], rtol=2e-3, atol=2e-4 * scale)
