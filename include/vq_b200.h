@@ -30,7 +30,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 9
+#define VQB200_ABI_VERSION 10
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -182,6 +182,14 @@ VQB200_API int vqb200_st_loss(const float* z, const float* zq, int64_t n_elems, 
 VQB200_API int vqb200_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
                           double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out,
                           void* stream);
+
+/* Multi-GPU statistics: vqb200_stats_pack writes this rank's float64 pack [sum sq err | element count | histogram]
+ * (K_total + 2 doubles: counts stay exact to 2^53), the caller all-reduces it (SUM) and
+ * vqb200_stats_finalize_packed is vqb200_stats_finalize on the reduced pack (stats_out[2] = global mean sq err). */
+VQB200_API int vqb200_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems,
+                      double* packed_out, void* stream);
+VQB200_API int vqb200_stats_finalize_packed(const double* packed, int K_total, float count_add, float* ep_usage,
+                                 float* ep_cnt, float* stats_out, void* stream);
 
 /* EMA codebook update, part 1: segment sums.  Replaces the dense one-hot GEMM of
  * models/vq_vae.py:81-83.  seg_sum [K_total, D] and seg_cnt [K_total] are zeroed by the caller. */

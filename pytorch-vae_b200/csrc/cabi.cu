@@ -373,6 +373,19 @@ int vqb200_stats_finalize(const int32_t* hist, int K_total, float count_add, con
                                static_cast<cudaStream_t>(stream));
 }
 
+int vqb200_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, double* packed_out,
+                      void* stream) {
+  VQ_REQUIRE(hist && packed_out && K_total > 0, VQB200_EINVAL);
+  return launch_stats_pack(hist, K_total, sqerr_sum, n_elems, packed_out, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_stats_finalize_packed(const double* packed, int K_total, float count_add, float* ep_usage, float* ep_cnt,
+                                 float* stats_out, void* stream) {
+  VQ_REQUIRE(packed && stats_out && K_total > 0, VQB200_EINVAL);
+  return launch_stats_finalize_packed(packed, K_total, count_add, ep_usage, ep_cnt, stats_out,
+                                      static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
                        float* seg_sum, float* seg_cnt, void* stream) {
   VQ_REQUIRE(N >= 0 && K_total > 0 && seg_sum && seg_cnt, VQB200_EINVAL);

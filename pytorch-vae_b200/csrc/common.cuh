@@ -148,6 +148,10 @@ int launch_gather(const float* z, const float* E, const int64_t* idx, int64_t N,
 int launch_st_loss(const float* z, const float* zq, int64_t n_elems, float* st, double* sqerr_sum, cudaStream_t s);
 int launch_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
                           double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out, cudaStream_t s);
+int launch_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, double* out,
+                      cudaStream_t s);
+int launch_stats_finalize_packed(const double* packed, int K_total, float count_add, float* ep_usage, float* ep_cnt,
+                                 float* stats_out, cudaStream_t s);
 int launch_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
                        float* seg_sum, float* seg_cnt, cudaStream_t s);
 int launch_commit_backward(const float* g, const float* gc, const float* z, const float* zq, int64_t n_elems,

@@ -416,15 +416,21 @@ int launch_rvq_finalize(const float* z, const int64_t* idx, int64_t lstride, int
 // --------------------------------------------------------------------------------------------
 // statistics: one CTA over the K_total-bin histogram
 // --------------------------------------------------------------------------------------------
+// PACKED: the statistics come from the all-reduced float64 pack [sum sq err | element count | histogram]
+// (vqb200_stats_pack) instead of this rank's int32 histogram and double sum.
+template <bool PACKED>
 __global__ void __launch_bounds__(1024)
-stats_finalize_kernel(const int32_t* __restrict__ hist, int K_total, float count_add,
-                      const double* __restrict__ sqerr_sum, double inv_elems, float* ep_usage, float* ep_cnt,
-                      float* __restrict__ stats_out) {
+stats_finalize_kernel(const int32_t* __restrict__ hist_i, const double* __restrict__ packed, int K_total,
+                      float count_add, const double* __restrict__ sqerr_sum, double inv_elems, float* ep_usage,
+                      float* ep_cnt, float* __restrict__ stats_out) {
   __shared__ double red[32];
   __shared__ double s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto hist = [&](int k) -> long long {
+    return PACKED ? __double2ll_rn(packed[2 + k]) : static_cast<long long>(hist_i[k]);
+  };
   double t = 0.0;
-  for (int k = tid; k < K_total; k += blockDim.x) t += static_cast<double>(hist[k]);
+  for (int k = tid; k < K_total; k += blockDim.x) t += static_cast<double>(hist(k));
   t = warp_sum(t);
   if (lane == 0) red[warp] = t;
   __syncthreads();
@@ -437,7 +443,7 @@ stats_finalize_kernel(const int32_t* __restrict__ hist, int K_total, float count
   const double total = s_total;
   double h = 0.0, dead = 0.0;
   for (int k = tid; k < K_total; k += blockDim.x) {
-    const int c = hist[k];
+    const long long c = hist(k);
     if (c > 0) { const double p = static_cast<double>(c) / total; h += p * log(p); }
     else dead += 1.0;
     if (ep_usage) ep_usage[k] += static_cast<float>(c);
@@ -457,7 +463,8 @@ stats_finalize_kernel(const int32_t* __restrict__ hist, int K_total, float count
       const bool any = b < static_cast<double>(K_total);
       stats_out[0] = any ? static_cast<float>(exp(-a)) : 0.f;
       stats_out[1] = static_cast<float>(b / static_cast<double>(K_total));
-      stats_out[2] = sqerr_sum ? static_cast<float>(*sqerr_sum * inv_elems) : 0.f;
+      if (PACKED) stats_out[2] = static_cast<float>(packed[0] / (packed[1] < 1.0 ? 1.0 : packed[1]));
+      else stats_out[2] = sqerr_sum ? static_cast<float>(*sqerr_sum * inv_elems) : 0.f;
       if (ep_cnt) ep_cnt[0] += count_add;
     }
   }
@@ -465,8 +472,29 @@ stats_finalize_kernel(const int32_t* __restrict__ hist, int K_total, float count
 
 int launch_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
                           double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out, cudaStream_t s) {
-  stats_finalize_kernel<<<1, 1024, 0, s>>>(hist, K_total, count_add, sqerr_sum, inv_elems, ep_usage, ep_cnt,
-                                           stats_out);
+  stats_finalize_kernel<false><<<1, 1024, 0, s>>>(hist, nullptr, K_total, count_add, sqerr_sum, inv_elems, ep_usage,
+                                                  ep_cnt, stats_out);
+  return status_of(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256)
+stats_pack_kernel(const int32_t* __restrict__ hist, int K_total, const double* __restrict__ sqerr_sum, double n_elems,
+                  double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { out[0] = sqerr_sum ? *sqerr_sum : 0.0; out[1] = n_elems; }
+  if (i < K_total) out[2 + i] = static_cast<double>(hist[i]);
+}
+
+int launch_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, double* out,
+                      cudaStream_t s) {
+  stats_pack_kernel<<<(K_total + 255) / 256, 256, 0, s>>>(hist, K_total, sqerr_sum, n_elems, out);
+  return status_of(cudaGetLastError());
+}
+
+int launch_stats_finalize_packed(const double* packed, int K_total, float count_add, float* ep_usage, float* ep_cnt,
+                                 float* stats_out, cudaStream_t s) {
+  stats_finalize_kernel<true><<<1, 1024, 0, s>>>(nullptr, packed, K_total, count_add, nullptr, 0.0, ep_usage, ep_cnt,
+                                                 stats_out);
   return status_of(cudaGetLastError());
 }
 

@@ -220,6 +220,18 @@ def stats_finalize(hist, count_add, sqerr_sum, inv_elems, ep_usage, ep_cnt, stat
     _count(1)
 
 
+def stats_pack(hist, sqerr_sum, n_elems, out):
+    check(lib.vqb200_stats_pack(ptr(hist), hist.numel(), ptr(sqerr_sum), float(n_elems), ptr(out), stream_ptr()),
+          "vqb200_stats_pack")
+    _count(1)
+
+
+def stats_finalize_packed(packed, K_total, count_add, ep_usage, ep_cnt, stats_out):
+    check(lib.vqb200_stats_finalize_packed(ptr(packed), K_total, float(count_add), ptr(ep_usage), ptr(ep_cnt),
+                                           ptr(stats_out), stream_ptr()), "vqb200_stats_finalize_packed")
+    _count(1)
+
+
 def scatter_add(z, idx, row_mask, seg_sum, seg_cnt):
     _need_cuda(z, idx, seg_sum)
     _f32c(z, "z")

@@ -147,9 +147,12 @@ class VectorQuantizerEMA(nn.Module):
 
     # ------------------------------------------------------------------ EMA
     @torch.no_grad()
-    def _ema_update(self, flat_raw: Tensor, indices: Tensor, row_mask: Optional[Tensor] = None):
+    def _ema_update(self, flat_raw: Tensor, indices: Tensor, row_mask: Optional[Tensor] = None,
+                    level: Optional[int] = None):
         """models/vq_vae.py:77-89 without the dense one-hot: segment sums by scatter-add, then the
-        lerp / divide for ALL codes fused with the cache refresh."""
+        lerp / divide for ALL codes fused with the cache refresh.  ``level`` (optional): the residual level the
+        indices belong to -- with ``ema_sync="allreduce"`` only that level's slice of the segment sums is non-zero,
+        so only it is all-reduced (a quarter of the bytes at four levels)."""
         if flat_raw.numel() == 0 or indices.numel() == 0:
             return
         cache = self._codebook_cache()
@@ -159,7 +162,12 @@ class VectorQuantizerEMA(nn.Module):
         seg_sum, seg_cnt = seg[: self.K * self.D], seg[self.K * self.D:]
         ops.scatter_add(flat, idx, row_mask, seg_sum, seg_cnt)
         if self.ema_sync == "allreduce" and sharding.dist_ready():
-            torch.distributed.all_reduce(seg)
+            if level is None or self.num_quantizers == 1:
+                torch.distributed.all_reduce(seg)
+            else:
+                a, b = level * self.K_per, (level + 1) * self.K_per
+                torch.distributed.all_reduce(seg_sum[a * self.D:b * self.D])
+                torch.distributed.all_reduce(seg_cnt[a:b])
         ops.ema_finalize(seg_sum, seg_cnt, self.decay, self.eps, self.ema_cluster_size, self.ema_embedding,
                          self.embedding, cache)
         cache.key = (self.embedding.data_ptr(), self.embedding._version)
@@ -252,8 +260,8 @@ class VectorQuantizerEMA(nn.Module):
         flat = z_e.detach().reshape(-1, D).contiguous()
         N = flat.shape[0]
         z_soft = ops.soft_assign(flat, self.embedding, tau)
-        scratch = torch.zeros(2 + self.K, dtype=torch.int32, device=dev)
-        sqerr, hist = scratch[:2].view(torch.float64), scratch[2:]
+        scratch = torch.zeros(4 + self.K, dtype=torch.int32, device=dev)
+        sqerr, hist = scratch[:4].view(torch.float64), scratch[4:]
         z_q = torch.empty(N, D, dtype=torch.float32, device=dev)
         idx = torch.empty(N, dtype=torch.int64, device=dev)
         do_ema = bool(self.training and do_ema_update and N > 0)
@@ -291,9 +299,9 @@ class VectorQuantizerEMA(nn.Module):
         L = self.num_quantizers
 
         # one zeroed scratch: [sqerr_sum (double) | hist int32[K]]
-        scratch = torch.zeros(2 + self.K, dtype=torch.int32, device=dev)
-        sqerr = scratch[:2].view(torch.float64)
-        hist = scratch[2:]
+        scratch = torch.zeros(4 + self.K, dtype=torch.int32, device=dev)
+        sqerr = scratch[:4].view(torch.float64)               # [sum sq err, element count (filled only when syncing)]
+        hist = scratch[4:]
         stats3 = torch.empty(3, dtype=torch.float32, device=dev)
         z_q = torch.empty(N, D, dtype=torch.float32, device=dev)
         z_q_st = torch.empty(N, D, dtype=torch.float32, device=dev)
@@ -385,7 +393,7 @@ class VectorQuantizerEMA(nn.Module):
             # level sum in level order (:261); RVQ histogram ignores the mask (:266)
             ops.gather(residual, E, idx_l, zq_out=z_q, accumulate=level > 0, residual_out=nxt, hist=hist)
             if ema_ok:
-                self._ema_update(residual, idx_l, valid_u8)
+                self._ema_update(residual, idx_l, valid_u8, level=level)
             if nxt is not None:
                 residual = nxt
         ops.st_loss(flat, z_q, zq_st_out=z_q_st, sqerr_sum=sqerr)
@@ -436,8 +444,8 @@ class VectorQuantizerEMA(nn.Module):
         s_in, s_out = pipe["in"], pipe["out"]
         ev_in, ev_run = pipe["ev_in"], pipe["ev_run"]
 
-        scratch = torch.zeros(2 + self.K, dtype=torch.int32, device=dev)
-        sqerr, hist = scratch[:2].view(torch.float64), scratch[2:]
+        scratch = torch.zeros(4 + self.K, dtype=torch.int32, device=dev)
+        sqerr, hist = scratch[:4].view(torch.float64), scratch[4:]
         stats3 = torch.empty(3, dtype=torch.float32, device=dev)
         stage = torch.empty(ring, min(chunk_rows, max(N, 1)), D, dtype=torch.float32, device=dev)
         z_q = torch.empty(N, D, dtype=torch.float32, device=dev) if want_all else None
@@ -509,13 +517,17 @@ class VectorQuantizerEMA(nn.Module):
         return p
 
     def _finalize_stats(self, hist, count_add, sqerr, n_elems, stats3):
-        inv = 1.0 / max(n_elems, 1)
+        """``sqerr``: float64 tensor whose first word is this rank's sum of squared errors."""
         if self.stats_sync and sharding.dist_ready():
-            # global statistics: ONE small all-reduce instead of the reference's
-            # per-rank perplexities averaged by sync_dist
-            sqerr, hist = sharding.allreduce_stats(sqerr, n_elems, hist)    # sqerr is now the global mean
-            inv = 1.0
-        ops.stats_finalize(hist, count_add, sqerr, inv, self._ep_usage, self._ep_cnt, stats3)
+            # global statistics: ONE small all-reduce (SURVEY.md section 8e) instead of the reference's per-rank
+            # perplexities averaged by sync_dist.  pack kernel -> NCCL -> finalize on the reduced pack: three
+            # launches on the step path (the 4 KB reduction sits inside a 0.4 ms step at the c2 shape)
+            pack = torch.empty(self.K + 2, dtype=torch.float64, device=hist.device)
+            ops.stats_pack(hist, sqerr, n_elems, pack)
+            torch.distributed.all_reduce(pack)
+            ops.stats_finalize_packed(pack, self.K, count_add, self._ep_usage, self._ep_cnt, stats3)
+            return
+        ops.stats_finalize(hist, count_add, sqerr, 1.0 / max(n_elems, 1), self._ep_usage, self._ep_cnt, stats3)
 
 
 class _UsageProbsFn(torch.autograd.Function):

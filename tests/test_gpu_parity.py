@@ -442,3 +442,23 @@ def test_rvq_finalize_matches_level_order_sum(vq, dev, K_per, D, L, N, lstride_p
     # optional outputs may be absent
     vq.ops.rvq_finalize(T(z, dev), idt.view(-1), stride, L, T(E, dev), zq_out=zq)
     assert np.array_equal(npy(zq), want)
+
+
+def test_packed_statistics_equal_direct(vq, dev):
+    """The multi-GPU statistics path (pack -> all-reduce -> finalize on the pack) on one rank == the direct path."""
+    K = 777
+    rs = np.random.RandomState(4)
+    hist = T(rs.randint(0, 50, K).astype(np.int32) * (rs.rand(K) > 0.3), dev).to(torch.int32)
+    sq = torch.tensor([123.456, 0.0], dtype=torch.float64, device=dev)
+    n_elems = 4096 * 64
+    a, b = torch.empty(3, device=dev), torch.empty(3, device=dev)
+    ua, ub = torch.zeros(K, device=dev), torch.zeros(K, device=dev)
+    ca, cb = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    vq.ops.stats_finalize(hist, 4096.0, sq, 1.0 / n_elems, ua, ca, a)
+    pack = torch.empty(K + 2, dtype=torch.float64, device=dev)
+    vq.ops.stats_pack(hist, sq, n_elems, pack)
+    assert float(pack[0]) == 123.456 and float(pack[1]) == n_elems and torch.equal(pack[2:].to(torch.int32), hist)
+    vq.ops.stats_finalize_packed(pack, K, 4096.0, ub, cb, b)
+    assert torch.equal(a, b) and torch.equal(ua, ub) and torch.equal(ca, cb)
+    vq.ops.stats_finalize_packed(pack * 2, K, 4096.0, ub, cb, b)      # two identical ranks: same statistics
+    np.testing.assert_allclose(npy(a), npy(b), rtol=1e-6)
