@@ -195,7 +195,9 @@ def run_b200(args, w):
     if train:                                            # stage-2 schedule values (configs/stage2_vq.yaml:117-123)
         q.train()
         q.beta, q.decay = 0.0005, 0.98
-        q.ema_sync = "allreduce" if world > 1 else "local"
+        # "allreduce": the replicated codebooks stay identical (segment sums summed over ranks before every level's
+        # EMA finalize); "local": the reference's behaviour under DDP (each rank updates from its own rows)
+        q.ema_sync = args.ema_sync if world > 1 else "local"
     else:
         q.eval()
     z_pin = torch.from_numpy(z_host).pin_memory()
@@ -377,7 +379,8 @@ def run_b200(args, w):
             "config": {"workload": w["desc"], "K": K, "D": D, "levels": L, "rows_per_gpu": N,
                        "search_mode": args.mode, "l2": "inputs+outputs per step exceed the 126 MB L2"
                        if N * D * 12 > 126e6 else "L2-resident working set (no flush)",
-                       "parallelism": f"rows sharded x{world}, codebook replicated", "cuda_graph": bool(args.graph)},
+                       "parallelism": f"rows sharded x{world}, codebook replicated", "cuda_graph": bool(args.graph),
+                       **({"ema_sync": q.ema_sync} if train else {})},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": N * D * 4,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms / args.steps,
                     "api": "train step: H2D batch (double-buffered on a copy stream), forward+backward, D2H loss" if train else
@@ -400,6 +403,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")   # c4 = extract, c5 = training step
     ap.add_argument("--mode", choices=["fp32", "bf16_input"], default="fp32")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--ema-sync", choices=["allreduce", "local"], default="allreduce",
+                    help="c5 on several GPUs: all-reduce the EMA segment sums (default) or update per rank")
     ap.add_argument("--graph", action="store_true", help="replay the forward as one CUDA graph (launch-bound shapes)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
