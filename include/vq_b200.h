@@ -30,7 +30,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 10
+#define VQB200_ABI_VERSION 11
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -126,6 +126,16 @@ VQB200_API int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float*
                              float one_minus_decay, float eps, float* ema_cluster_size, float* ema_embedding,
                              int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* One level of the training-mode residual forward up to the exchange point of a multi-GPU EMA update:
+ * search -> gather (zq_out accumulated when level > 0, residual_out for the next level or NULL, histogram) ->
+ * segment sums of THIS rank (seg_sum / seg_cnt zeroed here).  The caller all-reduces the sums and calls
+ * vqb200_ema_finalize.  Arrays are the whole cache arrays, as in vqb200_rvq_train_forward. */
+VQB200_API int vqb200_rvq_train_level(const float* residual, int64_t N, int D, const float* E,
+                           const uint16_t* E_lp_planes, const float* ee_half, const float* level_meta, int K_per,
+                           int L, int level, int mode, int64_t* idx_out, float* zq_out, float* residual_out,
+                           int32_t* hist, float* seg_sum, float* seg_cnt, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 /* Measurement hook (bench.py): while enabled, vqb200_search brackets every launch of its dominant kernel (the
  * tcgen05 search kernel; the SIMT kernel on shapes that take the SIMT path) with CUDA events on the launching

@@ -16,7 +16,7 @@ MODE_FP32_EXACT = 0
 MODE_BF16_INPUT = 1
 MAX_LEVELS = 32
 LEVEL_META_FLOATS = 8
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _p = C.c_void_p
 _i = C.c_int
@@ -43,6 +43,7 @@ SIGNATURES = {
     "vqb200_rvq_train_launches": (_i, [_i64, _i, _i, _i, _i]),
     "vqb200_rvq_train_forward": (_i, [_p, _i64, _i, _p, _p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p, _p,
                                       _p, _sz, _p]),
+    "vqb200_rvq_train_level": (_i, [_p, _i64, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "vqb200_residual_prep": (_i, [_p, _p, _p, _i64, _i, _i, _i, _p, _p, _p, _p, _p]),
     "vqb200_search_prepped": (_i, [_p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _i, _i, _i64, _p, _p, _sz, _p]),
     "vqb200_quantize_fused_supported": (_i, [_i64, _i, _i, _i]),

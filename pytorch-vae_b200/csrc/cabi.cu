@@ -239,6 +239,45 @@ int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_
   return launch_st_loss(z, zq_out, N * D, zq_st_out, sqerr_sum, s);
 }
 
+// One training level up to the point where ranks exchange their segment sums: search -> gather -> scatter-add.
+int vqb200_rvq_train_level(const float* residual, int64_t N, int D, const float* E, const uint16_t* E_lp_planes,
+                           const float* ee_half, const float* level_meta, int K_per, int L, int level, int mode,
+                           int64_t* idx_out, float* zq_out, float* residual_out, int32_t* hist, float* seg_sum,
+                           float* seg_cnt, void* workspace, size_t workspace_bytes, void* stream) {
+  VQ_REQUIRE(N > 0 && K_per > 0 && L >= 1 && level >= 0 && level < L, VQB200_EINVAL);
+  VQ_REQUIRE(residual && idx_out && E && E_lp_planes && ee_half && level_meta && zq_out && seg_sum && seg_cnt,
+             VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(residual) && aligned16(E) && aligned16(E_lp_planes) && aligned16(zq_out) &&
+                 aligned16(residual_out) && aligned16(seg_sum), VQB200_EALIGN);
+  VQ_REQUIRE(workspace_bytes >= vqb200_search_workspace_bytes(N, K_per, D, mode) && workspace, VQB200_EWORKSPACE);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  const int K_total = K_per * L;
+  const int64_t s0 = static_cast<int64_t>(level) * K_per;
+  const uint16_t* plane = E_lp_planes + (bf ? 0 : static_cast<size_t>(K_total) * D);
+  const float* ee_bf = ee_half + K_total;
+  int st;
+  if (tc_supported(N, K_per, D)) {
+    VQ_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, VQB200_EALIGN);
+    st = launch_search_tc(residual, N, D, E + s0 * D, plane + s0 * D, ee_half + s0, ee_bf + s0,
+                          level_meta + level * VQB200_LEVEL_META_FLOATS, K_per, mode, s0, idx_out, workspace,
+                          workspace_bytes, s);
+  } else {
+    st = launch_search_simt(residual, nullptr, N, D, E + s0 * D, (bf ? ee_bf : ee_half) + s0, K_per, bf ? 1 : 0, s0,
+                            idx_out, nullptr, s);
+  }
+  if (st != VQB200_OK) return st;
+  st = launch_gather(residual, E, idx_out, N, D, K_total, zq_out, level > 0, nullptr, residual_out, nullptr, hist,
+                     nullptr, s);
+  if (st != VQB200_OK) return st;
+  cudaError_t e = cudaMemsetAsync(seg_sum, 0, static_cast<size_t>(K_total) * D * 4, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(seg_cnt, 0, static_cast<size_t>(K_total) * 4, s);
+  if (e != cudaSuccess) return status_of(e);
+  return launch_scatter_add(residual, idx_out, nullptr, N, D, K_total, seg_sum, seg_cnt, s);
+}
+
 int vqb200_residual_prep(const float* z, const float* E_full, const int64_t* idx, int64_t N, int D, int K_total,
                          int mode, const float* next_level_meta, float* residual_out, uint16_t* z16_out,
                          float* margin_out, void* stream) {

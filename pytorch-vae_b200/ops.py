@@ -116,6 +116,21 @@ def rvq_train_forward(z, E, cache: CodebookCache, mode, decay, eps, ema_cluster_
     _count(lib.vqb200_rvq_train_launches(N, K, D, L, mode))
 
 
+def rvq_train_level(residual, E, cache: CodebookCache, level, mode, idx_out, zq_out, residual_out, hist, seg_sum,
+                    seg_cnt):
+    """search -> gather -> scatter-add of one training level (this rank's segment sums; the EMA finalize follows
+    the caller's all-reduce)."""
+    N, D = residual.shape
+    K, L = cache.K_per, cache.levels
+    ws_bytes = lib.vqb200_search_workspace_bytes(N, K, D, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=residual.device)
+    check(lib.vqb200_rvq_train_level(ptr(residual), N, D, ptr(E), ptr(cache.E_bf16), ptr(cache.ee_half),
+                                     ptr(cache.level_meta), K, L, level, mode, ptr(idx_out), ptr(zq_out),
+                                     ptr(residual_out), ptr(hist), ptr(seg_sum), ptr(seg_cnt), ptr(ws), ws_bytes,
+                                     stream_ptr()), "vqb200_rvq_train_level")
+    _count(search_launches(N, K, D, mode) + 2)
+
+
 def residual_prep(z, E, idx, cache: CodebookCache, next_level: int, mode: int, residual_out, z16_out, margin_out):
     """residual_out = z - E[idx] together with the next level's 16-bit operand copy and admission margins."""
     _need_cuda(z, E, idx, residual_out)

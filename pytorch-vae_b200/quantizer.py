@@ -379,6 +379,22 @@ class VectorQuantizerEMA(nn.Module):
                                   self.ema_embedding, idx_levels[0], z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist)
             cache.key = (self.embedding.data_ptr(), self.embedding._version)
             return
+        if ema_ok and valid_u8 is None and n > 0 and self.ema_sync == "allreduce" and sharding.dist_ready():
+            # training with the segment sums all-reduced over ranks: per level ONE library call up to the exchange
+            # point (search, gather, scatter-add), the all-reduce, and the EMA finalize
+            seg = torch.empty(self.K * D + self.K, dtype=torch.float32, device=flat.device)
+            seg_sum, seg_cnt = seg[: self.K * D], seg[self.K * D:]
+            for level in range(L):
+                nxt = spare[level % 2] if level < L - 1 else None
+                ops.rvq_train_level(residual, E, cache, level, mode, idx_levels[level], z_q, nxt, hist, seg_sum, seg_cnt)
+                torch.distributed.all_reduce(seg)
+                ops.ema_finalize(seg_sum, seg_cnt, self.decay, self.eps, self.ema_cluster_size, self.ema_embedding,
+                                 self.embedding, cache)
+                if nxt is not None:
+                    residual = nxt
+            cache.key = (self.embedding.data_ptr(), self.embedding._version)
+            ops.st_loss(flat, z_q, zq_st_out=z_q_st, sqerr_sum=sqerr)
+            return
         for level in range(L):
             idx_l = idx_levels[level]
             if level > 0 and do_ema:

@@ -462,3 +462,33 @@ def test_packed_statistics_equal_direct(vq, dev):
     assert torch.equal(a, b) and torch.equal(ua, ub) and torch.equal(ca, cb)
     vq.ops.stats_finalize_packed(pack * 2, K, 4096.0, ub, cb, b)      # two identical ranks: same statistics
     np.testing.assert_allclose(npy(a), npy(b), rtol=1e-6)
+
+
+def test_allreduced_ema_training_path_equals_local_on_one_rank(vq, dev, monkeypatch):
+    """The multi-GPU training path (per level: one library call up to the exchange point, all-reduce, EMA finalize)
+    with the all-reduce stubbed to the identity must reproduce the single-call local path."""
+    import torch.distributed as dist
+    from synth import large_case_inputs
+    E, z = large_case_inputs(91, 256, 128, 3, 16, 64)
+
+    def run(allreduce):
+        q = vq.VectorQuantizerEMA(256, 128, num_quantizers=3, print_init=False, decay=0.9).to(dev).train()
+        q.embedding.copy_(T(E, dev))
+        if allreduce:
+            q.ema_sync = "allreduce"
+            monkeypatch.setattr(vq.sharding, "dist_ready", lambda: True)
+            monkeypatch.setattr(dist, "all_reduce", lambda t, *a, **k: None)
+            q.stats_sync = False
+        outs = []
+        for step in range(2):
+            zz = T(z, dev) * (1.0 + 0.1 * step)
+            outs.append([t.clone() for t in q(zz, do_ema_update=True)])
+        monkeypatch.undo()
+        return q, outs
+    ql, ol = run(False)
+    qa, oa = run(True)
+    for a, b in zip(ol, oa):
+        assert torch.equal(a[2], b[2])
+        assert torch.allclose(a[1], b[1], rtol=1e-4, atol=1e-5) and torch.allclose(a[3], b[3], rtol=1e-5)
+    assert torch.allclose(ql.ema_cluster_size, qa.ema_cluster_size, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(ql.embedding, qa.embedding, rtol=1e-3, atol=1e-5)
