@@ -114,3 +114,46 @@ def test_shard_partitions():
         spans = [S.shard_codes(k, w, r) for r in range(w)]
         assert spans[0][0] == 0 and max(e for _, e in spans) == k
         assert all(a[1] == b[0] or b[0] == b[1] == k for a, b in zip(spans, spans[1:]))
+
+
+def test_extra_entry_points_refuse_cpu_tensors():
+    """forward_host / soft_forward / usage_code_probs / kmeans / graph replays: no CPU path behind any of them."""
+    q = vq.VectorQuantizerEMA(32, 16, print_init=False)
+    with pytest.raises(RuntimeError):
+        q.forward_host(torch.randn(2, 4, 16))                 # module buffers are not on a CUDA device
+    with pytest.raises(RuntimeError):
+        q.forward_host(torch.randn(2, 4, 16).double())
+    with pytest.raises(ValueError):
+        q.forward_host(torch.randn(2, 4, 16), outputs="everything")
+    with pytest.raises(ValueError):
+        q.forward_host(torch.randn(8, 16))                    # non-3-D, like forward()
+    with pytest.raises(RuntimeError):
+        q.soft_forward(torch.randn(2, 4, 16), 1.0)
+    with pytest.raises(RuntimeError):
+        q.usage_code_probs(torch.randn(2, 4, 16))
+    with pytest.raises(RuntimeError):
+        vq.kmeans_fit(torch.randn(64, 16), 8)
+    with pytest.raises(RuntimeError):
+        vq.rvq_kmeans_fit(torch.randn(64, 16), 8, 2)
+    with pytest.raises(RuntimeError):
+        vq.GraphedForward(q.eval(), torch.randn(2, 4, 16))
+    with pytest.raises(RuntimeError):
+        vq.GraphedTrainStep(q.eval(), torch.randn(2, 4, 16))  # needs training mode (and CUDA)
+    with pytest.raises(RuntimeError):
+        vq.ops.rvq_finalize(torch.randn(4, 16), torch.zeros(4, dtype=torch.int64), 4, 1, torch.randn(8, 16))
+
+
+def test_launch_and_workspace_accounting_without_a_gpu():
+    """The size / count queries of the one-call entry points are pure host functions."""
+    lib = vq._cabi.lib
+    N, K, D, L = 8192, 1024, 512, 4
+    per = lib.vqb200_search_launches(N, K, D, 0)
+    assert per == 5 and lib.vqb200_search_path(N, K, D, 0) == 1
+    assert lib.vqb200_rvq_forward_launches(N, K, D, L, 0) == per + (L - 1) * (per - 1) + (L - 1) + 1
+    assert lib.vqb200_rvq_train_launches(N, K, D, L, 0) == L * (per + 3) + 1
+    ws = lib.vqb200_search_workspace_bytes(N, K, D, 0)
+    assert lib.vqb200_rvq_forward_workspace_bytes(N, K, D, L, 0) >= ws + 2 * N * D * 4 + N * D * 2 + N * 4
+    assert lib.vqb200_rvq_train_workspace_bytes(N, K, D, L, 0) >= ws + 2 * N * D * 4 + (K * L * D + K * L) * 4
+    assert lib.vqb200_quantize_fused_supported(1 << 20, 512, 64, 0) == 1
+    assert lib.vqb200_quantize_fused_supported(1 << 20, 512, 128, 0) == 0
+    assert lib.vqb200_rvq_forward_launches(0, K, D, L, 0) == 0
