@@ -678,7 +678,9 @@ bool fused_supported(int64_t N, int K, int D) {
   if (f && f[0] == '1') return false;
   const char* g = std::getenv("VQB200_NO_FUSED");
   if (g && g[0] == '1') return false;
-  return D == 64 && K >= TC_BN && K < (1 << 24) && N >= 4096 && N <= 0x7fffffff;
+  const char* h = std::getenv("VQB200_FUSED_D128");        // D = 128 (BM = 128, one CTA per SM): opt-out switch
+  const bool d128 = D == 128 && !(h && h[0] == '0');
+  return (D == 64 || d128) && K >= TC_BN && K < (1 << 24) && N >= 4096 && N <= 0x7fffffff;
 }
 
 size_t fused_workspace_bytes(int64_t N) { return 256 + fz_align(static_cast<size_t>(N) * 4) + fz_align(static_cast<size_t>(N) * 8); }
@@ -696,63 +698,48 @@ static int fused_bm() {
   return (e && e[0] == '1') ? 128 : 256;
 }
 
-template <int BM>
-static int launch_fused_bm(const CUtensorMap& map_zf, const CUtensorMap& map_e, FusedParams& p, bool bf, int D,
-                           cudaStream_t s) {
-  // two CTAs of BM = 128 share one SM's 228 KB (1 KB reserved per CTA)
-  const int limit = BM == 256 ? TC_SMEM_LIMIT : (233472 - 2 * 1024) / 2;
+// D = 64: BM = 256, one CTA per SM (or BM = 128 with two co-resident CTAs, a measurement switch).
+// D = 128: BM = 128, one CTA per SM (the fp32 staging tile of 256 rows would not fit).
+template <int D, int BM>
+static int launch_fused_cfg(const CUtensorMap& map_zf, const CUtensorMap& map_e, FusedParams& p, bool bf,
+                            cudaStream_t s) {
+  constexpr bool kPair = D == 64 && BM == 128;            // two CTAs of BM = 128 share one SM's 228 KB (1 KB reserved each)
+  const int limit = kPair ? (233472 - 2 * 1024) / 2 : TC_SMEM_LIMIT;
   int stages = 8;
   while (stages > 2 && fused_smem_bytes(D, stages, BM) > limit) --stages;
   if (fused_smem_bytes(D, stages, BM) > limit) return VQB200_ESHAPE;
+  const char* dbg = std::getenv("VQB200_DEBUG");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(quantize_fused_kernel<64, false, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+    cudaError_t e = cudaFuncSetAttribute(quantize_fused_kernel<D, false, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(quantize_fused_kernel<64, true, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
+      e = cudaFuncSetAttribute(quantize_fused_kernel<D, true, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     if (e != cudaSuccess) return status_of(e);
     // co-residency needs the largest shared-memory carve-out the SM offers
-    cudaFuncSetAttribute(quantize_fused_kernel<64, false, BM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaFuncSetAttribute(quantize_fused_kernel<64, true, BM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    const char* dbg = std::getenv("VQB200_DEBUG");
-    if (dbg && dbg[0] == '1') {
+    cudaFuncSetAttribute(quantize_fused_kernel<D, false, BM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(quantize_fused_kernel<D, true, BM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (dbg && dbg[0] == '1') {                             // NB: the occupancy API reports 1 for any tcgen05.alloc kernel
       int nb = -1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, quantize_fused_kernel<64, false, BM>, fz_threads(BM),
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, quantize_fused_kernel<D, false, BM>, fz_threads(BM),
                                                     fused_smem_bytes(D, stages, BM));
-      fprintf(stderr, "[vqb200] fused BM=%d stages=%d smem=%d B: %d resident CTA(s) per SM\n", BM, stages,
-              fused_smem_bytes(D, stages, BM), nb);
-      int dev = 0, a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&a0, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-      cudaDeviceGetAttribute(&a1, cudaDevAttrReservedSharedMemoryPerBlock, dev);
-      cudaDeviceGetAttribute(&a2, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
-      cudaDeviceGetAttribute(&a3, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-      cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, quantize_fused_kernel<64, false, BM>);
-      fprintf(stderr, "[vqb200] smem/SM %d reserved/block %d regs/SM %d optin %d | kernel regs %d static smem %zu local %zu maxdyn %d carveout %d\n",
-              a0, a1, a2, a3, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes,
-              fa.preferredShmemCarveout);
-      for (int sm : {114048, 112000, 108000, 100000, 90000, 70000, 50000})
-        for (int th : {256, 224, 192}) {
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, quantize_fused_kernel<64, false, BM>, th, sm);
-          fprintf(stderr, "[vqb200]   dyn smem %d threads %d -> %d CTA/SM\n", sm, th, nb);
-        }
+      fprintf(stderr, "[vqb200] fused D=%d BM=%d stages=%d smem=%d B: occupancy API says %d CTA(s) per SM\n", D, BM,
+              stages, fused_smem_bytes(D, stages, BM), nb);
     }
     attr_done = true;
   }
   p.stages = stages;
   p.row_tiles = static_cast<int>((p.n_rows + BM - 1) / BM);
-  int slots = kNumSMs * (BM == 256 ? 1 : 2);
+  int slots = kNumSMs * (kPair ? 2 : 1);
   const char* genv = std::getenv("VQB200_FUSED_GRID");          // measurement switch
   if (genv && std::atoi(genv) > 0) slots = std::atoi(genv);
   const int grid = p.row_tiles < slots ? p.row_tiles : slots;
   const int smem = fused_smem_bytes(D, stages, BM);
-  const char* dbg = std::getenv("VQB200_DEBUG");
   const bool trace = dbg && dbg[0] == '2';
   p.dbg = nullptr;
   if (trace) cudaMallocManaged(&p.dbg, static_cast<size_t>(grid) * 3 * sizeof(long long));
   timing_mark_begin(s);
-  if (bf) quantize_fused_kernel<64, true, BM><<<grid, fz_threads(BM), smem, s>>>(map_zf, map_e, p);
-  else quantize_fused_kernel<64, false, BM><<<grid, fz_threads(BM), smem, s>>>(map_zf, map_e, p);
+  if (bf) quantize_fused_kernel<D, true, BM><<<grid, fz_threads(BM), smem, s>>>(map_zf, map_e, p);
+  else quantize_fused_kernel<D, false, BM><<<grid, fz_threads(BM), smem, s>>>(map_zf, map_e, p);
   timing_mark_end(s);
   if (trace) {                                                   // CTAs that overlapped in time on one SM
     cudaStreamSynchronize(s);
@@ -764,7 +751,8 @@ static int launch_fused_bm(const CUtensorMap& map_zf, const CUtensorMap& map_e, 
       for (int j = i + 1; j < grid; ++j)
         if (p.dbg[i * 3] == p.dbg[j * 3] && p.dbg[i * 3 + 1] < p.dbg[j * 3 + 2] && p.dbg[j * 3 + 1] < p.dbg[i * 3 + 2]) ++overlap;
     }
-    fprintf(stderr, "[vqb200] fused BM=%d grid=%d: %d co-resident CTA pairs, span %.1f us\n", BM, grid, overlap, (hi - lo) * 1e-3);
+    fprintf(stderr, "[vqb200] fused D=%d BM=%d grid=%d: %d co-resident CTA pairs, span %.1f us\n", D, BM, grid, overlap,
+            (hi - lo) * 1e-3);
     cudaFree(p.dbg);
   }
   return status_of(cudaGetLastError());
@@ -777,7 +765,7 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
   if (!fused_supported(N, K, D)) return VQB200_ESHAPE;
   if (workspace_bytes < fused_workspace_bytes(N)) return VQB200_EWORKSPACE;
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
-  const int BM = fused_bm();
+  const int BM = D == 128 ? 128 : fused_bm();
 
   uint8_t* w = static_cast<uint8_t*>(workspace);
   int* counters = reinterpret_cast<int*>(w); w += 256;
@@ -803,7 +791,9 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
   p.idx_offset = idx_offset; p.idx_out = idx_out; p.zq_out = zq_out; p.zq_st_out = zq_st_out;
   p.sqerr_sum = sqerr_sum; p.hist = hist; p.row_mask = row_mask;
   p.fb_rows = fb_rows; p.fb_packed = fb_packed; p.counters = counters;
-  const int ls = BM == 256 ? launch_fused_bm<256>(map_zf, map_e, p, bf, D, s) : launch_fused_bm<128>(map_zf, map_e, p, bf, D, s);
+  const int ls = D == 128 ? launch_fused_cfg<128, 128>(map_zf, map_e, p, bf, s)
+                          : BM == 256 ? launch_fused_cfg<64, 256>(map_zf, map_e, p, bf, s)
+                                      : launch_fused_cfg<64, 128>(map_zf, map_e, p, bf, s);
   if (ls != VQB200_OK) return ls;
 
   const int st = launch_search_simt_list(z, fb_rows, counters, N, D, E, bf ? ee_half_bf16 : ee_half, K, bf ? 1 : 0,

@@ -38,11 +38,12 @@ def forward(vq, z, E, K, mode="fp32", fused=True, mask=None):
     return used, st, zq, idx, stats, q
 
 
-@pytest.mark.parametrize("K,N,mode", [(512, 8192, "fp32"), (128, 4096, "fp32"), (1000, 300 * 64, "fp32"),
-                                      (2048, 16384, "fp32"), (4096, 8192, "fp32"), (512, 1 << 18, "fp32"),
-                                      (512, 8192, "bf16_input")])
-def test_fused_equals_multikernel(vq, K, N, mode):
-    D = 64
+@pytest.mark.parametrize("K,N,mode,D", [(512, 8192, "fp32", 64), (128, 4096, "fp32", 64), (1000, 300 * 64, "fp32", 64),
+                                        (2048, 16384, "fp32", 64), (4096, 8192, "fp32", 64), (512, 1 << 18, "fp32", 64),
+                                        (512, 8192, "bf16_input", 64), (512, 8192, "fp32", 128),
+                                        (1000, 300 * 64, "fp32", 128), (512, 1 << 17, "fp32", 128),
+                                        (2048, 8192, "bf16_input", 128)])
+def test_fused_equals_multikernel(vq, K, N, mode, D):
     E, z = large_case_inputs(300 + K + N % 977, K, D, 1, N // 64, 64)
     uf, st_f, zq_f, idx_f, stats_f, qf = forward(vq, z, E, K, mode, fused=True)
     um, st_m, zq_m, idx_m, stats_m, qm = forward(vq, z, E, K, mode, fused=False)
