@@ -159,7 +159,7 @@ VQB200_API int vqb200_gather(const float* z, const float* E, const int64_t* idx,
                   float* zq_out, int zq_accumulate, float* zq_st_out, float* residual_out,
                   double* sqerr_sum, int32_t* hist, const uint8_t* row_mask, void* stream);
 
-/* The whole single-level forward in ONE kernel (small code dimensions, currently D = 64): search, exact re-rank,
+/* The whole single-level forward in ONE kernel (small code dimensions: D = 64 and D = 128): search, exact re-rank,
  * gather, straight-through, commitment partial sum and histogram, reading the fp32 latents once.  Same
  * outputs, bit for bit, as vqb200_search followed by vqb200_gather.  Every output except idx_out is optional.
  * vqb200_quantize_fused_supported returns 1 when the shape takes this path. */
