@@ -155,5 +155,6 @@ def test_launch_and_workspace_accounting_without_a_gpu():
     assert lib.vqb200_rvq_forward_workspace_bytes(N, K, D, L, 0) >= ws + 2 * N * D * 4 + N * D * 2 + N * 4
     assert lib.vqb200_rvq_train_workspace_bytes(N, K, D, L, 0) >= ws + 2 * N * D * 4 + (K * L * D + K * L) * 4
     assert lib.vqb200_quantize_fused_supported(1 << 20, 512, 64, 0) == 1
-    assert lib.vqb200_quantize_fused_supported(1 << 20, 512, 128, 0) == 0
+    assert lib.vqb200_quantize_fused_supported(1 << 20, 512, 128, 0) == 1
+    assert lib.vqb200_quantize_fused_supported(1 << 20, 512, 256, 0) == 0
     assert lib.vqb200_rvq_forward_launches(0, K, D, L, 0) == 0
