@@ -34,5 +34,5 @@ for i in range(reps):
 ev[reps].record()
 torch.cuda.synchronize()
 ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
-print(f"BM={os.environ.get('VQB200_FUSED_BM', '128')} grid={os.environ.get('VQB200_FUSED_GRID', 'auto')} "
+print(f"BM={os.environ.get('VQB200_FUSED_BM', '256')} grid={os.environ.get('VQB200_FUSED_GRID', 'auto')} "
       f"K={K} D={D} N={N} {mode}: {ms[len(ms) // 2]:.4f} ms")

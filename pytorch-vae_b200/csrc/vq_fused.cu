@@ -1,20 +1,22 @@
-// Fully fused quantizer forward for small code dimensions (D = 64): ONE persistent kernel reads the fp32
-// latents once and writes indices, z_q, z_q_st, the commitment partial sum and the usage histogram -- the
+// Fully fused quantizer forward for small code dimensions (D = 64 and D = 128): ONE persistent kernel reads the
+// fp32 latents once and writes indices, z_q, z_q_st, the commitment partial sum and the usage histogram -- the
 // algorithmic HBM traffic of the path (12 D + 8 bytes per latent) and nothing else.  The multi-kernel
-// pipeline of vq_search_tc.cu + gather crosses HBM/L2 four times per latent; at D = 64 that, not the tensor
+// pipeline of vq_search_tc.cu + gather crosses HBM/L2 four times per latent; at small D that, not the tensor
 // work, bounds the step.
 //
-// Per CTA (one per SM, persistent over 256-row tiles), 12 warps:
-//   warp 0      TMA producer: fp32 latent tile [256 x D] (prefetched one tile ahead) + bf16 codebook blocks
-//   warp 1      MMA issuer:   tcgen05.mma M=128 N=128 K=16, two row halves, accumulators double-buffered in TMEM,
-//                             pre-loaded with -|e|^2/2 so the accumulator IS the score
-//   warps 2-9   epilogue:     scan scores out of TMEM, keep <= 4 live candidate records per row IN REGISTERS
-//                             (a record dies as soon as the running threshold passes it), then per tile of rows:
-//                             prune, score survivors exactly (fp64, lane groups, inputs from L2), write idx,
-//                             z_q = E[idx], z_q_st = fl(z + fl(z_q - z)), sum (z_q - z)^2, histogram
-//   warps 10-11 converters:   fp32 tile (swizzled TMA layout) -> bf16 UMMA operand tile (128-byte swizzle),
-//                             row norms -> admission margins
-// Exactness argument, margin and hand-back rules are those of vq_search_tc.cu.
+// Per CTA (one per SM, persistent over BM-row tiles; BM = 256 at D = 64, 128 at D = 128), 16 warps at BM = 256:
+//   warp 0       TMA producer: fp32 latent tile [BM x D] (prefetched one tile ahead) + 16-bit codebook blocks
+//   warp 1       MMA issuer:   tcgen05.mma M=128 N=128 K=16 per row half, accumulators double-buffered in TMEM and
+//                              pre-loaded with -|e|^2/2 so the accumulator IS the score
+//   warps 2-9    epilogue:     scan scores out of TMEM; groups of 8 columns that reach the running admission
+//                              threshold go, raw scores and all, into a 4-entry shared-memory ring per row (its
+//                              ageing is a register shift chain); then per tile: prune against the final threshold,
+//                              score multi-survivor rows exactly (fp64, lane groups, inputs from L2), write idx and
+//                              the histogram, publish the tile's codes in shared memory
+//   warps 10-15  converters:   fp32 tile (swizzled TMA layout) -> fp16 (fp32 mode) / bf16 UMMA operand tile
+//                / output      (128-byte swizzle), measured conversion error -> admission margins; then, one tile
+//                              behind the epilogue: z_q = E[idx], z_q_st = fl(z + fl(z_q - z)), sum (z_q - z)^2
+// Exactness argument, margin and hand-back rules are those of vq_search_tc.cu / common.cuh.
 #include <cstdio>
 #include <initializer_list>
 #include <cstdlib>
@@ -23,10 +25,10 @@
 
 namespace vqb {
 
-// Two tile heights.  BM = 256: one CTA per SM, 8 epilogue warps (12 warps, 170 registers, no spills).
-// BM = 128: TWO CTAs per SM (half the shared memory, 256 TMEM columns and <= 128 registers each): the scan of
-// one CTA's tile overlaps the re-rank / output phase of the other's -- those phases are latency-bound (TMEM and
-// L2 round trips on dependent chains), so a second resident pipeline roughly doubles the SM's throughput.
+// Tile heights.  BM = 256 (D = 64): one CTA per SM, 8 epilogue + 6 converter/output warps (16 warps cap every
+// thread at 128 registers).  BM = 128: D = 128 (the fp32 staging tile of 256 rows would not fit), one CTA per SM;
+// and, as a measurement switch at D = 64 (VQB200_FUSED_BM=128), TWO co-resident CTAs per SM with 256 TMEM columns
+// each -- measured slower than BM = 256: the same number of epilogue warps per SM, twice the per-tile overheads.
 constexpr int fz_nconv(int BM) { return BM == 256 ? 6 : 2; }   // converter / output warps (16 warps: 128 registers each)
 constexpr int fz_nepi(int BM) { return BM / 32; }
 constexpr int fz_threads(int BM) { return 64 + fz_nepi(BM) * 32 + fz_nconv(BM) * 32; }   // 448 / 256
