@@ -668,7 +668,48 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
     uint32_t first = 0;
     float thr = __int_as_float(0x7fc00000);
     bool fallback = false;
-    if (mine) {
+    if (rpw == 1 && base < n) {
+      // One row per warp (small n): the whole warp prunes it -- lane j takes record j of each slice (one coalesced
+      // 256-byte load per slice) instead of lane 0 walking up to 31 records per slice through dependent loads.
+      const int64_t r = base;
+      float bs = __int_as_float(0xff800000);
+      int c_l = 0;
+      if (lane < nsub) { c_l = cnt[r * nsub + lane]; bs = best[r * nsub + lane]; }
+      bool bad = lane < nsub && (c_l < 0 || c_l > TC_CAND || (c_l == 0 && bs != __int_as_float(0xff800000)));
+      bad = __any_sync(0xffffffffu, bad);
+      float bmax = bs;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+      const float mg = margin[r];
+      if (!bad && mg == mg) {
+        thr = bmax - mg;
+        for (int sb = 0; sb < nsub; ++sb) {
+          const int c = __shfl_sync(0xffffffffu, c_l, sb);
+          uint2 ent = make_uint2(0u, 0xff800000u);
+          if (lane < c) ent = cand[(r * nsub + sb) * TC_SLOTS + lane];
+          const bool hit = lane < c && __uint_as_float(ent.y) >= thr;
+          const unsigned hits = __ballot_sync(0xffffffffu, hit);
+          if (hits) {
+            if (ns == 0) first = __shfl_sync(0xffffffffu, ent.x, __ffs(hits) - 1);
+            ns += __popc(hits);
+            int pc = hit ? __popc(ent.x & 0xffu) : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+            ncodes += pc;
+          }
+        }
+      }
+      if (lane == 0) {                                   // ns, ncodes, first, thr are warp-uniform here
+        if (ns == 1 && ncodes == 1) {
+          idx_out[r] = idx_offset + ((first >> 8) << 3) + (__ffs(first & 0xffu) - 1);
+        } else if (ns < 1 || ncodes > RR_LIST) {
+          fallback = true;
+          const int pos = atomicAdd(counters + 0, 1);
+          fb_rows[pos] = static_cast<int>(r);
+          fb_packed[r] = ~0ull;
+        }
+      }
+    } else if (mine) {
       float bmax = __int_as_float(0xff800000);
       bool bad = false;
       for (int sb = 0; sb < nsub; ++sb) {
