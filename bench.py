@@ -195,8 +195,10 @@ def run_b200(args, w):
     if train:                                            # stage-2 schedule values (configs/stage2_vq.yaml:117-123)
         q.train()
         q.beta, q.decay = 0.0005, 0.98
-        # "allreduce": the replicated codebooks stay identical (segment sums summed over ranks before every level's
-        # EMA finalize); "local": the reference's behaviour under DDP (each rank updates from its own rows)
+        # "local" (default): every rank updates its replicated codebook from its own rows -- the reference's behaviour
+        # (under DDP rank 0's buffers are then broadcast) and BASELINE.json's north star ("only the scalar loss and
+        # the code-usage histogram are NCCL-allreduced"); "allreduce": segment sums summed over ranks before every
+        # level's EMA finalize, so the replicas stay identical without a broadcast
         q.ema_sync = args.ema_sync if world > 1 else "local"
     else:
         q.eval()
@@ -403,8 +405,9 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c2")   # c4 = extract, c5 = training step
     ap.add_argument("--mode", choices=["fp32", "bf16_input"], default="fp32")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--ema-sync", choices=["allreduce", "local"], default="allreduce",
-                    help="c5 on several GPUs: all-reduce the EMA segment sums (default) or update per rank")
+    ap.add_argument("--ema-sync", choices=["allreduce", "local"], default="local",
+                    help="c5 on several GPUs: update the codebook per rank (default, as the reference) or all-reduce the "
+                         "EMA segment sums")
     ap.add_argument("--graph", action="store_true", help="replay the forward as one CUDA graph (launch-bound shapes)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
