@@ -29,9 +29,11 @@ namespace vqb {
 // thread at 128 registers).  BM = 128: D = 128 (the fp32 staging tile of 256 rows would not fit), one CTA per SM;
 // and, as a measurement switch at D = 64 (VQB200_FUSED_BM=128), TWO co-resident CTAs per SM with 256 TMEM columns
 // each -- measured slower than BM = 256: the same number of epilogue warps per SM, twice the per-tile overheads.
-constexpr int fz_nconv(int BM) { return BM == 256 ? 6 : 2; }   // converter / output warps (16 warps: 128 registers each)
+// converter / output warps: 6 where the CTA has the SM to itself (16 warps at BM = 256, 12 at D = 128), 2 in the
+// two-CTAs-per-SM variant (D = 64, BM = 128)
+constexpr int fz_nconv(int D, int BM) { return (D == 64 && BM == 128) ? 2 : 6; }
 constexpr int fz_nepi(int BM) { return BM / 32; }
-constexpr int fz_threads(int BM) { return 64 + fz_nepi(BM) * 32 + fz_nconv(BM) * 32; }   // 448 / 256
+constexpr int fz_threads(int D, int BM) { return 64 + fz_nepi(BM) * 32 + fz_nconv(D, BM) * 32; }   // 512 / 384 / 256
 constexpr int FZ_PAIRS = 64;          // (row, code) pairs scored per warp pass
 constexpr int fz_hist(int BM) { return BM == 256 ? 2048 : 1024; }   // codebooks up to this size: shared-memory histogram
 constexpr int FZ_RING_BYTES = 4 * (2 * 32 * 16 + 32 * 8);           // per warp: FZ_RING entries x 32 lanes x 40 bytes
@@ -96,11 +98,11 @@ __device__ __forceinline__ void fz_scan(const uint32_t (&v)[32], uint32_t code0,
 }
 
 template <int D, bool BF16, int FZ_BM>
-__global__ void __launch_bounds__(fz_threads(FZ_BM), FZ_BM == 256 ? 1 : 2)
+__global__ void __launch_bounds__(fz_threads(D, FZ_BM), (D == 64 && FZ_BM == 128) ? 2 : 1)
 quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_constant__ CUtensorMap tmap_e,
                       const FusedParams p) {
-  constexpr int FZ_NEPI = fz_nepi(FZ_BM), FZ_THREADS = fz_threads(FZ_BM), FZ_HIST = fz_hist(FZ_BM);
-  constexpr int FZ_NCONV = fz_nconv(FZ_BM);
+  constexpr int FZ_NEPI = fz_nepi(FZ_BM), FZ_THREADS = fz_threads(D, FZ_BM), FZ_HIST = fz_hist(FZ_BM);
+  constexpr int FZ_NCONV = fz_nconv(D, FZ_BM);
   constexpr int HALVES = FZ_BM / 128;              // M = 128 accumulator tiles per row tile
   constexpr uint32_t TMEM_COLS = 2 * HALVES * TC_BN;   // two accumulator buffers
   constexpr int KBLK = D / TC_KB;                  // bf16 operand blocks along D
@@ -722,7 +724,7 @@ static int launch_fused_cfg(const CUtensorMap& map_zf, const CUtensorMap& map_e,
     cudaFuncSetAttribute(quantize_fused_kernel<D, true, BM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     if (dbg && dbg[0] == '1') {                             // NB: the occupancy API reports 1 for any tcgen05.alloc kernel
       int nb = -1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, quantize_fused_kernel<D, false, BM>, fz_threads(BM),
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, quantize_fused_kernel<D, false, BM>, fz_threads(D, BM),
                                                     fused_smem_bytes(D, stages, BM));
       fprintf(stderr, "[vqb200] fused D=%d BM=%d stages=%d smem=%d B: occupancy API says %d CTA(s) per SM\n", D, BM,
               stages, fused_smem_bytes(D, stages, BM), nb);
@@ -740,8 +742,8 @@ static int launch_fused_cfg(const CUtensorMap& map_zf, const CUtensorMap& map_e,
   p.dbg = nullptr;
   if (trace) cudaMallocManaged(&p.dbg, static_cast<size_t>(grid) * 3 * sizeof(long long));
   timing_mark_begin(s);
-  if (bf) quantize_fused_kernel<D, true, BM><<<grid, fz_threads(BM), smem, s>>>(map_zf, map_e, p);
-  else quantize_fused_kernel<D, false, BM><<<grid, fz_threads(BM), smem, s>>>(map_zf, map_e, p);
+  if (bf) quantize_fused_kernel<D, true, BM><<<grid, fz_threads(D, BM), smem, s>>>(map_zf, map_e, p);
+  else quantize_fused_kernel<D, false, BM><<<grid, fz_threads(D, BM), smem, s>>>(map_zf, map_e, p);
   timing_mark_end(s);
   if (trace) {                                                   // CTAs that overlapped in time on one SM
     cudaStreamSynchronize(s);
