@@ -1,9 +1,14 @@
-"""Importable alias of the ``pytorch-vae_b200/`` package directory (a hyphen is not a valid
-identifier): ``import pytorch_vae_b200`` executes ``pytorch-vae_b200/__init__.py`` with this
-module's ``__path__`` pointing there, so submodules resolve to the real files."""
-import os as _os
+"""pytorch-vae_b200: B200-native (sm_100a) vector-quantizer hot path of jluuser/PyTorch-VAE.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "pytorch-vae_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+Drop-in for ``models/vq_vae.py``'s ``VectorQuantizerEMA``; see INTEGRATION.md.
+Importing this package loads ``lib/libvqb200.so`` and raises if it is missing --
+there is no fallback implementation.
+"""
+from . import _cabi, ops  # noqa: F401  (loads the shared library; ImportError if absent)
+from .quantizer import VectorQuantizer, VectorQuantizerEMA  # noqa: F401
+from .integration import install, uninstall  # noqa: F401
+from .graphs import GraphedForward, GraphedTrainStep  # noqa: F401
+from .kmeans import kmeans_fit, rvq_kmeans_fit  # noqa: F401
+
+__all__ = ["VectorQuantizerEMA", "VectorQuantizer", "GraphedForward", "GraphedTrainStep", "kmeans_fit", "rvq_kmeans_fit", "install",
+           "uninstall", "ops"]

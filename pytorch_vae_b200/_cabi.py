@@ -78,7 +78,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(or `make -C pytorch-vae_b200/csrc`). This package has no fallback path.")
+            "(or `make -C pytorch_vae_b200/csrc`). This package has no fallback path.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol

@@ -85,7 +85,7 @@ def test_no_cpu_fallback():
     with pytest.raises(ValueError):
         vq.VectorQuantizerEMA(32, 18, print_init=False)
     # the product never touches the oracle
-    pkg = os.path.join(ROOT, "pytorch-vae_b200")
+    pkg = os.path.join(ROOT, "pytorch_vae_b200")
     for dp, _, fns in os.walk(pkg):
         for fn in fns:
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
