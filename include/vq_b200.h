@@ -9,7 +9,10 @@
  * Conventions
  *   - plain pointers and sizes only; every pointer is DEVICE memory unless it says "host"
  *   - row-major, contiguous; float rows must be 16-byte aligned (D % 4 == 0)
- *   - caller allocates every output and workspace; the library keeps no state
+ *   - caller allocates every output and workspace.  The library owns no data; the only process state is
+ *     (a) per device, three helper streams + events created on first use by the chunk pipeline of
+ *     vqb200_search / vqb200_quantize (never destroyed), (b) one-time cudaFuncSetAttribute flags per device and
+ *     (c) the vqb200_timing_* measurement hooks, which are process-global, NOT thread-safe and meant for bench.py
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises
  *   - return 0 on success, a negative VQB200_E* for argument errors, or a positive
  *     cudaError_t from the launch.  Nothing throws.  No CPU fallback exists.
@@ -30,7 +33,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 11
+#define VQB200_ABI_VERSION 12
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -195,10 +198,11 @@ VQB200_API int vqb200_stats_finalize(const int32_t* hist, int K_total, float cou
 
 /* Multi-GPU statistics: vqb200_stats_pack writes this rank's float64 pack [sum sq err | element count | histogram]
  * (K_total + 2 doubles: counts stay exact to 2^53), the caller all-reduces it (SUM) and
- * vqb200_stats_finalize_packed is vqb200_stats_finalize on the reduced pack (stats_out[2] = global mean sq err). */
+ * vqb200_stats_finalize_packed is vqb200_stats_finalize on the reduced pack (stats_out[2] = global mean sq err;
+ * ep_cnt += levels * (reduced element count / D), the GLOBAL number of quantized positions). */
 VQB200_API int vqb200_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems,
                       double* packed_out, void* stream);
-VQB200_API int vqb200_stats_finalize_packed(const double* packed, int K_total, float count_add, float* ep_usage,
+VQB200_API int vqb200_stats_finalize_packed(const double* packed, int K_total, int levels, int D, float* ep_usage,
                                  float* ep_cnt, float* stats_out, void* stream);
 
 /* EMA codebook update, part 1: segment sums.  Replaces the dense one-hot GEMM of

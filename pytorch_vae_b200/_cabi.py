@@ -16,7 +16,7 @@ MODE_FP32_EXACT = 0
 MODE_BF16_INPUT = 1
 MAX_LEVELS = 32
 LEVEL_META_FLOATS = 8
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _p = C.c_void_p
 _i = C.c_int
@@ -54,7 +54,7 @@ SIGNATURES = {
     "vqb200_st_loss": (_i, [_p, _p, _i64, _p, _p, _p]),
     "vqb200_stats_finalize": (_i, [_p, _i, _f, _p, _d, _p, _p, _p, _p]),
     "vqb200_stats_pack": (_i, [_p, _i, _p, _d, _p, _p]),
-    "vqb200_stats_finalize_packed": (_i, [_p, _i, _f, _p, _p, _p, _p]),
+    "vqb200_stats_finalize_packed": (_i, [_p, _i, _i, _i, _p, _p, _p, _p]),
     "vqb200_scatter_add": (_i, [_p, _p, _p, _i64, _i, _i, _p, _p, _p]),
     "vqb200_ema_finalize": (_i, [_p, _p, _f, _f, _f, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "vqb200_kmeans_finalize": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),

@@ -418,10 +418,10 @@ int vqb200_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum,
   return launch_stats_pack(hist, K_total, sqerr_sum, n_elems, packed_out, static_cast<cudaStream_t>(stream));
 }
 
-int vqb200_stats_finalize_packed(const double* packed, int K_total, float count_add, float* ep_usage, float* ep_cnt,
+int vqb200_stats_finalize_packed(const double* packed, int K_total, int levels, int D, float* ep_usage, float* ep_cnt,
                                  float* stats_out, void* stream) {
-  VQ_REQUIRE(packed && stats_out && K_total > 0, VQB200_EINVAL);
-  return launch_stats_finalize_packed(packed, K_total, count_add, ep_usage, ep_cnt, stats_out,
+  VQ_REQUIRE(packed && stats_out && K_total > 0 && levels > 0 && D > 0, VQB200_EINVAL);
+  return launch_stats_finalize_packed(packed, K_total, levels, D, ep_usage, ep_cnt, stats_out,
                                       static_cast<cudaStream_t>(stream));
 }
 

@@ -56,6 +56,12 @@ __device__ __forceinline__ void st_stream(float4* p, const float4& v) {
                : "memory");
 }
 
+// cudaFuncSetAttribute is per device: one-time flags are kept per device ordinal
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
 inline int status_of(cudaError_t e) { return e == cudaSuccess ? VQB200_OK : static_cast<int>(e); }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -150,7 +156,7 @@ int launch_stats_finalize(const int32_t* hist, int K_total, float count_add, con
                           double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out, cudaStream_t s);
 int launch_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, double* out,
                       cudaStream_t s);
-int launch_stats_finalize_packed(const double* packed, int K_total, float count_add, float* ep_usage, float* ep_cnt,
+int launch_stats_finalize_packed(const double* packed, int K_total, int levels, int D, float* ep_usage, float* ep_cnt,
                                  float* stats_out, cudaStream_t s);
 int launch_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
                        float* seg_sum, float* seg_cnt, cudaStream_t s);

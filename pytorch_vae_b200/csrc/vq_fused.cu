@@ -713,7 +713,8 @@ static int launch_fused_cfg(const CUtensorMap& map_zf, const CUtensorMap& map_e,
   while (stages > 2 && fused_smem_bytes(D, stages, BM) > limit) --stages;
   if (fused_smem_bytes(D, stages, BM) > limit) return VQB200_ESHAPE;
   const char* dbg = std::getenv("VQB200_DEBUG");
-  static bool attr_done = false;
+  static bool attr_done_dev[64] = {};
+  bool& attr_done = attr_done_dev[current_device_slot()];
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(quantize_fused_kernel<D, false, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, limit);
     if (e == cudaSuccess)

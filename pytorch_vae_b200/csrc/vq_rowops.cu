@@ -465,7 +465,7 @@ stats_finalize_kernel(const int32_t* __restrict__ hist_i, const double* __restri
       stats_out[1] = static_cast<float>(b / static_cast<double>(K_total));
       if (PACKED) stats_out[2] = static_cast<float>(packed[0] / (packed[1] < 1.0 ? 1.0 : packed[1]));
       else stats_out[2] = sqerr_sum ? static_cast<float>(*sqerr_sum * inv_elems) : 0.f;
-      if (ep_cnt) ep_cnt[0] += count_add;
+      if (ep_cnt) ep_cnt[0] += PACKED ? static_cast<float>(rint(packed[1] * inv_elems)) : count_add;   // PACKED: global count
     }
   }
 }
@@ -491,9 +491,11 @@ int launch_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum,
   return status_of(cudaGetLastError());
 }
 
-int launch_stats_finalize_packed(const double* packed, int K_total, float count_add, float* ep_usage, float* ep_cnt,
+int launch_stats_finalize_packed(const double* packed, int K_total, int levels, int D, float* ep_usage, float* ep_cnt,
                                  float* stats_out, cudaStream_t s) {
-  stats_finalize_kernel<true><<<1, 1024, 0, s>>>(nullptr, packed, K_total, count_add, nullptr, 0.0, ep_usage, ep_cnt,
+  // PACKED: inv_elems carries levels / D -- the positions every reduced element stands for
+  stats_finalize_kernel<true><<<1, 1024, 0, s>>>(nullptr, packed, K_total, 0.f, nullptr,
+                                                 static_cast<double>(levels) / static_cast<double>(D), ep_usage, ep_cnt,
                                                  stats_out);
   return status_of(cudaGetLastError());
 }
@@ -599,7 +601,7 @@ commit_backward_kernel(const float4* __restrict__ g, const float* __restrict__ g
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = ld_stream(z + i), q = ld_stream(zq + i);
     float4 o = g ? ld_stream(g + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    o.x += a * (v.x - q.x); o.y += a * (v.y - q.y); o.z += a * (v.z - q.z); o.w += a * (v.w - q.w);
+    if (gc) { o.x += a * (v.x - q.x); o.y += a * (v.y - q.y); o.z += a * (v.z - q.z); o.w += a * (v.w - q.w); }   // no commitment term: no 0 * inf
     st_stream(out + i, o);
   }
 }

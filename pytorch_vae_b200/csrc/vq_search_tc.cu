@@ -1026,13 +1026,15 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   // costs more than the overlap returns, so the default keeps the SMs to the tensor kernel.
   const char* envr = std::getenv("VQB200_TC2_REGS");
   const bool slim = envr && envr[0] == '1' && envr[1] == '2';
-  static bool attr2_done = false;
+  static bool attr2_done_dev[64] = {};
+  bool& attr2_done = attr2_done_dev[current_device_slot()];
   if (use2 && !attr2_done) {
     VQ_CUDA(cudaFuncSetAttribute(search_tc2_kernel<168>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     VQ_CUDA(cudaFuncSetAttribute(search_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr2_done = true;
   }
-  static bool attr_done[2] = {false, false};
+  static bool attr_done_dev[64][2] = {};
+  bool (&attr_done)[2] = attr_done_dev[current_device_slot()];
   if (!attr_done[pl.BM == 256]) {
     VQ_CUDA(pl.BM == 256
         ? cudaFuncSetAttribute(search_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT)

@@ -5,6 +5,8 @@ below enqueues hand-written sm_100a kernels from libvqb200.so and nothing else.
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 
 from . import _cabi
@@ -22,6 +24,22 @@ def launch_count() -> int:
 def _count(n: int):
     global _launches
     _launches += n
+
+
+def _on_device(fn):
+    """Run ``fn`` with the CUDA device of its first CUDA tensor argument current: the library launches on the
+    current device's current stream (``stream_ptr``), keeps its helper streams per device and sets kernel
+    attributes per device, so a module moved with ``.to('cuda:1')`` must not launch on device 0."""
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        for t in args:
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                if t.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(t.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapped
 
 
 def _need_cuda(*ts):
@@ -54,6 +72,7 @@ class CodebookCache:
         plane = 0 if mode == _cabi.MODE_BF16_INPUT else 1
         return self.E_bf16.data_ptr() + (plane * self.K_total + first_code) * self.D * 2
 
+    @_on_device
     def prepare(self, E: torch.Tensor):
         _need_cuda(E)
         _f32c(E, "embedding")
@@ -63,6 +82,7 @@ class CodebookCache:
         _count(1)
 
 
+@_on_device
 def search(z: torch.Tensor, E: torch.Tensor, cache: CodebookCache, level: int, mode: int,
            idx_out: torch.Tensor, idx_offset: int | None = None):
     """idx_out[n] = idx_offset + argmin_k |z_n - E[level*K_per + k]|^2 (one level)."""
@@ -83,6 +103,7 @@ def search(z: torch.Tensor, E: torch.Tensor, cache: CodebookCache, level: int, m
     _count(search_launches(N, K, D, mode))
 
 
+@_on_device
 def rvq_forward(z, E, cache: CodebookCache, mode: int, idx_out, zq_out=None, zq_st_out=None, sqerr_sum=None,
                 hist=None):
     """Eval-mode residual forward (all levels, finalize included) in one library call."""
@@ -99,6 +120,7 @@ def rvq_forward(z, E, cache: CodebookCache, mode: int, idx_out, zq_out=None, zq_
     _count(lib.vqb200_rvq_forward_launches(N, K, D, L, mode))
 
 
+@_on_device
 def rvq_train_forward(z, E, cache: CodebookCache, mode, decay, eps, ema_cluster_size, ema_embedding, idx_out, zq_out,
                       zq_st_out=None, sqerr_sum=None, hist=None):
     """Training-mode residual forward with a local EMA update after every level, in one library call."""
@@ -116,6 +138,7 @@ def rvq_train_forward(z, E, cache: CodebookCache, mode, decay, eps, ema_cluster_
     _count(lib.vqb200_rvq_train_launches(N, K, D, L, mode))
 
 
+@_on_device
 def rvq_train_level(residual, E, cache: CodebookCache, level, mode, idx_out, zq_out, residual_out, hist, seg_sum,
                     seg_cnt):
     """search -> gather -> scatter-add of one training level (this rank's segment sums; the EMA finalize follows
@@ -131,6 +154,7 @@ def rvq_train_level(residual, E, cache: CodebookCache, level, mode, idx_out, zq_
     _count(search_launches(N, K, D, mode) + 2)
 
 
+@_on_device
 def residual_prep(z, E, idx, cache: CodebookCache, next_level: int, mode: int, residual_out, z16_out, margin_out):
     """residual_out = z - E[idx] together with the next level's 16-bit operand copy and admission margins."""
     _need_cuda(z, E, idx, residual_out)
@@ -143,6 +167,7 @@ def residual_prep(z, E, idx, cache: CodebookCache, next_level: int, mode: int, r
     _count(1)
 
 
+@_on_device
 def search_prepped(z, z16, margin, E, cache: CodebookCache, level: int, mode: int, idx_out):
     """``search`` for rows whose operand copy and margins ``residual_prep`` already produced (tensor path only)."""
     _need_cuda(z, E, idx_out)
@@ -173,6 +198,7 @@ def fused_supported(N, K, D, mode) -> bool:
     return bool(lib.vqb200_quantize_fused_supported(N, K, D, mode))
 
 
+@_on_device
 def quantize_fused(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st_out=None, sqerr_sum=None,
                    hist=None, row_mask=None):
     """Single-level forward in one kernel: idx, z_q, z_q_st, sum (z_q - z)^2 and histogram from one read of z."""
@@ -191,6 +217,7 @@ def quantize_fused(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st
     _count(3)     # fused kernel, exact hand-back kernel, fix-up kernel
 
 
+@_on_device
 def quantize(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st_out=None, sqerr_sum=None, hist=None,
              row_mask=None):
     """Single-level search + gather in one call; on the tensor path the gather of each chunk of rows overlaps the
@@ -210,6 +237,7 @@ def quantize(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st_out=N
     _count(n_search + chunks)
 
 
+@_on_device
 def gather(z, E, idx, zq_out=None, accumulate=False, zq_st_out=None, residual_out=None, sqerr_sum=None,
            hist=None, row_mask=None):
     _need_cuda(z, E, idx)
@@ -221,6 +249,7 @@ def gather(z, E, idx, zq_out=None, accumulate=False, zq_st_out=None, residual_ou
     _count(1)
 
 
+@_on_device
 def st_loss(z, zq, zq_st_out=None, sqerr_sum=None):
     _need_cuda(z, zq)
     check(lib.vqb200_st_loss(ptr(z), ptr(zq), z.numel(), ptr(zq_st_out), ptr(sqerr_sum), stream_ptr()),
@@ -228,6 +257,7 @@ def st_loss(z, zq, zq_st_out=None, sqerr_sum=None):
     _count(1)
 
 
+@_on_device
 def stats_finalize(hist, count_add, sqerr_sum, inv_elems, ep_usage, ep_cnt, stats_out):
     check(lib.vqb200_stats_finalize(ptr(hist), hist.numel(), float(count_add), ptr(sqerr_sum), float(inv_elems),
                                     ptr(ep_usage), ptr(ep_cnt), ptr(stats_out), stream_ptr()),
@@ -235,18 +265,21 @@ def stats_finalize(hist, count_add, sqerr_sum, inv_elems, ep_usage, ep_cnt, stat
     _count(1)
 
 
+@_on_device
 def stats_pack(hist, sqerr_sum, n_elems, out):
     check(lib.vqb200_stats_pack(ptr(hist), hist.numel(), ptr(sqerr_sum), float(n_elems), ptr(out), stream_ptr()),
           "vqb200_stats_pack")
     _count(1)
 
 
-def stats_finalize_packed(packed, K_total, count_add, ep_usage, ep_cnt, stats_out):
-    check(lib.vqb200_stats_finalize_packed(ptr(packed), K_total, float(count_add), ptr(ep_usage), ptr(ep_cnt),
+@_on_device
+def stats_finalize_packed(packed, K_total, levels, D, ep_usage, ep_cnt, stats_out):
+    check(lib.vqb200_stats_finalize_packed(ptr(packed), K_total, int(levels), int(D), ptr(ep_usage), ptr(ep_cnt),
                                            ptr(stats_out), stream_ptr()), "vqb200_stats_finalize_packed")
     _count(1)
 
 
+@_on_device
 def scatter_add(z, idx, row_mask, seg_sum, seg_cnt):
     _need_cuda(z, idx, seg_sum)
     _f32c(z, "z")
@@ -256,6 +289,7 @@ def scatter_add(z, idx, row_mask, seg_sum, seg_cnt):
     _count(1)
 
 
+@_on_device
 def ema_finalize(seg_sum, seg_cnt, decay, eps, ema_cluster_size, ema_embedding, E, cache: CodebookCache):
     # the reference forms (1 - decay) in Python double and the multiply rounds it to fp32
     check(lib.vqb200_ema_finalize(ptr(seg_sum), ptr(seg_cnt), float(decay), float(1 - decay), float(eps),
@@ -265,6 +299,7 @@ def ema_finalize(seg_sum, seg_cnt, decay, eps, ema_cluster_size, ema_embedding, 
     _count(1)
 
 
+@_on_device
 def kmeans_finalize(seg_sum, seg_cnt, E, cache: CodebookCache):
     """Lloyd step: E[k] <- mean of the rows assigned to k (empty clusters keep their centroid) + cache refresh."""
     check(lib.vqb200_kmeans_finalize(ptr(seg_sum), ptr(seg_cnt), cache.K_total, cache.D, cache.K_per, ptr(E),
@@ -273,6 +308,7 @@ def kmeans_finalize(seg_sum, seg_cnt, E, cache: CodebookCache):
     _count(1)
 
 
+@_on_device
 def rvq_finalize(z, idx_level0, level_stride, L, E, zq_out=None, zq_st_out=None, sqerr_sum=None, hist=None):
     """Residual-VQ tail in one pass: z_q (level-order sum), z_q_st, squared error and histogram from the indices.
     ``idx_level0`` is level 0's id vector; level l's starts ``l * level_stride`` elements further on."""
@@ -284,6 +320,7 @@ def rvq_finalize(z, idx_level0, level_stride, L, E, zq_out=None, zq_st_out=None,
     _count(1)
 
 
+@_on_device
 def usage_probs(z, E):
     """(p_code [K], row_stats [N, 2]): p_code = mean_n softmax_k(z_n . e_k) (models/vq_vae.py:1305-1307)."""
     _need_cuda(z, E)
@@ -298,6 +335,7 @@ def usage_probs(z, E):
     return p_sum / max(N, 1), row_stats
 
 
+@_on_device
 def usage_probs_backward(z, E, row_stats, grad_p):
     N, D = z.shape
     out = torch.empty_like(z)
@@ -307,6 +345,7 @@ def usage_probs_backward(z, E, row_stats, grad_p):
     return out
 
 
+@_on_device
 def soft_assign(z, E, tau: float, out=None):
     """z_soft = softmax(-|z - e|^2 / tau) @ E (models/vq_vae.py:838-843), online softmax, nothing materialised."""
     _need_cuda(z, E)
@@ -321,6 +360,7 @@ def soft_assign(z, E, tau: float, out=None):
     return out
 
 
+@_on_device
 def commit_backward(grad_st, grad_commit, z, zq, scale, out):
     check(lib.vqb200_commit_backward(ptr(grad_st), ptr(grad_commit), ptr(z), ptr(zq), z.numel(), float(scale),
                                      ptr(out), stream_ptr()), "vqb200_commit_backward")
@@ -330,6 +370,7 @@ def commit_backward(grad_st, grad_commit, z, zq, scale, out):
 _IDX_BYTES = {torch.int16: 2, torch.int32: 4, torch.int64: 8}
 
 
+@_on_device
 def relayout_indices(idx_level_major: torch.Tensor, Q: int, B: int, M: int, dtype=torch.int64,
                      out: torch.Tensor | None = None) -> torch.Tensor:
     """Level-major flat RVQ ids [Q*B*M] -> token-major [B, M*Q] (optionally narrowed), on the device."""
@@ -347,6 +388,7 @@ def relayout_indices(idx_level_major: torch.Tensor, Q: int, B: int, M: int, dtyp
     return out
 
 
+@_on_device
 def indices_to_latent(idx: torch.Tensor, E: torch.Tensor, Q: int) -> torch.Tensor:
     """Token-major ids [n_tok*Q] -> z_q [n_tok, D], summing the Q levels in level order."""
     _need_cuda(idx, E)
@@ -364,6 +406,7 @@ def indices_to_latent(idx: torch.Tensor, E: torch.Tensor, Q: int) -> torch.Tenso
     return out
 
 
+@_on_device
 def search_packed(z, E_slice, ee_half_slice, idx_offset, packed_out):
     """Codebook-sharded search: packed[n] = key(d) << 32 | (idx_offset + argmin) over this shard's codes."""
     _need_cuda(z, E_slice, packed_out)
@@ -374,6 +417,7 @@ def search_packed(z, E_slice, ee_half_slice, idx_offset, packed_out):
     _count(1)
 
 
+@_on_device
 def minloc_unpack(packed, idx_out):
     check(lib.vqb200_minloc_unpack(ptr(packed), packed.numel(), ptr(idx_out), stream_ptr()),
           "vqb200_minloc_unpack")

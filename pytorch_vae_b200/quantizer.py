@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import math
 import os
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -39,6 +40,8 @@ class _QuantizeFn(torch.autograd.Function):
         stats = stats3[:2]
         commit = stats3[2]
         ctx.save_for_backward(z_e, z_q)
+        ctx.set_materialize_grads(False)     # an unused output arrives as None, not as a zero tensor: the pure
+                                             # straight-through backward (F.mse_loss on the reference side) launches nothing
         ctx.mark_non_differentiable(z_q, indices, stats)
         return z_q_st, z_q, indices, stats, commit
 
@@ -50,6 +53,8 @@ class _QuantizeFn(torch.autograd.Function):
         if g_commit is None:
             return g_st, None, None, None                     # pure straight-through: no kernel at all
         z = z_e.detach().contiguous()
+        if z.numel() == 0:
+            return torch.zeros_like(z_e), None, None, None
         out = torch.empty_like(z)
         gst = None if g_st is None else g_st.contiguous()
         gc = g_commit.to(torch.float32).contiguous()
@@ -235,8 +240,20 @@ class VectorQuantizerEMA(nn.Module):
         do_ema = bool(self.training and do_ema_update)
         z_q_st, z_q, indices, stats, commit = _QuantizeFn.apply(z_e, self, do_ema, mask)
         self.last_commit = commit
-        self._last_pair = (z_q, z_e)
+        self._last_pair = (weakref.ref(z_q), weakref.ref(z_e))   # identity check only: keeps no graph alive
         return z_q_st, z_q, indices, stats
+
+    # transient per-forward / per-device state: autograd-attached tensors, CUDA streams and events, the derived
+    # codebook cache.  Never part of a copy or a pickle (copy.deepcopy(model) after a training forward would
+    # otherwise fail on the non-leaf ``last_commit``); all of it is rebuilt on the next forward.
+    _TRANSIENT = ("last_commit", "_last_pair", "_hpipe", "_cache")
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        for k in self._TRANSIENT:
+            if k in state:
+                state[k] = None
+        return state
 
     @torch.no_grad()
     def soft_forward(self, z_e: Tensor, tau: float, do_ema_update: bool = True):
@@ -279,7 +296,7 @@ class VectorQuantizerEMA(nn.Module):
         """``F.mse_loss(z_q.detach(), z_e)`` (models/vq_vae.py:1293).  When called with the pair the
         last forward produced, returns the value the gather pass already accumulated (its backward is
         the fused commit_backward kernel); otherwise runs the fused st_loss kernel on the pair."""
-        if self._last_pair is not None and z_q is self._last_pair[0] and z_e is self._last_pair[1]:
+        if self._last_pair is not None and z_q is self._last_pair[0]() and z_e is self._last_pair[1]():
             return self.last_commit
         return _CommitFn.apply(z_e, z_q.detach())
 
@@ -514,6 +531,9 @@ class VectorQuantizerEMA(nn.Module):
             idx_ret = out_indices.view(B, M * L)
         else:
             idx_ret = out_indices.view(B, M) if L == 1 else out_indices.view(-1)
+        if wait:
+            stats_h = stats_h.clone()     # the pinned staging buffer is shared by every call on this device; with
+                                          # wait=False the caller reads it after its own synchronise, before the next call
         if not want_all:
             return None, None, idx_ret, stats_h
         return z_q_st.view(B, M, D), z_q.view(B, M, D), idx_ret, stats_h
@@ -536,7 +556,7 @@ class VectorQuantizerEMA(nn.Module):
             pack = torch.empty(self.K + 2, dtype=torch.float64, device=hist.device)
             ops.stats_pack(hist, sqerr, n_elems, pack)
             torch.distributed.all_reduce(pack)
-            ops.stats_finalize_packed(pack, self.K, count_add, self._ep_usage, self._ep_cnt, stats3)
+            ops.stats_finalize_packed(pack, self.K, self.num_quantizers, self.D, self._ep_usage, self._ep_cnt, stats3)
             return
         ops.stats_finalize(hist, count_add, sqerr, 1.0 / max(n_elems, 1), self._ep_usage, self._ep_cnt, stats3)
 

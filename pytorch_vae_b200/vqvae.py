@@ -74,8 +74,16 @@ class VQVAE(nn.Module):
                  tokenizer_layers: int = 2, tokenizer_dropout: float = 0.1, latent_sigmoid: bool = False,
                  latent_sigmoid_ae_only: bool = True, reinit_dead_codes: bool = True, reinit_prob: float = 1.0,
                  dead_usage_threshold: int = 0, ema_update_freeze_steps: int = 0, print_init: bool = True,
-                 search_mode: str = "fp32", **kwargs):
+                 search_mode: str = "fp32", rigid_aug_prob: float = 0.0, max_noise_std: float = 0.0,
+                 noise_warmup_steps: int = 0, **kwargs):
         super().__init__()
+        # input augmentations of the reference's forward (models/vq_vae.py:775-792) are not on the hot path and are
+        # not mirrored: refuse them loudly instead of silently training without them
+        if float(rigid_aug_prob) != 0.0 or float(max_noise_std) != 0.0:
+            raise NotImplementedError("rigid_aug_prob / max_noise_std != 0: input augmentation is outside the hot path; "
+                                      "train with the reference VQVAE and pytorch_vae_b200.install()")
+        self.rigid_aug_prob, self.max_noise_std = 0.0, 0.0
+        self.noise_warmup_steps = int(noise_warmup_steps)
         self.soft_vq_use = bool(soft_vq_use)                # models/vq_vae.py:436-440
         self.soft_vq_tau_start, self.soft_vq_tau_end = float(soft_vq_tau_start), float(soft_vq_tau_end)
         self.soft_vq_tau_warm_steps = int(soft_vq_tau_warm_steps)
@@ -238,6 +246,7 @@ class VQVAE(nn.Module):
             self.training_steps += 1
         z_e = self._tokenize_to_codes(h_fuse, mask)
 
+        do_ema = False
         if not self.use_vq or self.quantizer is None:
             z_dec, z_q_raw = z_e, z_e
             indices = torch.zeros(z_e.size(0), z_e.size(1), dtype=torch.long, device=z_e.device)
@@ -259,11 +268,12 @@ class VQVAE(nn.Module):
             do_ema = self.training and self.training_steps >= self.ema_update_freeze_steps
             z_dec, z_q_raw, indices, stats = self.quantizer(z_e, do_ema_update=do_ema, allow_reinit=do_ema, mask=None)
             ppl, dead = stats[0], stats[1]
-            # dead-code re-init cadence, models/vq_vae.py:874-891 (every 500 steps once training_steps >= 800)
-            if self.training and do_ema and self.training_steps % 500 == 0 and \
-                    self.training_steps >= max(self.ema_update_freeze_steps, 800):
-                usage = torch.bincount(indices.reshape(-1), minlength=self.quantizer.K).float()
-                self.quantizer._maybe_reinit_dead_codes(z_e.detach().reshape(-1, z_e.size(-1)), usage)
+        # dead-code re-init cadence, models/vq_vae.py:874-891: AFTER the soft / hard branch, for both of them
+        # (every 500 steps once training_steps >= max(freeze, 800)), gated on the branch's do_ema_update
+        if self.use_vq and self.quantizer is not None and self.training and do_ema and \
+                self.training_steps % 500 == 0 and self.training_steps >= max(self.ema_update_freeze_steps, 800):
+            usage = torch.bincount(indices.reshape(-1), minlength=self.quantizer.K).float()
+            self.quantizer._maybe_reinit_dead_codes(z_e.detach().reshape(-1, z_e.size(-1)), usage)
 
         recons = self.decode(z_dec, mask=mask)
         return [recons, target, (z_q_raw, z_e, indices, ppl, dead), mask]

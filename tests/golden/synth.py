@@ -25,3 +25,8 @@ def large_case_inputs(seed, K_per, D, L, B, M, scale=None, clustered=False):
         src = rs.randint(0, K_per, size=(B, M))
         z = (E[src] + 0.1 / np.sqrt(D) * rs.standard_normal((B, M, D))).astype(np.float32)
     return E, z
+
+
+def train_step_inputs(seed, step, B, M, D):
+    """Latents of training step ``step`` of a train_golden.npz case (fresh rows every step)."""
+    return np.random.RandomState(seed + 10 + step).standard_normal((B, M, D)).astype(np.float32)

@@ -458,9 +458,9 @@ def test_packed_statistics_equal_direct(vq, dev):
     pack = torch.empty(K + 2, dtype=torch.float64, device=dev)
     vq.ops.stats_pack(hist, sq, n_elems, pack)
     assert float(pack[0]) == 123.456 and float(pack[1]) == n_elems and torch.equal(pack[2:].to(torch.int32), hist)
-    vq.ops.stats_finalize_packed(pack, K, 4096.0, ub, cb, b)
+    vq.ops.stats_finalize_packed(pack, K, 1, 64, ub, cb, b)          # 4096 * 64 elements, D = 64 -> 4096 positions
     assert torch.equal(a, b) and torch.equal(ua, ub) and torch.equal(ca, cb)
-    vq.ops.stats_finalize_packed(pack * 2, K, 4096.0, ub, cb, b)      # two identical ranks: same statistics
+    vq.ops.stats_finalize_packed(pack * 2, K, 1, 64, ub, cb, b)       # two identical ranks: same statistics
     np.testing.assert_allclose(npy(a), npy(b), rtol=1e-6)
 
 

@@ -228,3 +228,48 @@ def test_oracle_usage_entropy_matches_live_reference():
         np.testing.assert_allclose(p.sum(), 1.0, rtol=1e-5)
         scale = np.abs(g[f"{tag}/grad"]).max()
         np.testing.assert_allclose(grad, g[f"{tag}/grad"], rtol=2e-3, atol=2e-4 * scale)
+
+
+@pytest.mark.parametrize("name", ["c5_train", "c2_train"])
+def test_oracle_training_steps_match_live_reference(name):
+    """tests/golden/train_golden.npz (make_golden_train.py): three training-mode forwards of the live reference from
+    ZERO EMA buffers at the stage-2 shape (4 x 1024, D = 512, 8192 rows) and at K = 512 / D = 64 -- the codebook
+    collapses to exact duplicates after the first update.  The oracle reproduces indices, statistics and buffers."""
+    import os
+
+    from synth import train_step_inputs
+    from oracle.replay import chain_alive, replay_step
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "train_golden.npz"))
+    seed, K_per, D, L, B, M, steps = (int(v) for v in g[f"{name}/meta"])
+    E, _ = large_case_inputs(seed, K_per, D, L, 1, 1)
+    q = O.OracleQuantizer(K_per, D, num_quantizers=L, embedding=E, decay=float(g[f"{name}/decay"]))
+    q.training = True
+    rows = g[f"{name}/rows"]
+    identical = True
+    for s in range(steps):
+        z = train_step_inputs(seed, s, B, M, D)
+        p = f"{name}/step{s}"
+        shadow = O.OracleQuantizer(K_per, D, num_quantizers=L, embedding=q.embedding.copy(), decay=q.decay)
+        shadow.ema_cluster_size, shadow.ema_embedding = q.ema_cluster_size.copy(), q.ema_embedding.copy()
+        st, zq, idx, stats = q.forward(z, do_ema_update=True)
+        ref = g[f"{p}/idx"].astype(np.int64).reshape(idx.shape)
+        first, frac = chain_alive(idx, ref, L)
+        assert sum(f.size for f in first) <= 2 and frac > 0.999
+        identical &= np.array_equal(idx.reshape(-1), ref.reshape(-1))
+        # the replay helper the GPU tests use agrees with the oracle's own forward
+        rep = replay_step(shadow, z, idx)
+        assert rep["outside"] == [0] * L and rep["mismatch"] == [0] * L
+        assert np.array_equal(rep["zq"], zq)
+        np.testing.assert_allclose(shadow.embedding, q.embedding, rtol=0, atol=0)
+        if identical:
+            np.testing.assert_allclose(stats, g[f"{p}/stats"], rtol=1e-5)
+            np.testing.assert_allclose(O.commitment_mse(zq, z), float(g[f"{p}/commit"]), rtol=1e-5)
+            np.testing.assert_allclose(q.ema_cluster_size, g[f"{p}/ema_cluster_size"], rtol=1e-6, atol=1e-7)
+            for buf in ("embedding", "ema_embedding"):
+                a = getattr(q, buf)
+                nrm = np.sqrt((a.astype(np.float64) ** 2).sum(1))
+                np.testing.assert_allclose(nrm, g[f"{p}/{buf}_norm"], rtol=1e-5, atol=1e-6)
+                np.testing.assert_allclose(a[rows], g[f"{p}/{buf}_rows"], rtol=1e-5, atol=1e-6)
+            assert int((np.abs(q.embedding).sum(1) == 0).sum()) == int(g[f"{p}/n_zero_codes"])
+            if f"{p}/embedding" in g.files:
+                np.testing.assert_allclose(q.embedding, g[f"{p}/embedding"], rtol=1e-5, atol=1e-6)
