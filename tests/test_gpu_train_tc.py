@@ -10,7 +10,8 @@ the dead-code de-duplication of codebook_refresh_kernel is on the path.
 Checked against (a) the live reference's outputs (tests/golden/train_golden.npz, make_golden_train.py) and
 (b) the numpy oracle through the teacher-forced replay of oracle/replay.py.  Tolerances: indices equal to
 the oracle's except near-ties (fp64 gap < 1e-6 relative, none outside), z_q bit-exact from the pre-update
-codebook of the first step, loss 1e-5, ema_cluster_size 1e-6, ema_embedding / embedding 1e-5 (scatter-add order).
+codebook of the first step, loss 1e-5, ema_cluster_size 1e-6, ema_embedding / embedding 1e-5 relative + 2e-6 of the
+buffer's largest magnitude (fp32 summation order of segment sums with up to 8192 terms).
 """
 import os
 
@@ -94,8 +95,11 @@ def run_case(vq, dev, name, expect_fused, graph=False):
         usage, ppl, dead = O.usage_stats(idx_n, K_per * L)
         np.testing.assert_allclose(npy(stats), [ppl, dead], rtol=1e-5)
         np.testing.assert_allclose(npy(q.ema_cluster_size), oq.ema_cluster_size, rtol=1e-6, atol=1e-7)
-        np.testing.assert_allclose(npy(q.ema_embedding), oq.ema_embedding, rtol=1e-5, atol=1e-6)
-        np.testing.assert_allclose(npy(q.embedding), oq.embedding, rtol=1e-5, atol=1e-6)
+        # segment sums of up to 8192 rows (a collapsed level sends every row to ONE code): 1e-5 relative plus the
+        # fp32 summation-order noise of such a sum, 2e-6 of the buffer's largest magnitude (observed: 1.1e-6 on 2 of
+        # 2 M elements; the reference's own one-hot GEMM carries the same noise)
+        for got, want in ((npy(q.ema_embedding), oq.ema_embedding), (npy(q.embedding), oq.embedding)):
+            np.testing.assert_allclose(got, want, rtol=1e-5, atol=2e-6 * max(1.0, float(np.abs(want).max())))
         # collapsed codes are EXACTLY zero on both sides (0 / (0 + eps))
         assert np.array_equal(np.abs(npy(q.embedding)).sum(1) == 0, np.abs(oq.embedding).sum(1) == 0)
 
