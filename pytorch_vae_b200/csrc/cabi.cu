@@ -71,7 +71,7 @@ int vqb200_timing_collect(float* total_ms, int* n_launches) {
 
 int vqb200_search_path(int64_t N, int K, int D, int mode) {
   (void)mode;
-  return tc_supported(N, K, D) ? 1 : 0;
+  return tc_supported(N, K, D) ? (tc_side_pipeline(N, K, D) ? 2 : 1) : 0;
 }
 
 int vqb200_codebook_prepare(const float* E, int K_total, int D, int K_per, uint16_t* E_bf16, float* ee_half,

@@ -117,6 +117,7 @@ int launch_search_simt_list(const float* z, const int32_t* row_list, const int* 
 bool tc_supported(int64_t N, int K, int D);
 size_t tc_workspace_bytes(int64_t N, int K, int D);
 int tc_launches(int64_t N, int K, int D);
+bool tc_side_pipeline(int64_t N, int K, int D);   // several chunks on the CTA-pair kernel with side jobs (vq_search_tc.cu)
 // optional gather stage appended to each chunk of the tensor-core search pipeline
 struct GatherArgs {
   const float* E_full;      // [K_total, D] (idx_out holds GLOBAL ids)

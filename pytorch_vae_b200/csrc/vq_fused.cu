@@ -401,7 +401,13 @@ quantize_fused_kernel(const __grid_constant__ CUtensorMap tmap_zf, const __grid_
     const int64_t total_tiles = static_cast<int64_t>((n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                                                      static_cast<int>(gridDim.x)) * p.code_tiles;
     int64_t la = 0;                                   // index into the sequence of the next tile to fetch
-    auto la_next = [&]() -> int { return la < total_tiles ? static_cast<int>((la++) % p.code_tiles) : (la++, -1); };
+    int la_t = 0;                                     // its code tile (kept incrementally: no division per tile)
+    auto la_next = [&]() -> int {
+      if (la++ >= total_tiles) return -1;
+      const int t = la_t;
+      la_t = (la_t + 1 == p.code_tiles) ? 0 : la_t + 1;
+      return t;
+    };
     for (uint32_t b = 0; b < 2; ++b) {
       const int tt = la_next();
       if (tt >= 0) preload(load_bias(tt), b);

@@ -21,6 +21,7 @@
 //                              (2 buffers x BM/128 halves x 128 columns = all 512 columns at BM=256)
 //   warps 2+ : epilogue      - tcgen05.ld 32 columns at a time, subtract |e|^2/2, running max and
 //                              candidate append; overlaps the MMAs of the next code tile
+#include <cstdio>
 #include <cstdlib>
 
 #include "tc_ptx.cuh"
@@ -129,6 +130,7 @@ struct TcParams {
   uint2* cand;           // [n_rows][ksplit][TC_SLOTS] records {code group << 8 | admit mask, group max}
   int* cnt;              // [n_rows][ksplit]
   float* best;           // [n_rows][ksplit]
+  long long* clk;        // VQB200_DEBUG=4: per CTA [clock64, globaltimer] at start and at end (effective SM clock)
 };
 
 // Scan 32 accumulator columns of one row.  The accumulator was pre-loaded with -|e|^2/2, so the TMEM words ARE
@@ -417,6 +419,152 @@ search_tc_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_consta
 // Protocol: the leader CTA (rank 0) issues every MMA.  Both CTAs' TMA loads credit the LEADER's full / z-full
 // barriers; MMA completions are committed with a multicast arrive to the barriers at the same offsets in both
 // CTAs; both CTAs' epilogue warps arrive (remotely for the peer) on the leader's tmem-empty barriers.
+// ---- side jobs: HBM-bound streaming work of the NEIGHBOURING chunks, run by extra warps of the persistent tensor
+// kernel.  The tensor kernel fills every SM (one CTA, ~218 KB of shared memory), so no other kernel co-resides with
+// it and the chunk pipeline's side passes -- the pre-pass of the next chunk (fp32 -> 16-bit operand + margins,
+// 6 D bytes per row) and the gather / straight-through / loss / histogram pass of the previous chunk (12 D bytes per
+// row), both at the HBM roofline when run alone -- used to sit BETWEEN the tensor kernels: 4.5 ms of a 16.4 ms step
+// at K = 8192, D = 256, N = 2^22.  Six extra warps per CTA stream that work while the tensor pipe is busy: it needs
+// ~1.5 TB/s of the 6.5 TB/s HBM and ~2 % of the issue slots, and touches neither the TMA / MMA / epilogue protocol
+// nor their registers (setmaxnreg gives the epilogue warp groups 168 registers, everything else 88).
+struct SideJobs {
+  int D, mode;
+  // gather of an EARLIER chunk (its indices are final: re-rank and hand-back ran before this launch)
+  const float* g_z; const int64_t* g_idx; int64_t g_rows;
+  const float* g_E; int g_K_total;
+  float* g_zq; float* g_zq_st; double* g_sqerr; int32_t* g_hist; const uint8_t* g_mask;
+  // pre-pass of a LATER chunk
+  const float* p_z; int64_t p_rows; __nv_bfloat16* p_zb; float* p_margin; const float* level_meta;
+};
+
+// One warp per row, SL float4 slices per lane (D = 128 SL), RB rows in flight.
+template <int SL>
+__device__ __forceinline__ void side_gather(const SideJobs& sj, int64_t w0, int64_t nw, int lane) {
+  constexpr int RB = SL == 1 ? 6 : (SL == 2 ? 3 : (SL == 3 ? 2 : 1));   // 48 data registers in flight (32 at D = 512)
+  const int D4 = SL * 32;
+  const float4* Z = reinterpret_cast<const float4*>(sj.g_z);
+  const float4* E = reinterpret_cast<const float4*>(sj.g_E);
+  float4* ZQ = reinterpret_cast<float4*>(sj.g_zq);
+  float4* ST = reinterpret_cast<float4*>(sj.g_zq_st);
+  float err = 0.f;
+  for (int64_t r0 = w0 * RB; r0 < sj.g_rows; r0 += nw * RB) {
+    int k[RB];
+    float4 v[RB][SL], e[RB][SL];
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int64_t row = r0 + u;
+      k[u] = -1;
+      if (row < sj.g_rows) {
+        const int64_t kk = sj.g_idx[row];
+        k[u] = (kk >= 0 && kk < sj.g_K_total) ? static_cast<int>(kk) : -1;
+#pragma unroll
+        for (int s = 0; s < SL; ++s) v[u][s] = ld_stream(Z + row * D4 + s * 32 + lane);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RB; ++u)
+      if (k[u] >= 0) {
+#pragma unroll
+        for (int s = 0; s < SL; ++s) e[u][s] = __ldg(E + static_cast<int64_t>(k[u]) * D4 + s * 32 + lane);
+      }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      if (k[u] < 0) continue;
+      const int64_t row = r0 + u;
+#pragma unroll
+      for (int s = 0; s < SL; ++s) {
+        const float4 q = e[u][s], zz = v[u][s];
+        float4 df;
+        df.x = __fsub_rn(q.x, zz.x); df.y = __fsub_rn(q.y, zz.y); df.z = __fsub_rn(q.z, zz.z); df.w = __fsub_rn(q.w, zz.w);
+        if (ZQ) st_stream(ZQ + row * D4 + s * 32 + lane, q);
+        if (ST) st_stream(ST + row * D4 + s * 32 + lane,
+                          make_float4(__fadd_rn(zz.x, df.x), __fadd_rn(zz.y, df.y), __fadd_rn(zz.z, df.z), __fadd_rn(zz.w, df.w)));
+        err = fmaf(df.x, df.x, err); err = fmaf(df.y, df.y, err); err = fmaf(df.z, df.z, err); err = fmaf(df.w, df.w, err);
+      }
+      if (sj.g_hist && lane == 0 && (!sj.g_mask || sj.g_mask[row])) atomicAdd(sj.g_hist + k[u], 1);
+    }
+  }
+  if (sj.g_sqerr) {
+    const double t = warp_sum(static_cast<double>(err));
+    if (lane == 0 && t != 0.0) atomicAdd(sj.g_sqerr, t);
+  }
+}
+
+template <int SL>
+__device__ __forceinline__ void side_prep(const SideJobs& sj, int64_t w0, int64_t nw, int lane) {
+  constexpr int RB = SL == 1 ? 6 : (SL == 2 ? 3 : (SL == 3 ? 2 : 1));   // 48 data registers in flight (32 at D = 512)
+  const int D4 = SL * 32, D = SL * 128;
+  const bool bfm = sj.mode == VQB200_MODE_BF16_INPUT;
+  const float emax = bfm ? sj.level_meta[2] : sj.level_meta[0];
+  const float emax_lp = sj.level_meta[4], rho_e = sj.level_meta[5];
+  const bool code_bad = sj.level_meta[1] != 0.f;
+  const float coef = 2.f * static_cast<float>(D + 32) * 1.1920929e-7f;
+  const float4* Z = reinterpret_cast<const float4*>(sj.p_z);
+  uint2* ZB = reinterpret_cast<uint2*>(sj.p_zb);
+  for (int64_t r0 = w0 * RB; r0 < sj.p_rows; r0 += nw * RB) {
+    float4 v[RB][SL];
+#pragma unroll
+    for (int u = 0; u < RB; ++u)
+      if (r0 + u < sj.p_rows) {
+#pragma unroll
+        for (int s = 0; s < SL; ++s) v[u][s] = ld_stream(Z + (r0 + u) * D4 + s * 32 + lane);
+      }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      const int64_t row = r0 + u;
+      if (row >= sj.p_rows) continue;                       // warp-uniform
+      float ss = 0.f, sse = 0.f;
+#pragma unroll
+      for (int s = 0; s < SL; ++s) {
+        const float4 x = v[u][s];
+        uint2 pk;
+        float f0, f1, f2, f3;
+        if (bfm) {
+          const __nv_bfloat162 a = __floats2bfloat162_rn(x.x, x.y), b = __floats2bfloat162_rn(x.z, x.w);
+          pk.x = *reinterpret_cast<const uint32_t*>(&a); pk.y = *reinterpret_cast<const uint32_t*>(&b);
+          f0 = __uint_as_float(pk.x << 16); f1 = __uint_as_float(pk.x & 0xffff0000u);
+          f2 = __uint_as_float(pk.y << 16); f3 = __uint_as_float(pk.y & 0xffff0000u);
+          ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
+        } else {
+          pk.x = f16x2_bits_flush(x.x, x.y); pk.y = f16x2_bits_flush(x.z, x.w);
+          const float2 g0 = f16x2_bits_to_float2(pk.x), g1 = f16x2_bits_to_float2(pk.y);
+          f0 = g0.x; f1 = g0.y; f2 = g1.x; f3 = g1.y;
+          ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+          const float d0 = x.x - f0, d1 = x.y - f1, d2 = x.z - f2, d3 = x.w - f3;      // exact differences
+          sse += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+        ZB[row * D4 + s * 32 + lane] = pk;
+      }
+      ss = warp_sum(ss);
+      sse = warp_sum(sse);
+      if (lane == 0) {
+        float m = bfm ? coef * (sqrtf(ss) * 1.0001f) * emax + 1e-30f : admission_margin_fp32(ss, sse, emax, emax_lp, rho_e, D);
+        if (code_bad || !(ss < __int_as_float(0x7f800000)) || !(sse < __int_as_float(0x7f800000)))
+          m = __int_as_float(0x7fc00000);   // NaN: exact path
+        sj.p_margin[row] = m;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void run_side_jobs(const SideJobs& sj, int side_warp, int n_side, int lane) {
+  const int64_t w0 = static_cast<int64_t>(blockIdx.x) * n_side + side_warp;
+  const int64_t nw = static_cast<int64_t>(gridDim.x) * n_side;
+  const int SL = sj.D >> 7;
+  if (sj.g_rows > 0) {
+    if (SL == 1) side_gather<1>(sj, w0, nw, lane);
+    else if (SL == 2) side_gather<2>(sj, w0, nw, lane);
+    else if (SL == 3) side_gather<3>(sj, w0, nw, lane);
+    else side_gather<4>(sj, w0, nw, lane);
+  }
+  if (sj.p_rows > 0) {
+    if (SL == 1) side_prep<1>(sj, w0, nw, lane);
+    else if (SL == 2) side_prep<2>(sj, w0, nw, lane);
+    else if (SL == 3) side_prep<3>(sj, w0, nw, lane);
+    else side_prep<4>(sj, w0, nw, lane);
+  }
+}
+
 constexpr int P2_ROWS = 128;        // rows per CTA
 constexpr int P2_BN = 256;          // codes per pair tile (each CTA stages 128 of them)
 constexpr int P2_CS = 2;            // column slices: 8 epilogue warps = 4 lane quarters x 2 slices of 128 columns
@@ -427,10 +575,14 @@ constexpr int P2_WCOLS = P2_BN / P2_CS;
 // 4096 registers free in every scheduler partition, which is what lets ONE 256-thread block of the chunk
 // pipeline's side kernels (pre-pass, re-rank, gather: <= 64 registers) co-reside with this persistent kernel
 // (an experiment switch: see launch_search_tc for the measurement; the default build is uncapped).
-template <int REGS>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(REGS)
-search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
-                  const TcParams p) {
+// SIDE = 0: ten warps (TMA, MMA, 8 epilogue).  SIDE = 6: sixteen warps in four warp groups -- {TMA, MMA, side, side},
+// {epilogue x4}, {epilogue x4}, {side x4} -- launched at 128 registers per thread; the epilogue groups then take 168
+// and the others give back down to 88 (setmaxnreg), and the side warps run the SideJobs.
+constexpr int P2_SIDE = 6;
+template <int SIDE>
+__device__ __forceinline__ void search_tc2_body(const CUtensorMap& tmap_z, const CUtensorMap& tmap_e, const TcParams& p,
+                                                const SideJobs& sj) {
+  constexpr int EPI0 = SIDE > 0 ? 4 : 2;               // first epilogue warp (a warp may touch TMEM lanes 32 (w % 4) ...)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int KBLK = p.D / TC_KB;
@@ -467,6 +619,14 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
   const int n_items = p.row_tiles;                     // 256-row tiles, one per pair step
+  if (p.clk && threadIdx.x == 0) {
+    long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.clk[blockIdx.x * 4 + 0] = clock64(); p.clk[blockIdx.x * 4 + 1] = g;
+  }
+  if (SIDE > 0) {
+    if (warp >= EPI0 && warp < EPI0 + P2_NEPI) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  }
 
   if (warp == 0) {
     // ============================== TMA producer (both CTAs) ==============================
@@ -530,9 +690,12 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_const
         __syncwarp();
       }
     }
+  } else if (SIDE > 0 && (warp < EPI0 || warp >= EPI0 + P2_NEPI)) {
+    // ============================== side warps: streaming work of the neighbouring chunks ==============================
+    run_side_jobs(sj, warp < EPI0 ? warp - 2 : warp - (EPI0 + P2_NEPI) + 2, SIDE, lane);
   } else {
     // ============================== epilogue (both CTAs, own TMEM) ==============================
-    const int we = warp - 2;
+    const int we = warp - EPI0;
     const int quarter = warp & 3;
     const int cs = we >> 2;
     float* ee_slot = reinterpret_cast<float*>(gen + (ee_smem - base)) + we * P2_WCOLS;
@@ -570,7 +733,13 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_const
     };
     const int64_t total_tiles = static_cast<int64_t>((n_items - pair + n_pairs - 1) / n_pairs) * p.code_tiles;
     int64_t la = 0;
-    auto la_next = [&]() -> int { return la < total_tiles ? static_cast<int>((la++) % p.code_tiles) : (la++, -1); };
+    int la_t = 0;                                       // code tile of sequence position la (no division per tile)
+    auto la_next = [&]() -> int {
+      if (la++ >= total_tiles) return -1;
+      const int t = la_t;
+      la_t = (la_t + 1 == p.code_tiles) ? 0 : la_t + 1;
+      return t;
+    };
     for (uint32_t b = 0; b < 2; ++b) {
       const int tt = la_next();
       if (tt >= 0) preload(load_bias(tt), b);
@@ -624,11 +793,31 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (p.clk && threadIdx.x == 0) {
+    long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.clk[blockIdx.x * 4 + 2] = clock64(); p.clk[blockIdx.x * 4 + 3] = g;
+  }
   cluster_sync_all();                                  // neither CTA leaves while the peer may still touch it
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+}
+
+template <int REGS>
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(REGS)
+search_tc2_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
+                  const TcParams p) {
+  SideJobs none;
+  none.g_rows = 0; none.p_rows = 0;
+  search_tc2_body<0>(tmap_z, tmap_e, p, none);
+}
+
+// the same with six side warps (sixteen warps: 128 registers per thread at launch, re-divided by setmaxnreg)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 256 + 32 * P2_SIDE, 1)
+search_tc2_side_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
+                       const TcParams p, const SideJobs sj) {
+  search_tc2_body<P2_SIDE>(tmap_z, tmap_e, p, sj);
 }
 
 // ------------------------------------------------------------------------------------ exact re-rank
@@ -920,12 +1109,7 @@ size_t tc_workspace_bytes(int64_t N, int K, int D) {
   return tc_set_bytes(rows, D, pl.BM) * (N > pl.chunk_rows ? 2 : 1);
 }
 
-int tc_launches(int64_t N, int K, int D) {
-  TcPlan pl;
-  if (!tc_plan(N, K, D, &pl)) return 0;
-  const int64_t chunks = (N + pl.chunk_rows - 1) / pl.chunk_rows;
-  return static_cast<int>(chunks) * 5;   // zprep, tcgen05 search, re-rank, SIMT hand-back, unpack
-}
+int tc_launches(int64_t N, int K, int D);
 
 // Helper streams for the chunk pipeline (created once per device, never destroyed).
 struct TcPipe {
@@ -980,10 +1164,52 @@ static TcSet carve(uint8_t* w, int64_t cap, int D, int BM) {
     if (e_ != cudaSuccess) return status_of(e_); \
   } while (0)
 
-// The search over N rows runs chunk by chunk through three stages -- pre-pass, tcgen05 kernel, re-rank (+ exact
-// hand-back) -- and, with more than one chunk, the stages of neighbouring chunks overlap on three streams:
-// the pre-pass and re-rank kernels are short and latency-bound, the tensor kernel is persistent with one CTA per
-// SM, so they co-reside.  Everything is joined back into the caller's stream before returning.
+// Does the side-job pipeline apply?  Several chunks, every chunk large enough for the CTA-pair kernel, D a multiple
+// of 128 (one warp covers a row with whole float4 slices), not switched off (VQB200_TC2_SIDE=0).
+static bool tc_pair_allowed(int K, int D, int* stages2_out, int* zbufs2_out) {
+  const char* env2 = std::getenv("VQB200_TC2");
+  const bool want2 = !(env2 && env2[0] == '0');
+  const int z2 = P2_ROWS * D * 2;
+  const int zbufs2 = (2 * z2 + 4 * TC_STAGE_BYTES + P2_NEPI * P2_WCOLS * 4 + 2048 <= TC_SMEM_LIMIT) ? 2 : 1;
+  int stages2 = (TC_SMEM_LIMIT - (1024 + zbufs2 * z2 + P2_NEPI * P2_WCOLS * 4 + 256)) / TC_STAGE_BYTES;
+  if (stages2 > 8) stages2 = 8;
+  if (stages2_out) *stages2_out = stages2;
+  if (zbufs2_out) *zbufs2_out = zbufs2;
+  return want2 && stages2 >= 3 && K >= P2_BN;
+}
+static constexpr int64_t kPairMinRows = static_cast<int64_t>(kNumSMs / 2) * 2 * P2_ROWS;
+
+bool tc_side_pipeline(int64_t N, int K, int D) {
+  TcPlan pl;
+  if (!tc_plan(N, K, D, &pl)) return false;
+  // OPT-IN (VQB200_TC2_SIDE=1 | p | g | i).  Measured on the B200 pool (profiles/r02_c3_side_variants.txt, c3,
+  // 2^22 rows): the tensor kernel runs power-capped at ~1.39 GHz effective (clock64 / globaltimer), 4.2 M cycles per
+  // 2^20-row launch; with the side warps streaming it needs 5.6 M cycles at the same clock (4.0 ms instead of 3.4)
+  // and the step goes from 17.4 to 18.3 ms -- everything that shares an SM with the epilogue costs more than the
+  // overlap returns, exactly as the co-resident side KERNELS did in round 1.  Kept as a tested switch.
+  const char* es = std::getenv("VQB200_TC2_SIDE");
+  if (!es || es[0] == '0') return false;
+  if (N <= pl.chunk_rows || D % 128 != 0) return false;
+  const int64_t last = N - ((N - 1) / pl.chunk_rows) * pl.chunk_rows;
+  return tc_pair_allowed(K, D, nullptr, nullptr) && pl.chunk_rows >= kPairMinRows && last >= kPairMinRows;
+}
+
+int tc_launches(int64_t N, int K, int D) {
+  TcPlan pl;
+  if (!tc_plan(N, K, D, &pl)) return 0;
+  const int chunks = static_cast<int>((N + pl.chunk_rows - 1) / pl.chunk_rows);
+  // per chunk: pre-pass, tcgen05 search, re-rank, SIMT hand-back, unpack; with the side-job pipeline only the first
+  // chunk has a pre-pass of its own
+  return tc_side_pipeline(N, K, D) ? chunks * 4 + 1 : chunks * 5;
+}
+
+// The search over N rows runs chunk by chunk through pre-pass -> tcgen05 kernel -> re-rank (+ exact hand-back)
+// [-> gather].  Two schedules:
+//  * side-job pipeline (several chunks, CTA-pair kernel, D % 128 == 0): ONE stream; the tensor kernel of chunk i
+//    carries, on six extra warps, the pre-pass of chunk i+1 and the gather of chunk i-1 (see SideJobs), so only the
+//    first pre-pass, the small re-rank kernels and the last gather run outside a tensor kernel;
+//  * otherwise: the stages of neighbouring chunks on three streams (they serialise against the persistent tensor
+//    kernel, but the launch gaps overlap), joined back into the caller's stream before returning.
 int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                      int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s, const GatherArgs* ga,
@@ -994,7 +1220,15 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
   const int64_t cap = N < pl.chunk_rows ? N : pl.chunk_rows;
   const int n_chunks = static_cast<int>((N + pl.chunk_rows - 1) / pl.chunk_rows);
-  TcPipe* pipe = n_chunks > 1 ? tc_pipe() : nullptr;
+  const bool side = !prep && tc_side_pipeline(N, K, D);
+  // measurement switches: VQB200_TC2_SIDE=i keeps the sixteen-warp kernel but leaves its side warps idle (the
+  // pre-pass and the gather run as separate kernels), =g / =p give them only the gather / only the pre-pass
+  const char* esv = std::getenv("VQB200_TC2_SIDE");
+  const char sv = esv ? esv[0] : '0';
+  const bool side_gather_on = sv != 'i' && sv != 'p', side_prep_on = sv != 'i' && sv != 'g';
+  const char* edbg = std::getenv("VQB200_DEBUG");
+  const bool clk_dbg = edbg && edbg[0] == '4';
+  TcPipe* pipe = (n_chunks > 1 && !side) ? tc_pipe() : nullptr;
   const bool piped = pipe != nullptr;
   // VQB200_TC_PRIO=1 runs the tensor kernel on a high-priority helper stream (measured: 17.9 ms against 17.4 ms
   // per c3 step on the caller's stream -- nothing co-resides with the persistent kernel, so priority only adds
@@ -1013,17 +1247,13 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   const int code_tiles = (K + TC_BN - 1) / TC_BN;
 
   // CTA-pair kernel (cta_group::2): large row counts only (no code splits), z tile of 128 rows must fit
-  const char* env2 = std::getenv("VQB200_TC2");
-  const bool want2 = !(env2 && env2[0] == '0');
+  int stages2 = 0, zbufs2 = 1;
   const int z2 = P2_ROWS * D * 2;
-  const int zbufs2 = (2 * z2 + 4 * TC_STAGE_BYTES + P2_NEPI * P2_WCOLS * 4 + 2048 <= TC_SMEM_LIMIT) ? 2 : 1;
-  int stages2 = (TC_SMEM_LIMIT - (1024 + zbufs2 * z2 + P2_NEPI * P2_WCOLS * 4 + 256)) / TC_STAGE_BYTES;
-  if (stages2 > 8) stages2 = 8;
-  const bool use2 = want2 && stages2 >= 3 && K >= P2_BN && cap >= static_cast<int64_t>(kNumSMs / 2) * 2 * P2_ROWS;
-  // VQB200_TC2_REGS=128 selects the register-capped build under which one side-kernel block per SM co-resides
+  const bool use2 = tc_pair_allowed(K, D, &stages2, &zbufs2) && cap >= kPairMinRows;
+  // VQB200_TC2_REGS=128 selects the register-capped build under which one side-KERNEL block per SM co-resides
   // with the persistent tensor kernel.  Measured (c3, 2^22 rows): 19.2 ms per step against 17.4-17.9 ms -- the
   // side kernels' warps take issue slots and LSU bandwidth from the epilogue (tensor kernel 2.9 -> 3.8 ms), which
-  // costs more than the overlap returns, so the default keeps the SMs to the tensor kernel.
+  // costs more than the overlap returns.  (The side-job pipeline above is the design that replaced it.)
   const char* envr = std::getenv("VQB200_TC2_REGS");
   const bool slim = envr && envr[0] == '1' && envr[1] == '2';
   static bool attr2_done_dev[64] = {};
@@ -1031,6 +1261,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
   if (use2 && !attr2_done) {
     VQ_CUDA(cudaFuncSetAttribute(search_tc2_kernel<168>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     VQ_CUDA(cudaFuncSetAttribute(search_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    VQ_CUDA(cudaFuncSetAttribute(search_tc2_side_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr2_done = true;
   }
   static bool attr_done_dev[64][2] = {};
@@ -1047,22 +1278,38 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     VQ_CUDA(cudaStreamWaitEvent(s_rr, pipe->fork, 0));
     if (prio) VQ_CUDA(cudaStreamWaitEvent(s_tc, pipe->fork, 0));
   }
+  auto chunk_rows_of = [&](int c) -> int64_t {
+    const int64_t r0 = static_cast<int64_t>(c) * pl.chunk_rows;
+    return (N - r0) < pl.chunk_rows ? (N - r0) : pl.chunk_rows;
+  };
+  auto launch_prep = [&](int c, cudaStream_t st) {
+    const int64_t rows = chunk_rows_of(c);
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    const TcSet& w = sets[n_chunks > 1 ? (c & 1) : 0];
+    zprep_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(z + static_cast<int64_t>(c) * pl.chunk_rows * D, rows, D,
+                                                                 mode, level_meta, w.zb, w.margin, nullptr, nullptr, 0, nullptr);
+  };
+  auto launch_gather_chunk = [&](int c, cudaStream_t st) -> int {
+    const int64_t r0 = static_cast<int64_t>(c) * pl.chunk_rows;
+    return launch_gather(z + r0 * D, ga->E_full, idx_out + r0, chunk_rows_of(c), D, ga->K_total,
+                         ga->zq_out ? ga->zq_out + r0 * D : nullptr, 0, ga->zq_st_out ? ga->zq_st_out + r0 * D : nullptr,
+                         nullptr, ga->sqerr_sum, ga->hist, ga->row_mask ? ga->row_mask + r0 : nullptr, st);
+  };
 
+  int pending_gather = -1;                             // side pipeline: chunk whose gather has not been issued yet
+  bool next_prepped = false;                           // side pipeline: the pre-pass of this chunk rode on the previous kernel
   int ci = 0;
   for (int64_t r0 = 0; r0 < N; r0 += pl.chunk_rows, ++ci) {
-    const int64_t rows = (N - r0) < pl.chunk_rows ? (N - r0) : pl.chunk_rows;
+    const int64_t rows = chunk_rows_of(ci);
     const float* zc = z + r0 * D;
-    const int b = piped ? (ci & 1) : 0;
+    const int b = n_chunks > 1 ? (ci & 1) : 0;
     const TcSet& w = sets[b];
 
     // ---- stage 1: pre-pass (needs the set free: the re-rank of chunk ci-2 has finished with it)
     if (piped && ci >= 2) VQ_CUDA(cudaStreamWaitEvent(s_prep, pipe->done[b], 0));
     VQ_CUDA(cudaMemsetAsync(w.counters, 0, 2 * sizeof(int), s_prep));
-    int64_t blocks = (rows + 7) / 8;
-    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    if (!prep)
-      zprep_kernel<<<static_cast<unsigned>(blocks), 256, 0, s_prep>>>(zc, rows, D, mode, level_meta, w.zb, w.margin,
-                                                                      nullptr, nullptr, 0, nullptr);
+    if (!prep && !(side && next_prepped)) launch_prep(ci, s_prep);
     VQ_CUDA(cudaGetLastError());
     const __nv_bfloat16* zb_c = prep ? reinterpret_cast<const __nv_bfloat16*>(prep->z16) + r0 * D : w.zb;
     const float* mg_c = prep ? prep->margin + r0 : w.margin;
@@ -1077,7 +1324,9 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     p.n_rows = rows; p.D = D; p.K = K;
     p.ee_half = bf ? ee_half_bf16 : ee_half;
     p.margin = mg_c; p.cand = w.cand; p.cnt = w.cnt; p.best = w.best;
-    const bool pair_now = use2 && rows >= static_cast<int64_t>(kNumSMs / 2) * 2 * P2_ROWS;
+    p.clk = nullptr;
+    if (clk_dbg) cudaMallocManaged(&p.clk, kNumSMs * 4 * sizeof(long long));
+    const bool pair_now = use2 && rows >= kPairMinRows;
     int nsub;
     if (pair_now) {
       if (!make_map(&map_z, zb_c, rows, D, P2_ROWS, !bf)) return VQB200_EDRIVER;
@@ -1089,29 +1338,75 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
       nsub = P2_CS;
       const int pairs = p.row_tiles < kNumSMs / 2 ? p.row_tiles : kNumSMs / 2;
       const int smem2 = 1024 + zbufs2 * z2 + stages2 * TC_STAGE_BYTES + P2_NEPI * P2_WCOLS * 4 + 256;
-      timing_mark_begin(s_tc);
-      if (slim) search_tc2_kernel<128><<<2 * pairs, 64 + P2_NEPI * 32, smem2, s_tc>>>(map_z, map_e, p);
-      else search_tc2_kernel<168><<<2 * pairs, 64 + P2_NEPI * 32, smem2, s_tc>>>(map_z, map_e, p);
-      timing_mark_end(s_tc);
+      if (side) {
+        SideJobs sj;
+        sj.D = D; sj.mode = mode;
+        sj.g_rows = 0; sj.p_rows = 0;
+        sj.g_z = nullptr; sj.g_idx = nullptr; sj.g_E = nullptr; sj.g_K_total = 0; sj.g_zq = nullptr; sj.g_zq_st = nullptr;
+        sj.g_sqerr = nullptr; sj.g_hist = nullptr; sj.g_mask = nullptr;
+        sj.p_z = nullptr; sj.p_zb = nullptr; sj.p_margin = nullptr; sj.level_meta = level_meta;
+        if (ga && pending_gather >= 0 && !side_gather_on) {
+          const int gs = launch_gather_chunk(pending_gather, s);
+          if (gs != VQB200_OK) return gs;
+          pending_gather = -1;
+        }
+        if (ga && pending_gather >= 0) {               // gather of the previous chunk: its indices are final
+          const int64_t g0 = static_cast<int64_t>(pending_gather) * pl.chunk_rows;
+          sj.g_z = z + g0 * D; sj.g_idx = idx_out + g0; sj.g_rows = chunk_rows_of(pending_gather);
+          sj.g_E = ga->E_full; sj.g_K_total = ga->K_total;
+          sj.g_zq = ga->zq_out ? ga->zq_out + g0 * D : nullptr;
+          sj.g_zq_st = ga->zq_st_out ? ga->zq_st_out + g0 * D : nullptr;
+          sj.g_sqerr = ga->sqerr_sum; sj.g_hist = ga->hist;
+          sj.g_mask = ga->row_mask ? ga->row_mask + g0 : nullptr;
+          pending_gather = -1;
+        }
+        next_prepped = false;
+        if (ci + 1 < n_chunks && side_prep_on) {       // pre-pass of the next chunk into the other workspace set
+          const TcSet& wn = sets[(ci + 1) & 1];
+          sj.p_z = z + (r0 + pl.chunk_rows) * D; sj.p_rows = chunk_rows_of(ci + 1);
+          sj.p_zb = wn.zb; sj.p_margin = wn.margin;
+          next_prepped = true;
+        }
+        timing_mark_begin(s_tc);
+        search_tc2_side_kernel<<<2 * pairs, 64 + P2_NEPI * 32 + P2_SIDE * 32, smem2, s_tc>>>(map_z, map_e, p, sj);
+        timing_mark_end(s_tc);
+      } else {
+        timing_mark_begin(s_tc);
+        if (slim) search_tc2_kernel<128><<<2 * pairs, 64 + P2_NEPI * 32, smem2, s_tc>>>(map_z, map_e, p);
+        else search_tc2_kernel<168><<<2 * pairs, 64 + P2_NEPI * 32, smem2, s_tc>>>(map_z, map_e, p);
+        timing_mark_end(s_tc);
+      }
     } else {
-    if (!make_map(&map_z, zb_c, rows, D, pl.BM, !bf)) return VQB200_EDRIVER;
-    p.idesc = bf ? kIdesc : kIdescF16;
-    p.row_tiles = static_cast<int>((rows + pl.BM - 1) / pl.BM);
-    p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, pl.ksplit_max, &p.tiles_per_split);
-    p.code_tiles = code_tiles;
-    p.stages = pl.stages;
-    p.zbufs = pl.zbufs;
-    nsub = p.ksplit * tc_cs(pl.BM);
-    const int items = p.row_tiles * p.ksplit;
-    const int grid = items < kNumSMs ? items : kNumSMs;
-    timing_mark_begin(s_tc);
-    if (pl.BM == 256)
-      search_tc_kernel<256><<<grid, 64 + 256 * tc_cs(256), pl.smem_bytes, s_tc>>>(map_z, map_e, p);
-    else
-      search_tc_kernel<128><<<grid, 64 + 128 * tc_cs(128), pl.smem_bytes, s_tc>>>(map_z, map_e, p);
-    timing_mark_end(s_tc);
+      if (!make_map(&map_z, zb_c, rows, D, pl.BM, !bf)) return VQB200_EDRIVER;
+      p.idesc = bf ? kIdesc : kIdescF16;
+      p.row_tiles = static_cast<int>((rows + pl.BM - 1) / pl.BM);
+      p.ksplit = pick_ksplit(rows, pl.BM, code_tiles, pl.ksplit_max, &p.tiles_per_split);
+      p.code_tiles = code_tiles;
+      p.stages = pl.stages;
+      p.zbufs = pl.zbufs;
+      nsub = p.ksplit * tc_cs(pl.BM);
+      const int items = p.row_tiles * p.ksplit;
+      const int grid = items < kNumSMs ? items : kNumSMs;
+      timing_mark_begin(s_tc);
+      if (pl.BM == 256)
+        search_tc_kernel<256><<<grid, 64 + 256 * tc_cs(256), pl.smem_bytes, s_tc>>>(map_z, map_e, p);
+      else
+        search_tc_kernel<128><<<grid, 64 + 128 * tc_cs(128), pl.smem_bytes, s_tc>>>(map_z, map_e, p);
+      timing_mark_end(s_tc);
     }
     VQ_CUDA(cudaGetLastError());
+    if (clk_dbg) {                                     // effective SM clock of this launch: cycles / wall time per CTA
+      cudaStreamSynchronize(s_tc);
+      double mhz = 0.0, us = 0.0;
+      const int nb = pair_now ? 2 * (p.row_tiles < kNumSMs / 2 ? p.row_tiles : kNumSMs / 2) : 0;
+      for (int i = 0; i < nb; ++i) {
+        const double dc = static_cast<double>(p.clk[i * 4 + 2] - p.clk[i * 4 + 0]);
+        const double dt = static_cast<double>(p.clk[i * 4 + 3] - p.clk[i * 4 + 1]);
+        mhz += dc / dt * 1e3 / nb; us += dt * 1e-3 / nb;
+      }
+      if (nb) fprintf(stderr, "[vqb200] pair kernel chunk %d: %.1f us per CTA, effective SM clock %.0f MHz\n", ci, us, mhz);
+      cudaFree(p.clk);
+    }
     if (piped) {
       VQ_CUDA(cudaEventRecord(pipe->tc[b], s_tc));
       VQ_CUDA(cudaStreamWaitEvent(s_rr, pipe->tc[b], 0));
@@ -1120,7 +1415,7 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     // ---- stage 3: prune + exact re-rank, then the rows handed back to the exact SIMT kernel
     int rpw = 32;                                      // rows per warp step: keep >= ~8K warps in flight
     while (rpw > 1 && rows / rpw < 8192) rpw >>= 1;
-    blocks = (rows + 8 * rpw - 1) / (8 * rpw);
+    int64_t blocks = (rows + 8 * rpw - 1) / (8 * rpw);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     const __nv_bfloat16* Eb = reinterpret_cast<const __nv_bfloat16*>(E_bf16);
     if (bf)
@@ -1138,13 +1433,18 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
     fb_unpack_kernel<<<64, 256, 0, s_rr>>>(w.fb_rows, w.fb_packed, w.counters, idx_out + r0);
     VQ_CUDA(cudaGetLastError());
     if (ga) {   // stage 4 (optional): gather / straight-through / loss / histogram of this chunk, behind its re-rank
-      const int gs = launch_gather(zc, ga->E_full, idx_out + r0, rows, D, ga->K_total,
-                                   ga->zq_out ? ga->zq_out + r0 * D : nullptr, 0,
-                                   ga->zq_st_out ? ga->zq_st_out + r0 * D : nullptr, nullptr, ga->sqerr_sum, ga->hist,
-                                   ga->row_mask ? ga->row_mask + r0 : nullptr, s_rr);
-      if (gs != VQB200_OK) return gs;
+      if (side) {
+        pending_gather = ci;                           // rides on the next chunk's tensor kernel
+      } else {
+        const int gs = launch_gather_chunk(ci, s_rr);
+        if (gs != VQB200_OK) return gs;
+      }
     }
     if (piped) VQ_CUDA(cudaEventRecord(pipe->done[b], s_rr));
+  }
+  if (ga && pending_gather >= 0) {                     // the last chunk's gather has no tensor kernel to ride on
+    const int gs = launch_gather_chunk(pending_gather, s);
+    if (gs != VQB200_OK) return gs;
   }
   if (piped) {                                         // join: the caller's stream sees every chunk finished
     VQ_CUDA(cudaStreamWaitEvent(s, pipe->done[0], 0));

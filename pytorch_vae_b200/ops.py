@@ -182,12 +182,16 @@ def search_prepped(z, z16, margin, E, cache: CodebookCache, level: int, mode: in
                                     cache.ee_half.data_ptr() + (cache.K_total + s) * 4,
                                     cache.level_meta.data_ptr() + level * _cabi.LEVEL_META_FLOATS * 4, K, mode, s,
                                     ptr(idx_out), ptr(ws), ws_bytes, stream_ptr()), "vqb200_search_prepped")
-    _count(search_launches(N, K, D, mode) - tc_chunks(N, K, D, mode))
+    _count(4 * tc_chunks(N, K, D, mode))       # per chunk: tcgen05 search, re-rank, hand-back, unpack
 
 
 def tc_chunks(N, K, D, mode) -> int:
-    """Chunks the tensor-path search splits N rows into (one pre-pass launch each)."""
-    return max(1, search_launches(N, K, D, mode) // 5) if lib.vqb200_search_path(N, K, D, mode) else 0
+    """Chunks the tensor-path search splits N rows into."""
+    path = lib.vqb200_search_path(N, K, D, mode)
+    if not path:
+        return 0
+    n = search_launches(N, K, D, mode)
+    return max(1, (n - 1) // 4) if path == 2 else max(1, n // 5)
 
 
 def search_launches(N, K, D, mode) -> int:
@@ -232,9 +236,10 @@ def quantize(z, E, cache: CodebookCache, mode, idx_out, zq_out=None, zq_st_out=N
                               cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, mode, 0,
                               ptr(idx_out), ptr(E), E.shape[0], ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist),
                               ptr(row_mask), ptr(ws), ws_bytes, stream_ptr()), "vqb200_quantize")
-    n_search = search_launches(N, K, D, mode)
-    chunks = max(1, n_search // 5) if lib.vqb200_search_path(N, K, D, mode) else 1
-    _count(n_search + chunks)
+    path = lib.vqb200_search_path(N, K, D, mode)
+    # one gather per chunk -- or, on the side-job pipeline (path 2), only the last chunk's: the others ride on the
+    # tensor kernels
+    _count(search_launches(N, K, D, mode) + (1 if path == 2 else max(1, tc_chunks(N, K, D, mode))))
 
 
 @_on_device

@@ -234,3 +234,42 @@ def test_fp16_operand_range_is_safe(vq, D, K, case):
     mm, outside = O.near_tie_rows(z, E, idx, ref)
     assert outside.size == 0, f"{case}: {outside.size} rows differ from the fp64 arbiter outside near-ties"
     assert mm.size <= 8
+
+
+@pytest.mark.parametrize("K,D,N,mask", [(1024, 256, 2 * (1 << 20) + 20480, False), (512, 384, (1 << 20) + 19000, True)])
+def test_side_job_pipeline_matches_plain_chunk_pipeline(K, D, N, mask, monkeypatch):
+    """Several chunks on the CTA-pair kernel: the tensor kernel of chunk i carries the pre-pass of chunk i+1 and the
+    gather / straight-through / loss / histogram pass of chunk i-1 on six side warps (SideJobs, vq_search_tc.cu).
+    Every output must equal the default pipeline's (separate pre-pass and gather kernels), and the
+    indices the oracle's on a sample of rows."""
+    import pytorch_vae_b200 as vq
+    dev = torch.device("cuda:0")
+    lib = vq._cabi.lib
+    gen = torch.Generator(device=dev).manual_seed(77)
+    E = torch.randn(K, D, device=dev, generator=gen) / np.sqrt(D)
+    z = torch.randn(1, N, D, device=dev, generator=gen)
+    m = (torch.rand(1, N, device=dev, generator=gen) > 0.3) if mask else None
+
+    def run():
+        q = vq.VectorQuantizerEMA(K, D, print_init=False).to(dev).eval()
+        q.embedding.copy_(E)
+        with torch.no_grad():
+            st, zq, idx, stats = q(z, do_ema_update=False, mask=m)
+        torch.cuda.synchronize()
+        return st, zq, idx, stats, q._ep_usage.clone(), q.last_commit.clone()
+    monkeypatch.delenv("VQB200_TC2_SIDE", raising=False)
+    assert lib.vqb200_search_path(N, K, D, 0) == 1          # default: the three-stream chunk pipeline
+    plain = run()
+    monkeypatch.setenv("VQB200_TC2_SIDE", "1")              # opt-in switch (measured slower on power-capped B200s)
+    assert lib.vqb200_search_path(N, K, D, 0) == 2, "this shape must take the side-job pipeline"
+    side = run()
+    assert torch.equal(side[2], plain[2])
+    assert torch.equal(side[1], plain[1]) and torch.equal(side[0], plain[0])
+    assert torch.equal(side[4], plain[4])
+    assert torch.allclose(side[3], plain[3], rtol=1e-6) and torch.allclose(side[5], plain[5], rtol=1e-6)
+    assert torch.equal(side[1].view(-1, D), E[side[2].view(-1)])
+    assert float(side[4].sum()) == (float(m.sum()) if mask else N)
+    rows = torch.randperm(N, generator=torch.Generator().manual_seed(5))[:2048].to(dev)
+    zs, En = z.view(-1, D)[rows].cpu().numpy(), E.cpu().numpy()
+    mm, outside = O.near_tie_rows(zs, En, side[2].view(-1)[rows].cpu().numpy(), O.nearest_code64(zs, En))
+    assert outside.size == 0 and mm.size <= 2
