@@ -33,7 +33,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 12
+#define VQB200_ABI_VERSION 13
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -277,6 +277,15 @@ VQB200_API int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int
 VQB200_API int vqb200_search_packed(const float* z, int64_t N, int D, const float* E, const float* ee_half, int K,
                          int64_t idx_offset, uint64_t* packed_out, void* stream);
 VQB200_API int vqb200_minloc_unpack(const uint64_t* packed, int64_t N, int64_t* idx_out, void* stream);
+
+/* The same on the TENSOR path (north star: "a codebook-sharded min-loc reduction is used when K.D exceeds the per-SM
+ * staging budget"): each rank runs vqb200_search over its slice of the codes (exact winner of the slice, global id),
+ *   pack_exact: packed[n] = (orderable(fp64 score of z_n against E_full[idx[n]]) with its low 24 bits cleared) | idx[n]
+ * (score = |e|^2/2 - z.e, fp64 accumulation; 40 bits of score + 24 bits of id, K_total <= 2^24), the ranks all-reduce(MIN)
+ * the packed words, and unpack24 extracts the ids.  Equal scores to 4e-9 relative resolve to the lower id. */
+VQB200_API int vqb200_pack_exact(const float* z, int64_t N, int D, const float* E_full, int K_total, const int64_t* idx,
+                      uint64_t* packed_out, void* stream);
+VQB200_API int vqb200_minloc_unpack24(const uint64_t* packed, int64_t N, int64_t* idx_out, void* stream);
 
 #ifdef __cplusplus
 }

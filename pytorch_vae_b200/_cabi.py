@@ -16,7 +16,7 @@ MODE_FP32_EXACT = 0
 MODE_BF16_INPUT = 1
 MAX_LEVELS = 32
 LEVEL_META_FLOATS = 8
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 _p = C.c_void_p
 _i = C.c_int
@@ -67,6 +67,8 @@ SIGNATURES = {
     "vqb200_indices_to_latent": (_i, [_p, _i, _i64, _i, _p, _i, _i, _p, _p]),
     "vqb200_search_packed": (_i, [_p, _i64, _i, _p, _p, _i, _i64, _p, _p]),
     "vqb200_minloc_unpack": (_i, [_p, _i64, _p, _p]),
+    "vqb200_pack_exact": (_i, [_p, _i64, _i, _p, _i, _p, _p, _p]),
+    "vqb200_minloc_unpack24": (_i, [_p, _i64, _p, _p]),
 }
 
 

@@ -535,6 +535,21 @@ int vqb200_search_packed(const float* z, int64_t N, int D, const float* E, const
                             static_cast<cudaStream_t>(stream));
 }
 
+int vqb200_pack_exact(const float* z, int64_t N, int D, const float* E_full, int K_total, const int64_t* idx,
+                      uint64_t* packed_out, void* stream) {
+  VQ_REQUIRE(N >= 0 && K_total > 0 && K_total <= (1 << 24), VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && E_full && idx && packed_out), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E_full), VQB200_EALIGN);
+  return launch_pack_exact(z, N, D, E_full, K_total, idx, packed_out, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_minloc_unpack24(const uint64_t* packed, int64_t N, int64_t* idx_out, void* stream) {
+  VQ_REQUIRE(N >= 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (packed && idx_out), VQB200_EINVAL);
+  return launch_minloc_unpack24(packed, N, idx_out, static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_minloc_unpack(const uint64_t* packed, int64_t N, int64_t* idx_out, void* stream) {
   VQ_REQUIRE(N >= 0, VQB200_EINVAL);
   VQ_REQUIRE(N == 0 || (packed && idx_out), VQB200_EINVAL);

@@ -683,6 +683,65 @@ __global__ void minloc_unpack_kernel(const uint64_t* __restrict__ p, int64_t N, 
     out[i] = static_cast<int64_t>(p[i] & 0xffffffffull);
 }
 
+// Codebook-sharded search on the tensor path: every rank has found the EXACT winner inside its slice of the codes
+// (vqb200_search on the slice: tcgen05 candidates + fp64 re-rank); to combine the winners of the ranks with one
+// all-reduce(MIN) each rank packs  (orderable(fp64 score) >> 24 << 24) | global id  -- 40 bits of the exact score
+// (sign, exponent, 28 mantissa bits: ties only below 4e-9 relative, then the lower id wins) and 24 bits of id.
+// The score is  |e|^2 / 2 - z.e  (the distance minus the row constant |z|^2, halved), fp64 accumulation of the
+// fp32 inputs, one warp per row.
+__global__ void __launch_bounds__(256)
+pack_exact_kernel(const float* __restrict__ z, int64_t N, int D, const float* __restrict__ E, int K_total,
+                  const int64_t* __restrict__ idx, uint64_t* __restrict__ packed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < N; row += nwarps) {
+    const int64_t k = idx[row];
+    double dot = 0.0, ee = 0.0;
+    const bool ok = k >= 0 && k < K_total;
+    if (ok) {
+      for (int d = lane * 4; d < D; d += 128) {
+        const float4 a = ld_stream(reinterpret_cast<const float4*>(z + row * D + d));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(E + k * D + d));
+        dot = fma(static_cast<double>(a.x), static_cast<double>(b.x), dot); ee = fma(static_cast<double>(b.x), static_cast<double>(b.x), ee);
+        dot = fma(static_cast<double>(a.y), static_cast<double>(b.y), dot); ee = fma(static_cast<double>(b.y), static_cast<double>(b.y), ee);
+        dot = fma(static_cast<double>(a.z), static_cast<double>(b.z), dot); ee = fma(static_cast<double>(b.z), static_cast<double>(b.z), ee);
+        dot = fma(static_cast<double>(a.w), static_cast<double>(b.w), dot); ee = fma(static_cast<double>(b.w), static_cast<double>(b.w), ee);
+      }
+    }
+    dot = warp_sum(dot);
+    ee = warp_sum(ee);
+    if (lane == 0) {
+      const double d = 0.5 * ee - dot;                        // smaller is nearer
+      uint64_t u = static_cast<uint64_t>(__double_as_longlong(d));
+      u = (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);   // order-preserving
+      if (d != d) u = 0ull;                                   // NaN wins, as in torch.argmin
+      packed[row] = ok ? ((u & ~0xffffffull) | static_cast<uint64_t>(k)) : ~0ull;
+    }
+  }
+}
+
+int launch_pack_exact(const float* z, int64_t N, int D, const float* E, int K_total, const int64_t* idx, uint64_t* packed,
+                      cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  int64_t blocks = (N + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  pack_exact_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(z, N, D, E, K_total, idx, packed);
+  return status_of(cudaGetLastError());
+}
+
+__global__ void minloc_unpack24_kernel(const uint64_t* __restrict__ p, int64_t N, int64_t* __restrict__ out) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride)
+    out[i] = static_cast<int64_t>(p[i] & 0xffffffull);
+}
+
+int launch_minloc_unpack24(const uint64_t* p, int64_t N, int64_t* out, cudaStream_t s) {
+  if (N == 0) return VQB200_OK;
+  minloc_unpack24_kernel<<<stream_grid(N), ROW_THREADS, 0, s>>>(p, N, out);
+  return status_of(cudaGetLastError());
+}
+
 int launch_minloc_unpack(const uint64_t* p, int64_t N, int64_t* out, cudaStream_t s) {
   if (N == 0) return VQB200_OK;
   minloc_unpack_kernel<<<stream_grid(N), ROW_THREADS, 0, s>>>(p, N, out);

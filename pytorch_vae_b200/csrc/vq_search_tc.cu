@@ -37,7 +37,7 @@ constexpr int TC_SLOTS = TC_CAND + 1;
 // With E_sub / idx_sub / residual_out the row is first replaced by the residual fl(z - E_sub[idx_sub[row]])
 // (models/vq_vae.py:258), which is also written out in fp32: the residual update of one RVQ level and the
 // pre-pass of the next in ONE read of the row.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const float* __restrict__ level_meta,
              __nv_bfloat16* __restrict__ zb, float* __restrict__ margin, const float* __restrict__ E_sub,
              const int64_t* __restrict__ idx_sub, int K_sub, float* __restrict__ residual_out) {
@@ -59,39 +59,56 @@ zprep_kernel(const float* __restrict__ z, int64_t n, int D, int mode, const floa
       ksub = idx_sub[row];
       if (ksub < 0 || ksub >= K_sub) ksub = -1;           // never produced by vqb200_search; leaves the row as is
     }
-    for (int c = lane; c < D4; c += 32) {
-      float4 v = ld_stream(reinterpret_cast<const float4*>(z) + row * D4 + c);
-      if (E_sub) {
-        if (ksub >= 0) {
-          const float4 e = __ldg(reinterpret_cast<const float4*>(E_sub) + ksub * D4 + c);
-          v.x = __fsub_rn(v.x, e.x); v.y = __fsub_rn(v.y, e.y); v.z = __fsub_rn(v.z, e.z); v.w = __fsub_rn(v.w, e.w);
+    // every load of the row (and of the code row being subtracted) is issued before the first conversion: at the
+    // stage-2 shape (8192 rows x 512 floats, one launch per level) the kernel is latency-, not bandwidth-bound
+    constexpr int ZP_SL = 4;                                 // float4 slices per lane held in flight: D <= 512
+    for (int c0 = lane; c0 < D4; c0 += 32 * ZP_SL) {
+      float4 vv[ZP_SL], ee4[ZP_SL];
+#pragma unroll
+      for (int u = 0; u < ZP_SL; ++u) {
+        const int c = c0 + u * 32;
+        if (c < D4) {
+          vv[u] = ld_stream(reinterpret_cast<const float4*>(z) + row * D4 + c);
+          if (E_sub && ksub >= 0) ee4[u] = __ldg(reinterpret_cast<const float4*>(E_sub) + ksub * D4 + c);
         }
-        st_stream(reinterpret_cast<float4*>(residual_out) + row * D4 + c, v);
       }
-      uint16_t b0, b1, b2, b3;
-      float f0, f1, f2, f3;
-      if (bfm) {
-        b0 = __bfloat16_as_ushort(__float2bfloat16_rn(v.x)); b1 = __bfloat16_as_ushort(__float2bfloat16_rn(v.y));
-        b2 = __bfloat16_as_ushort(__float2bfloat16_rn(v.z)); b3 = __bfloat16_as_ushort(__float2bfloat16_rn(v.w));
-        f0 = __uint_as_float(static_cast<uint32_t>(b0) << 16); f1 = __uint_as_float(static_cast<uint32_t>(b1) << 16);
-        f2 = __uint_as_float(static_cast<uint32_t>(b2) << 16); f3 = __uint_as_float(static_cast<uint32_t>(b3) << 16);
-      } else {
-        const uint32_t q0 = f16x2_bits_flush(v.x, v.y), q1 = f16x2_bits_flush(v.z, v.w);
-        b0 = static_cast<uint16_t>(q0); b1 = static_cast<uint16_t>(q0 >> 16);
-        b2 = static_cast<uint16_t>(q1); b3 = static_cast<uint16_t>(q1 >> 16);
-        const float2 g0 = f16x2_bits_to_float2(q0), g1 = f16x2_bits_to_float2(q1);
-        f0 = g0.x; f1 = g0.y; f2 = g1.x; f3 = g1.y;
-      }
-      uint2 pk;
-      pk.x = static_cast<uint32_t>(b0) | (static_cast<uint32_t>(b1) << 16);
-      pk.y = static_cast<uint32_t>(b2) | (static_cast<uint32_t>(b3) << 16);
-      reinterpret_cast<uint2*>(zb)[row * D4 + c] = pk;
-      if (bfm) {
-        ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
-      } else {
-        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        const float d0 = v.x - f0, d1 = v.y - f1, d2 = v.z - f2, d3 = v.w - f3;      // exact differences
-        sse += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+#pragma unroll
+      for (int u = 0; u < ZP_SL; ++u) {
+        const int c = c0 + u * 32;
+        if (c >= D4) continue;
+        float4 v = vv[u];
+        if (E_sub) {
+          if (ksub >= 0) {
+            const float4 e = ee4[u];
+            v.x = __fsub_rn(v.x, e.x); v.y = __fsub_rn(v.y, e.y); v.z = __fsub_rn(v.z, e.z); v.w = __fsub_rn(v.w, e.w);
+          }
+          st_stream(reinterpret_cast<float4*>(residual_out) + row * D4 + c, v);
+        }
+        uint16_t b0, b1, b2, b3;
+        float f0, f1, f2, f3;
+        if (bfm) {
+          b0 = __bfloat16_as_ushort(__float2bfloat16_rn(v.x)); b1 = __bfloat16_as_ushort(__float2bfloat16_rn(v.y));
+          b2 = __bfloat16_as_ushort(__float2bfloat16_rn(v.z)); b3 = __bfloat16_as_ushort(__float2bfloat16_rn(v.w));
+          f0 = __uint_as_float(static_cast<uint32_t>(b0) << 16); f1 = __uint_as_float(static_cast<uint32_t>(b1) << 16);
+          f2 = __uint_as_float(static_cast<uint32_t>(b2) << 16); f3 = __uint_as_float(static_cast<uint32_t>(b3) << 16);
+        } else {
+          const uint32_t q0 = f16x2_bits_flush(v.x, v.y), q1 = f16x2_bits_flush(v.z, v.w);
+          b0 = static_cast<uint16_t>(q0); b1 = static_cast<uint16_t>(q0 >> 16);
+          b2 = static_cast<uint16_t>(q1); b3 = static_cast<uint16_t>(q1 >> 16);
+          const float2 g0 = f16x2_bits_to_float2(q0), g1 = f16x2_bits_to_float2(q1);
+          f0 = g0.x; f1 = g0.y; f2 = g1.x; f3 = g1.y;
+        }
+        uint2 pk;
+        pk.x = static_cast<uint32_t>(b0) | (static_cast<uint32_t>(b1) << 16);
+        pk.y = static_cast<uint32_t>(b2) | (static_cast<uint32_t>(b3) << 16);
+        reinterpret_cast<uint2*>(zb)[row * D4 + c] = pk;
+        if (bfm) {
+          ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;
+        } else {
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          const float d0 = v.x - f0, d1 = v.y - f1, d2 = v.z - f2, d3 = v.w - f3;      // exact differences
+          sse += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
       }
     }
     ss = warp_sum(ss);
@@ -832,7 +849,7 @@ search_tc2_side_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_
 constexpr int RR_LIST = 64;   // surviving codes per row handled in-kernel; more -> exact SIMT kernel
 
 template <bool BF16>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb, const float* __restrict__ E,
               const __nv_bfloat16* __restrict__ Eb, int64_t n, int D, int nsub, int rpw,
               const float* __restrict__ margin, const uint2* __restrict__ cand, const int* __restrict__ cnt,
@@ -850,9 +867,13 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
   while (lpv & (lpv - 1)) lpv &= lpv - 1;               // largest power of two <= D/4 (D % 4 == 0)
   const int groups = 32 / lpv, gl = lane % lpv, gi = lane / lpv;
 
+  constexpr int RR_NS = 4;                              // slices whose records the one-row-per-warp path keeps in registers
+  const bool pre_ok = nsub <= RR_NS;
   for (int64_t base = warp * rpw; base < n; base += nwarps * rpw) {
     const int64_t row = base + lane;
     const bool mine = lane < rpw && row < n;
+    uint2 ents[RR_NS];
+    int cnts[RR_NS] = {0, 0, 0, 0};
     int ns = 0, ncodes = 0;
     uint32_t first = 0;
     float thr = __int_as_float(0x7fc00000);
@@ -860,9 +881,17 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
     if (rpw == 1 && base < n) {
       // One row per warp (small n): the whole warp prunes it -- lane j takes record j of each slice (one coalesced
       // 256-byte load per slice) instead of lane 0 walking up to 31 records per slice through dependent loads.
+      // With up to RR_NS slices the records are fetched SPECULATIVELY, together with the counts, the slice maxima and
+      // the margin (slots beyond a slice's count hold stale workspace bytes and are masked below): one memory round
+      // trip instead of one per slice plus two -- at 8192 rows per launch this kernel is a chain of L2 latencies.
       const int64_t r = base;
       float bs = __int_as_float(0xff800000);
       int c_l = 0;
+      if (pre_ok) {
+#pragma unroll
+        for (int sb = 0; sb < RR_NS; ++sb)
+          if (sb < nsub && lane < TC_CAND) ents[sb] = cand[(r * nsub + sb) * TC_SLOTS + lane];
+      }
       if (lane < nsub) { c_l = cnt[r * nsub + lane]; bs = best[r * nsub + lane]; }
       bool bad = lane < nsub && (c_l < 0 || c_l > TC_CAND || (c_l == 0 && bs != __int_as_float(0xff800000)));
       bad = __any_sync(0xffffffffu, bad);
@@ -872,10 +901,17 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
       const float mg = margin[r];
       if (!bad && mg == mg) {
         thr = bmax - mg;
+#pragma unroll
+        for (int sb = 0; sb < RR_NS; ++sb) cnts[sb] = sb < nsub ? __shfl_sync(0xffffffffu, c_l, sb) : 0;
         for (int sb = 0; sb < nsub; ++sb) {
           const int c = __shfl_sync(0xffffffffu, c_l, sb);
           uint2 ent = make_uint2(0u, 0xff800000u);
-          if (lane < c) ent = cand[(r * nsub + sb) * TC_SLOTS + lane];
+          if (pre_ok) {
+#pragma unroll
+            for (int q = 0; q < RR_NS; ++q) if (q == sb && lane < c) ent = ents[q];
+          } else if (lane < c) {
+            ent = cand[(r * nsub + sb) * TC_SLOTS + lane];
+          }
           const bool hit = lane < c && __uint_as_float(ent.y) >= thr;
           const unsigned hits = __ballot_sync(0xffffffffu, hit);
           if (hits) {
@@ -944,9 +980,16 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
       // expand the surviving records of row r into the shared code list
       int n_c = 0;
       for (int sb = 0; sb < nsub; ++sb) {
-        const int c = cnt[r * nsub + sb];
+        int c;
         uint2 ent = make_uint2(0u, 0xff800000u);
-        if (lane < c) ent = cand[(r * nsub + sb) * TC_SLOTS + lane];
+        if (rpw == 1 && pre_ok) {                      // the records are still in registers
+          c = 0;
+#pragma unroll
+          for (int q = 0; q < RR_NS; ++q) if (q == sb) { c = cnts[q]; if (lane < c) ent = ents[q]; }
+        } else {
+          c = cnt[r * nsub + sb];
+          if (lane < c) ent = cand[(r * nsub + sb) * TC_SLOTS + lane];
+        }
         const uint32_t mk = (lane < c && __uint_as_float(ent.y) >= thr_r) ? (ent.x & 0xffu) : 0u;
         int pre = __popc(mk);                          // exclusive prefix sum of the per-lane code counts
 #pragma unroll
@@ -964,47 +1007,90 @@ rerank_kernel(const float* __restrict__ z, const __nv_bfloat16* __restrict__ zb,
         n_c += tot;
       }
       __syncwarp();
-      // this lane's slice of the row (reused for every candidate)
+      // Exact scores.  Fast path (fp32 inputs, D <= 512 with a full warp per row, or smaller rows): this lane's slices
+      // of the row are loaded ONCE, and all slices of a candidate's code row are in flight together -- the
+      // chain is bound by L2 latency (one launch per residual level at 8192 rows), not by arithmetic.
+      constexpr int RR_SL = 4, RR_CB = 1;   // slices per lane, candidates per lane group in flight (registers)
+      const bool fast = !BF16 && D <= lpv * 4 * RR_SL;
+      float4 zr[RR_SL];
+      if (fast) {
+#pragma unroll
+        for (int sl = 0; sl < RR_SL; ++sl) {
+          const int d = gl * 4 + sl * lpv * 4;
+          if (d < D) zr[sl] = *reinterpret_cast<const float4*>(z + r * D + d);
+        }
+      }
       double top = -1e300;
       uint32_t top_idx = 0xffffffffu;
-      for (int c0 = 0; c0 < n_c; c0 += groups) {
-        const int ci = c0 + gi;
-        const bool ok = ci < n_c;
-        const uint32_t code = ok ? s_list[wib][ci] : 0u;
-        double dot = 0.0, ee = 0.0;
-        if (ok) {
-          for (int d = gl * 4; d < D; d += lpv * 4) {
-            float zv[4], ev[4];
-            if (BF16) {
-              const uint2 a = *reinterpret_cast<const uint2*>(zb + r * D + d);
-              const uint2 b = *reinterpret_cast<const uint2*>(Eb + static_cast<int64_t>(code) * D + d);
-              zv[0] = __uint_as_float(a.x << 16); zv[1] = __uint_as_float(a.x & 0xffff0000u);
-              zv[2] = __uint_as_float(a.y << 16); zv[3] = __uint_as_float(a.y & 0xffff0000u);
-              ev[0] = __uint_as_float(b.x << 16); ev[1] = __uint_as_float(b.x & 0xffff0000u);
-              ev[2] = __uint_as_float(b.y << 16); ev[3] = __uint_as_float(b.y & 0xffff0000u);
-            } else {
-              *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + r * D + d);
-              *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + d));
-            }
+      for (int c0 = 0; c0 < n_c; c0 += groups * RR_CB) {
+        uint32_t codes[RR_CB];
+        bool oks[RR_CB];
+        float4 er[RR_CB][RR_SL];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
-              ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+        for (int u = 0; u < RR_CB; ++u) {
+          const int ci = c0 + u * groups + gi;
+          oks[u] = ci < n_c;
+          codes[u] = oks[u] ? s_list[wib][ci] : 0u;
+          if (fast && oks[u]) {
+#pragma unroll
+            for (int sl = 0; sl < RR_SL; ++sl) {
+              const int d = gl * 4 + sl * lpv * 4;
+              if (d < D) er[u][sl] = __ldg(reinterpret_cast<const float4*>(E + static_cast<int64_t>(codes[u]) * D + d));
             }
           }
         }
-        for (int o = lpv >> 1; o > 0; o >>= 1) {       // reduce inside the lane group
-          dot += __shfl_xor_sync(0xffffffffu, dot, o);
-          ee += __shfl_xor_sync(0xffffffffu, ee, o);
+#pragma unroll
+        for (int u = 0; u < RR_CB; ++u) {
+          const bool ok = oks[u];
+          const uint32_t code = codes[u];
+          double dot = 0.0, ee = 0.0;
+          if (ok && fast) {
+#pragma unroll
+            for (int sl = 0; sl < RR_SL; ++sl) {
+              if (gl * 4 + sl * lpv * 4 < D) {
+                const float zv[4] = {zr[sl].x, zr[sl].y, zr[sl].z, zr[sl].w};
+                const float ev[4] = {er[u][sl].x, er[u][sl].y, er[u][sl].z, er[u][sl].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
+                  ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+                }
+              }
+            }
+          } else if (ok) {
+            for (int d = gl * 4; d < D; d += lpv * 4) {
+              float zv[4], ev[4];
+              if (BF16) {
+                const uint2 a = *reinterpret_cast<const uint2*>(zb + r * D + d);
+                const uint2 b = *reinterpret_cast<const uint2*>(Eb + static_cast<int64_t>(code) * D + d);
+                zv[0] = __uint_as_float(a.x << 16); zv[1] = __uint_as_float(a.x & 0xffff0000u);
+                zv[2] = __uint_as_float(a.y << 16); zv[3] = __uint_as_float(a.y & 0xffff0000u);
+                ev[0] = __uint_as_float(b.x << 16); ev[1] = __uint_as_float(b.x & 0xffff0000u);
+                ev[2] = __uint_as_float(b.y << 16); ev[3] = __uint_as_float(b.y & 0xffff0000u);
+              } else {
+                *reinterpret_cast<float4*>(zv) = *reinterpret_cast<const float4*>(z + r * D + d);
+                *reinterpret_cast<float4*>(ev) = __ldg(reinterpret_cast<const float4*>(E + static_cast<int64_t>(code) * D + d));
+              }
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                dot = fma(static_cast<double>(zv[q]), static_cast<double>(ev[q]), dot);
+                ee = fma(static_cast<double>(ev[q]), static_cast<double>(ev[q]), ee);
+              }
+            }
+          }
+          for (int o = lpv >> 1; o > 0; o >>= 1) {       // reduce inside the lane group
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            ee += __shfl_xor_sync(0xffffffffu, ee, o);
+          }
+          double sc = ok ? dot - 0.5 * ee : -1e300;
+          uint32_t cd = ok ? code : 0xffffffffu;
+          for (int o = lpv; o < 32; o <<= 1) {           // lexicographic (score, lowest index) across groups
+            const double so = __shfl_xor_sync(0xffffffffu, sc, o);
+            const uint32_t co = __shfl_xor_sync(0xffffffffu, cd, o);
+            if (so > sc || (so == sc && co < cd)) { sc = so; cd = co; }
+          }
+          if (sc > top || (sc == top && cd < top_idx)) { top = sc; top_idx = cd; }
         }
-        double sc = ok ? dot - 0.5 * ee : -1e300;
-        uint32_t cd = ok ? code : 0xffffffffu;
-        for (int o = lpv; o < 32; o <<= 1) {           // lexicographic (score, lowest index) across groups
-          const double so = __shfl_xor_sync(0xffffffffu, sc, o);
-          const uint32_t co = __shfl_xor_sync(0xffffffffu, cd, o);
-          if (so > sc || (so == sc && co < cd)) { sc = so; cd = co; }
-        }
-        if (sc > top || (sc == top && cd < top_idx)) { top = sc; top_idx = cd; }
       }
       if (lane == 0) idx_out[r] = idx_offset + top_idx;
       __syncwarp();

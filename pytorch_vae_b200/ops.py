@@ -423,6 +423,40 @@ def search_packed(z, E_slice, ee_half_slice, idx_offset, packed_out):
 
 
 @_on_device
+def search_slice(z, E, cache: CodebookCache, first_code: int, n_codes: int, mode: int, idx_out):
+    """idx_out[n] = first_code + argmin over the codes [first_code, first_code + n_codes) of a single-level codebook
+    (the slice a rank owns in the codebook-sharded search); same kernels as ``search``."""
+    _need_cuda(z, E, idx_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    ws_bytes = lib.vqb200_search_workspace_bytes(N, n_codes, D, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    check(lib.vqb200_search(ptr(z), N, D, E.data_ptr() + first_code * D * 4, cache.operand_ptr(mode, first_code),
+                            cache.ee_half.data_ptr() + first_code * 4,
+                            cache.ee_half.data_ptr() + (cache.K_total + first_code) * 4, cache.level_meta.data_ptr(),
+                            n_codes, mode, first_code, ptr(idx_out), ptr(ws), ws_bytes, stream_ptr()), "vqb200_search")
+    _count(search_launches(N, n_codes, D, mode))
+
+
+@_on_device
+def pack_exact(z, E, idx, packed_out):
+    """packed[n] = 40 bits of the exact fp64 score of z_n against E[idx[n]] | 24 bits of idx[n] (MIN-reducible)."""
+    _need_cuda(z, E, idx, packed_out)
+    _f32c(z, "z")
+    N, D = z.shape
+    check(lib.vqb200_pack_exact(ptr(z), N, D, ptr(E), E.shape[0], ptr(idx), ptr(packed_out), stream_ptr()),
+          "vqb200_pack_exact")
+    _count(1)
+
+
+@_on_device
+def minloc_unpack24(packed, idx_out):
+    check(lib.vqb200_minloc_unpack24(ptr(packed), packed.numel(), ptr(idx_out), stream_ptr()),
+          "vqb200_minloc_unpack24")
+    _count(1)
+
+
+@_on_device
 def minloc_unpack(packed, idx_out):
     check(lib.vqb200_minloc_unpack(ptr(packed), packed.numel(), ptr(idx_out), stream_ptr()),
           "vqb200_minloc_unpack")

@@ -67,13 +67,34 @@ def codebook_sharded_search(q, flat: torch.Tensor, group=None) -> torch.Tensor:
         raise NotImplementedError("codebook-sharded search is defined for single-level codebooks")
     world = dist.get_world_size(group) if dist_ready() else 1
     rank = dist.get_rank(group) if dist_ready() else 0
+    return sharded_search_slice(q, flat, world, rank, lambda p: allreduce_minloc(p, group) if world > 1 else p)
+
+
+def sharded_search_slice(q, flat: torch.Tensor, world: int, rank: int, reduce_min):
+    """One rank's share of the codebook-sharded search, with the cross-rank MIN supplied by the caller
+    (``reduce_min(packed int64) -> packed int64``; the tests simulate the ranks on one device).  On shapes the tensor
+    path serves (slice of >= 128 codes, D a multiple of 64, q.K <= 2^24) the slice is searched by the tcgen05 kernels
+    with the exact re-rank and the winner's exact fp64 score is packed (40 bits of score | 24 bits of id);
+    otherwise by the exact SIMT kernel (32-bit fp32 distance key | 32 bits of id)."""
+    from . import _cabi, ops
+    from .quantizer import _MODES
     s, e = shard_codes(q.K, world, rank)
     cache = q._codebook_cache()
-    packed = torch.full((flat.shape[0],), -1, dtype=torch.int64, device=flat.device)   # all ones = +inf key
-    if e > s:
-        ops.search_packed(flat.contiguous(), q.embedding[s:e], cache.ee_half[0, s:e], s, packed)
-    if world > 1:
-        packed = allreduce_minloc(packed, group)
+    flat = flat.contiguous()
+    N, D = flat.shape
+    mode = _MODES[q.search_mode]
+    # every rank must take the same route: decide on the SMALLEST slice
+    smallest = min(b - a for a, b in (shard_codes(q.K, world, r) for r in range(world)))
+    tensor = smallest > 0 and q.K <= (1 << 24) and mode == _cabi.MODE_FP32_EXACT and \
+        bool(_cabi.lib.vqb200_search_path(N, smallest, D, mode))
+    packed = torch.full((N,), -1, dtype=torch.int64, device=flat.device)   # all ones = +inf key
+    if tensor:
+        idx = torch.empty(N, dtype=torch.int64, device=flat.device)
+        ops.search_slice(flat, q.embedding, cache, s, e - s, mode, idx)
+        ops.pack_exact(flat, q.embedding, idx, packed)
+    elif e > s:
+        ops.search_packed(flat, q.embedding[s:e], cache.ee_half[0, s:e], s, packed)
+    packed = reduce_min(packed)
     out = torch.empty_like(packed)
-    ops.minloc_unpack(packed, out)
+    (ops.minloc_unpack24 if tensor else ops.minloc_unpack)(packed, out)
     return out

@@ -1,0 +1,80 @@
+"""Multi-GPU checks run under torchrun (one process per GPU, NCCL); launched by the gpu tests when >= 2 GPUs exist,
+or by hand:  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multi_gpu_worker.py all
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def sharded_search(dev, rank, world):
+    import pytorch_vae_b200 as vq
+    from pytorch_vae_b200 import sharding as S
+    K, D, N = 8192, 256, 50000
+    gen = torch.Generator(device=dev).manual_seed(11)             # identical tensors on every rank
+    E = torch.randn(K, D, device=dev, generator=gen) / np.sqrt(D)
+    E[K // 2 + 7] = E[3]                                          # a twin in the other rank's slice
+    z = torch.randn(N, D, device=dev, generator=gen)
+    z[:64] = E[3] + 0.01 * torch.randn(64, D, device=dev, generator=gen)
+    q = vq.VectorQuantizerEMA(K, D, print_init=False).to(dev).eval()
+    q.embedding.copy_(E)
+    with torch.no_grad():
+        full = q(z.view(1, N, D), do_ema_update=False)[2].view(-1)
+        got = S.codebook_sharded_search(q, z)
+    torch.cuda.synchronize()
+    assert torch.equal(got, full), f"rank {rank}: {(got != full).sum().item()} rows differ"
+    assert bool((got[:64] == 3).all())
+    gathered = [torch.empty_like(got) for _ in range(world)]
+    dist.all_gather(gathered, got)
+    assert all(torch.equal(g, got) for g in gathered)             # identical on every rank
+    if rank == 0:
+        print("sharded_search ok", flush=True)
+
+
+def row_sharded_stats(dev, rank, world):
+    """Rows sharded, codebook replicated, stats_sync: the all-reduced statistics equal the single-GPU statistics of the
+    concatenated batch; the indices equal the replicated run's slice."""
+    import pytorch_vae_b200 as vq
+    from pytorch_vae_b200 import sharding as S
+    K, D, N = 512, 64, 1 << 16
+    gen = torch.Generator(device=dev).manual_seed(5)
+    E = torch.randn(K, D, device=dev, generator=gen) / np.sqrt(D)
+    z = torch.randn(N // 64, 64, D, device=dev, generator=gen)
+    q1 = vq.VectorQuantizerEMA(K, D, print_init=False).to(dev).eval()
+    q1.embedding.copy_(E)
+    with torch.no_grad():
+        st, zq, idx, stats = q1(z, do_ema_update=False)
+    a, b = S.shard_rows(N // 64, world, rank)
+    q2 = vq.VectorQuantizerEMA(K, D, print_init=False).to(dev).eval()
+    q2.embedding.copy_(E)
+    q2.stats_sync = True
+    with torch.no_grad():
+        st2, zq2, idx2, stats2 = q2(z[a:b].contiguous(), do_ema_update=False)
+    torch.cuda.synchronize()
+    assert torch.equal(idx2, idx[a:b]) and torch.equal(zq2, zq[a:b])
+    assert torch.allclose(stats2, stats, rtol=1e-5), (stats2, stats)
+    assert torch.equal(q2._ep_usage, q1._ep_usage) and float(q2._ep_cnt) == float(q1._ep_cnt) == N
+    assert abs(float(q2.last_commit) - float(q1.last_commit)) < 1e-5 * float(q1.last_commit)
+    if rank == 0:
+        print("row_sharded_stats ok", flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    try:
+        if what in ("sharded_search", "all"):
+            sharded_search(dev, rank, world)
+        if what in ("row_sharded_stats", "all"):
+            row_sharded_stats(dev, rank, world)
+    finally:
+        dist.destroy_process_group()

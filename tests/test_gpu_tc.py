@@ -273,3 +273,69 @@ def test_side_job_pipeline_matches_plain_chunk_pipeline(K, D, N, mask, monkeypat
     zs, En = z.view(-1, D)[rows].cpu().numpy(), E.cpu().numpy()
     mm, outside = O.near_tie_rows(zs, En, side[2].view(-1)[rows].cpu().numpy(), O.nearest_code64(zs, En))
     assert outside.size == 0 and mm.size <= 2
+
+
+def test_codebook_sharded_search_on_the_tensor_path_simulated_ranks():
+    """North star: "a codebook-sharded min-loc reduction is used when K.D exceeds the per-SM staging budget".  Four
+    simulated ranks each search their slice of 2048 codes with the tcgen05 kernels (exact winner per slice), pack
+    40 bits of the winner's exact fp64 score with its id, and the MIN over the ranks must reproduce the replicated
+    search -- including a twin pair that straddles two slices (the lower id wins)."""
+    import pytorch_vae_b200 as vq
+    from pytorch_vae_b200 import sharding as S
+    dev = torch.device("cuda:0")
+    K, D, N, world = 8192, 256, 20000, 4
+    gen = torch.Generator(device=dev).manual_seed(11)
+    E = torch.randn(K, D, device=dev, generator=gen) / np.sqrt(D)
+    E[K // 2 + 7] = E[3]                                        # twins in slices 0 and 2
+    E[K - 1] = E[K // 4 + 1]                                    # twins in slices 1 and 3
+    z = torch.randn(N, D, device=dev, generator=gen)
+    z[:50] = E[3] + 0.01 * torch.randn(50, D, device=dev, generator=gen)
+    z[50:90] = E[K - 1] + 0.01 * torch.randn(40, D, device=dev, generator=gen)
+    q = vq.VectorQuantizerEMA(K, D, print_init=False).to(dev).eval()
+    q.embedding.copy_(E)
+    with torch.no_grad():
+        full = q(z.view(1, N, D), do_ema_update=False)[2].view(-1)
+    assert bool((full[:50] == 3).all()) and bool((full[50:90] == K // 4 + 1).all())
+    assert vq._cabi.lib.vqb200_search_path(N, K // world, D, 0) >= 1      # the slices take the tensor path
+    packs = []
+    for r in range(world):
+        S.sharded_search_slice(q, z, world, r, lambda p: (packs.append(p.clone()), p)[1])
+    sign = -(2 ** 63)
+    best = torch.stack([p ^ sign for p in packs]).min(0).values ^ sign
+    out = torch.empty_like(full)
+    vq.ops.minloc_unpack24(best, out)
+    assert torch.equal(out, full)
+    # world = 1 degenerates to the plain search
+    assert torch.equal(S.sharded_search_slice(q, z, 1, 0, lambda p: p), full)
+
+
+def test_codebook_sharded_search_two_gpus_nccl():
+    """The same over NCCL on two real GPUs (torchrun, one process per GPU): sharded == replicated, twins across the
+    shards resolve to the lower id.  Skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631",
+                        os.path.join(root, "tests", "multi_gpu_worker.py"), "sharded_search"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "sharded_search ok" in r.stdout
+
+
+def test_row_sharded_statistics_two_gpus_nccl():
+    """Rows sharded over two GPUs with stats_sync: indices equal the replicated run's slice, the all-reduced statistics
+    and the epoch accumulators (global position count included) equal the single-GPU ones.  Skipped on one GPU."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29632",
+                        os.path.join(root, "tests", "multi_gpu_worker.py"), "row_sharded_stats"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "row_sharded_stats ok" in r.stdout
