@@ -33,7 +33,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 13
+#define VQB200_ABI_VERSION 14
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -112,6 +112,11 @@ VQB200_API int vqb200_search_prepped(const float* z, const uint16_t* z16, const 
  * (plane 1) and level_meta are the WHOLE cache arrays ([K_per * L, ...]); idx_out [L * N] level-major global ids. */
 VQB200_API size_t vqb200_rvq_forward_workspace_bytes(int64_t N, int K_per, int D, int L, int mode);
 VQB200_API int vqb200_rvq_forward_launches(int64_t N, int K_per, int D, int L, int mode);
+/* 1 when vqb200_rvq_forward runs the shape as ONE persistent kernel (csrc/vq_rvq_fused.cu: a CTA owns 128 rows and walks
+ * all levels -- operand tile of the residual in shared memory, tcgen05 scores in TMEM, candidate records in shared
+ * memory, exact re-rank, residual update, outputs -- without a launch between levels): D in {128, 256, 384, 512},
+ * K_per >= 128, 2 <= L <= 8. */
+VQB200_API int vqb200_rvq_fused_supported(int64_t N, int K_per, int D, int L, int mode);
 VQB200_API int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp,
                        const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K_per, int L,
                        int mode, int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum,

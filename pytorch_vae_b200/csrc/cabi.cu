@@ -100,14 +100,20 @@ int vqb200_search_launches(int64_t N, int K, int D, int mode) {
 static size_t rvq_align(size_t v) { return (v + 255) / 256 * 256; }
 
 size_t vqb200_rvq_forward_workspace_bytes(int64_t N, int K_per, int D, int L, int mode) {
-  (void)L;                                               // two residual buffers whatever the number of levels
-  const size_t rows = static_cast<size_t>(N > 0 ? N : 0);
+  if (rvq_fused_supported(N, K_per, D, L)) return rvq_align(rvq_fused_workspace_bytes(N, D));
+  const size_t rows = static_cast<size_t>(N > 0 ? N : 0);   // two residual buffers whatever the number of levels
   return rvq_align(vqb200_search_workspace_bytes(N, K_per, D, mode)) + 2 * rvq_align(rows * D * 4) +
          rvq_align(rows * D * 2) + rvq_align(rows * 4);
 }
 
+int vqb200_rvq_fused_supported(int64_t N, int K_per, int D, int L, int mode) {
+  (void)mode;
+  return rvq_fused_supported(N, K_per, D, L) ? 1 : 0;
+}
+
 int vqb200_rvq_forward_launches(int64_t N, int K_per, int D, int L, int mode) {
   if (N <= 0 || L < 1) return 0;
+  if (rvq_fused_supported(N, K_per, D, L)) return 1;      // the persistent kernel
   const int per_search = vqb200_search_launches(N, K_per, D, mode);
   const bool tc = tc_supported(N, K_per, D);
   const int chunks = tc ? per_search / 5 : 0;
@@ -129,6 +135,9 @@ int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const u
   VQ_REQUIRE(workspace_bytes >= vqb200_rvq_forward_workspace_bytes(N, K_per, D, L, mode), VQB200_EWORKSPACE);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  if (rvq_fused_supported(N, K_per, D, L))                // every level inside ONE persistent kernel
+    return launch_rvq_fused(z, N, D, E, E_lp, bf ? ee_half_bf16 : ee_half, level_meta, K_per, L, mode, idx_out, zq_out,
+                            zq_st_out, sqerr_sum, hist, workspace, workspace_bytes, s);
   const bool tc = tc_supported(N, K_per, D);
   const int K_total = K_per * L;
   uint8_t* w = static_cast<uint8_t*>(workspace);

@@ -20,11 +20,14 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // Order-preserving float -> uint32 key with torch.argmin's NaN rule folded in:
-// NaN maps to 0, which sorts below -inf (key 0x007fffff), so a packed min picks the first NaN.
+// NaN maps to 0, so a packed min picks the first NaN.  d' = |e|^2/2 - z.e = -inf maps to 0 as well: the row-constant
+// |z|^2 is dropped here, and a row holding +-inf has |z|^2 = +inf in the reference, whose distance
+// (inf - 2 (+inf)) + |e|^2 is NaN exactly where d' is -inf -- so "first NaN or -inf" IS torch.argmin's answer for
+// such rows, also when the codebook holds a NaN code further up (tests/test_gpu_rvq_fused.py::hard_rows).
 __device__ __forceinline__ uint32_t dist_key(float d) {
   uint32_t u = __float_as_uint(d);
   uint32_t k = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-  return (d != d) ? 0u : k;
+  return (d != d || u == 0xff800000u) ? 0u : k;
 }
 __device__ __forceinline__ uint64_t pack_minloc(float d, uint32_t idx) {
   return (static_cast<uint64_t>(dist_key(d)) << 32) | idx;
@@ -140,6 +143,13 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                      int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s,
                      const GatherArgs* ga = nullptr, const PrepArgs* prep = nullptr);
+// persistent residual-VQ forward, all levels in one kernel (vq_rvq_fused.cu)
+bool rvq_fused_supported(int64_t N, int K_per, int D, int L);
+size_t rvq_fused_workspace_bytes(int64_t N, int D);
+int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
+                     const float* level_meta, int K_per, int L, int mode, int64_t* idx_out, float* zq_out,
+                     float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes,
+                     cudaStream_t s);
 bool fused_supported(int64_t N, int K, int D);
 size_t fused_workspace_bytes(int64_t N);
 int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,

@@ -715,7 +715,7 @@ pack_exact_kernel(const float* __restrict__ z, int64_t N, int D, const float* __
       const double d = 0.5 * ee - dot;                        // smaller is nearer
       uint64_t u = static_cast<uint64_t>(__double_as_longlong(d));
       u = (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);   // order-preserving
-      if (d != d) u = 0ull;                                   // NaN wins, as in torch.argmin
+      if (d != d || d == -__longlong_as_double(0x7ff0000000000000ll)) u = 0ull;   // NaN (or -inf: see dist_key) wins, as in torch.argmin
       packed[row] = ok ? ((u & ~0xffffffull) | static_cast<uint64_t>(k)) : ~0ull;
     }
   }

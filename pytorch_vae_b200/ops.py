@@ -15,6 +15,7 @@ from ._cabi import check, lib, ptr, stream_ptr
 # kernels launched by this process through the library (bench.py reports the delta per step)
 _launches = 0
 last_fused_workspace = None
+last_rvq_workspace = None
 
 
 def launch_count() -> int:
@@ -117,6 +118,8 @@ def rvq_forward(z, E, cache: CodebookCache, mode: int, idx_out, zq_out=None, zq_
                                  cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, L, mode,
                                  ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws),
                                  ws_bytes, stream_ptr()), "vqb200_rvq_forward")
+    global last_rvq_workspace
+    last_rvq_workspace = ws           # persistent kernel: counters[0] = rows that took its exhaustive search (read lazily)
     _count(lib.vqb200_rvq_forward_launches(N, K, D, L, mode))
 
 

@@ -149,6 +149,12 @@ def test_launch_and_workspace_accounting_without_a_gpu():
     N, K, D, L = 8192, 1024, 512, 4
     per = lib.vqb200_search_launches(N, K, D, 0)
     assert per == 5 and lib.vqb200_search_path(N, K, D, 0) == 1
+    # the stage-2 shape runs as ONE persistent kernel; a shape it does not take (D = 64) goes level by level
+    assert lib.vqb200_rvq_fused_supported(N, K, D, L, 0) == 1 and lib.vqb200_rvq_forward_launches(N, K, D, L, 0) == 1
+    assert lib.vqb200_rvq_forward_workspace_bytes(N, K, D, L, 0) >= 64 * 128 * D * 4
+    D = 64
+    per = lib.vqb200_search_launches(N, K, D, 0)
+    assert lib.vqb200_rvq_fused_supported(N, K, D, L, 0) == 0
     assert lib.vqb200_rvq_forward_launches(N, K, D, L, 0) == per + (L - 1) * (per - 1) + (L - 1) + 1
     assert lib.vqb200_rvq_train_launches(N, K, D, L, 0) == L * (per + 3) + 1
     ws = lib.vqb200_search_workspace_bytes(N, K, D, 0)
