@@ -181,6 +181,7 @@ int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const u
 
 // ---- the training-mode residual forward with a LOCAL EMA update after every level, in ONE call ----
 size_t vqb200_rvq_train_workspace_bytes(int64_t N, int K_per, int D, int L, int mode) {
+  if (rvq_fused_train_supported(N, K_per, D, L)) return rvq_align(rvq_fused_train_workspace_bytes(N, K_per, D, L));
   const size_t rows = static_cast<size_t>(N > 0 ? N : 0), Kt = static_cast<size_t>(K_per) * L;
   return rvq_align(vqb200_search_workspace_bytes(N, K_per, D, mode)) + 2 * rvq_align(rows * D * 4) +
          rvq_align((Kt * D + Kt) * 4);
@@ -188,6 +189,7 @@ size_t vqb200_rvq_train_workspace_bytes(int64_t N, int K_per, int D, int L, int 
 
 int vqb200_rvq_train_launches(int64_t N, int K_per, int D, int L, int mode) {
   if (N <= 0 || L < 1) return 0;
+  if (rvq_fused_train_supported(N, K_per, D, L)) return 1;               // the persistent kernel, training mode
   return L * (vqb200_search_launches(N, K_per, D, mode) + 3) + 1;      // + gather, scatter-add, EMA finalize; st_loss
 }
 
@@ -206,6 +208,10 @@ int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_
                  aligned16(ema_embedding) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, VQB200_EALIGN);
   VQ_REQUIRE(workspace_bytes >= vqb200_rvq_train_workspace_bytes(N, K_per, D, L, mode), VQB200_EWORKSPACE);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (rvq_fused_train_supported(N, K_per, D, L))          // every level, its EMA update and the cache refresh in ONE kernel
+    return launch_rvq_fused_train(z, N, D, E, E_lp_planes, ee_half, level_meta, K_per, L, mode, decay, one_minus_decay, eps,
+                                  ema_cluster_size, ema_embedding, idx_out, zq_out, zq_st_out, sqerr_sum, hist, workspace,
+                                  workspace_bytes, s);
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
   const bool tc = tc_supported(N, K_per, D);
   const int K_total = K_per * L;

@@ -45,6 +45,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// vector reduction into global memory (sm_90+): one L2 atomic transaction per 16 bytes
+__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 // Streaming 128-bit accesses: rows are touched once, keep them out of L1.
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
   float4 r;
@@ -150,6 +156,13 @@ int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uin
                      const float* level_meta, int K_per, int L, int mode, int64_t* idx_out, float* zq_out,
                      float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes,
                      cudaStream_t s);
+// the same kernel in training mode: local EMA update + cache refresh after every level inside it (one row tile per CTA)
+bool rvq_fused_train_supported(int64_t N, int K_per, int D, int L);
+size_t rvq_fused_train_workspace_bytes(int64_t N, int K_per, int D, int L);
+int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                           float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
+                           float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
+                           double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes, cudaStream_t s);
 bool fused_supported(int64_t N, int K, int D);
 size_t fused_workspace_bytes(int64_t N);
 int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,

@@ -503,10 +503,6 @@ int launch_stats_finalize_packed(const double* packed, int K_total, int levels, 
 // --------------------------------------------------------------------------------------------
 // EMA segment sums: warp per row, warp-aggregated counts, vector reductions into [K_total, D]
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ void red_add_v4(float* p, const float4& v) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
-}
 
 constexpr int SCATTER_SLICES = 4;   // float4 slices per lane held in registers: D <= 512
 

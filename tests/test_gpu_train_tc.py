@@ -120,8 +120,60 @@ def run_case(vq, dev, name, expect_fused, graph=False):
 
 
 def test_config5_training_steps_on_tensor_path(vq, dev):
-    """BASELINE configs[4]: K_per = 1024, D = 512, L = 4, N = 8192 through vqb200_rvq_train_forward."""
+    """BASELINE configs[4]: K_per = 1024, D = 512, L = 4, N = 8192 through vqb200_rvq_train_forward -- ONE persistent
+    kernel (csrc/vq_rvq_fused.cu, training mode: search, residual, EMA segment sums, the update of ALL codes and the
+    cache refresh after every level behind grid-wide barriers)."""
+    assert vq._cabi.lib.vqb200_rvq_train_launches(8192, 1024, 512, 4, 0) == 1
     run_case(vq, dev, "c5_train", expect_fused=False)
+
+
+def test_config5_training_steps_level_by_level(vq, dev, monkeypatch):
+    """The same three steps with the persistent kernel switched off: search -> gather -> scatter-add -> refresh per level."""
+    monkeypatch.setenv("VQB200_NO_RVQ_FUSED_TRAIN", "1")
+    assert vq._cabi.lib.vqb200_rvq_train_launches(8192, 1024, 512, 4, 0) > 4
+    run_case(vq, dev, "c5_train", expect_fused=False)
+
+
+@pytest.mark.parametrize("K_per,D,L,N,mode", [
+    (1024, 512, 4, 8192, "fp32"),
+    (1024, 512, 4, 9000, "fp32"),          # ragged last tile of 64
+    (300, 256, 3, 12000, "fp32"),          # 128-row tiles, N = 256 code tiles, codes per level off the tile
+    (256, 128, 2, 700, "bf16_input"),
+    (1024, 512, 8, 2048, "fp32"),
+])
+def test_persistent_training_kernel_matches_level_pipeline(vq, dev, monkeypatch, K_per, D, L, N, mode):
+    """Three training steps (from a random codebook with the reference's zero EMA buffers, so levels collapse and the
+    duplicate-zero-code rule is on the path) through the persistent kernel and through the level-by-level pipeline:
+    same indices (both re-rank exactly; the segment sums differ in summation order, which may move a later step's
+    near-ties), EMA buffers and codebook within the summation-order tolerance of the header."""
+    lib = vq._cabi.lib
+    E, z = large_case_inputs(77 + K_per + L, K_per, D, L, 3, N)     # three batches of N rows
+    z = z.reshape(3, N, D)
+
+    def run():
+        q = vq.VectorQuantizerEMA(K_per, D, num_quantizers=L, print_init=False, search_mode=mode).to(dev).train()
+        q.embedding.copy_(torch.from_numpy(E).to(dev))
+        outs = []
+        for step in range(3):
+            zt = torch.from_numpy(z[step]).to(dev).view(1, N, D)
+            st, zq, idx, stats = q(zt, do_ema_update=True)
+            outs.append((npy(idx), npy(zq).reshape(N, D), npy(st).reshape(N, D), npy(stats), float(q.last_commit)))
+        torch.cuda.synchronize()
+        return outs, npy(q.embedding), npy(q.ema_embedding), npy(q.ema_cluster_size), npy(q._ep_usage)
+    assert lib.vqb200_rvq_train_launches(N, K_per, D, L, 0) == 1
+    a = run()
+    monkeypatch.setenv("VQB200_NO_RVQ_FUSED_TRAIN", "1")
+    assert lib.vqb200_rvq_train_launches(N, K_per, D, L, 0) > 1
+    b = run()
+    for step, (x, y) in enumerate(zip(a[0], b[0])):
+        same = (x[0].reshape(L, N) == y[0].reshape(L, N)).all(0)
+        assert same.mean() > (0.999 if step == 0 else 0.99), f"step {step}: {(~same).sum()} rows differ"
+        if step == 0:
+            assert np.array_equal(x[1][same], y[1][same]) and np.array_equal(x[2][same], y[2][same])
+        np.testing.assert_allclose(x[4], y[4], rtol=1e-4)
+    np.testing.assert_allclose(a[3], b[3], rtol=1e-5, atol=1e-6)
+    for u, v in ((a[1], b[1]), (a[2], b[2])):
+        np.testing.assert_allclose(u, v, rtol=1e-4, atol=2e-6 * max(1e-30, float(np.abs(v).max())) + 1e-7)
 
 
 def test_config5_training_steps_as_cuda_graph(vq, dev):
