@@ -189,7 +189,7 @@ size_t vqb200_rvq_train_workspace_bytes(int64_t N, int K_per, int D, int L, int 
 
 int vqb200_rvq_train_launches(int64_t N, int K_per, int D, int L, int mode) {
   if (N <= 0 || L < 1) return 0;
-  if (rvq_fused_train_supported(N, K_per, D, L)) return 1;               // the persistent kernel, training mode
+  if (rvq_fused_train_supported(N, K_per, D, L)) return 3;               // refresh phase 1, the persistent kernel, refresh phase 2
   return L * (vqb200_search_launches(N, K_per, D, mode) + 3) + 1;      // + gather, scatter-add, EMA finalize; st_loss
 }
 
@@ -208,7 +208,7 @@ int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_
                  aligned16(ema_embedding) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0, VQB200_EALIGN);
   VQ_REQUIRE(workspace_bytes >= vqb200_rvq_train_workspace_bytes(N, K_per, D, L, mode), VQB200_EWORKSPACE);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (rvq_fused_train_supported(N, K_per, D, L))          // every level, its EMA update and the cache refresh in ONE kernel
+  if (rvq_fused_train_supported(N, K_per, D, L))          // refresh phase 1 -> every level in ONE kernel -> refresh phase 2
     return launch_rvq_fused_train(z, N, D, E, E_lp_planes, ee_half, level_meta, K_per, L, mode, decay, one_minus_decay, eps,
                                   ema_cluster_size, ema_embedding, idx_out, zq_out, zq_st_out, sqerr_sum, hist, workspace,
                                   workspace_bytes, s);

@@ -155,8 +155,8 @@ size_t rvq_fused_workspace_bytes(int64_t N, int D);
 int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
                      const float* level_meta, int K_per, int L, int mode, int64_t* idx_out, float* zq_out,
                      float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes,
-                     cudaStream_t s);
-// the same kernel in training mode: local EMA update + cache refresh after every level inside it (one row tile per CTA)
+                     cudaStream_t s, float* seg_sum = nullptr, float* seg_cnt = nullptr);
+// training mode: refresh phase 1 -> the same kernel reducing the EMA segment sums -> refresh phase 2 (three launches)
 bool rvq_fused_train_supported(int64_t N, int K_per, int D, int L);
 size_t rvq_fused_train_workspace_bytes(int64_t N, int K_per, int D, int L);
 int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
@@ -169,9 +169,12 @@ int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, cons
                           const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                           int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
                           const uint8_t* row_mask, void* workspace, size_t workspace_bytes, cudaStream_t s);
+// chain_phase (mode 1, residual codebooks): 0 = one EMA update of every code from seg_sum / seg_cnt; 1 = the decay-only
+// updates a level's codes receive from the EARLIER levels of a training forward (level l: l of them; level 0 untouched);
+// 2 = every level's own update from its segment sums followed by the decay-only updates of the LATER levels
 int launch_codebook_refresh(int mode, const float* seg_sum, const float* seg_cnt, float decay, float omd,
                             float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb, float* E,
-                            uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s);
+                            uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s, int chain_phase = 0);
 int launch_gather(const float* z, const float* E, const int64_t* idx, int64_t N, int D, int K_total, float* zq_out,
                   int zq_accumulate, float* zq_st_out, float* residual_out, double* sqerr_sum, int32_t* hist,
                   const uint8_t* row_mask, cudaStream_t s);

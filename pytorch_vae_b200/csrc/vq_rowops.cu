@@ -12,12 +12,17 @@ namespace vqb {
 // MODE 0: derive the cache from E.  MODE 1: EMA update (models/vq_vae.py:85-89) then the cache.
 // MODE 2: Lloyd step of the k-means initialiser -- E <- segment mean where the segment is non-empty (an empty
 // cluster keeps its centroid), then the cache.
+// MODE 1 with chain_phase != 0 (training forward of a residual codebook, vq_rvq_fused.cu): the reference runs one EMA
+// update per LEVEL and every update touches all K_total codes; for the codes of another level it is a decay-only step
+// (empty one-hot columns: n = 0, s = 0).  Phase 1 applies to a code of level l the l decay-only steps of the earlier
+// levels (the state the level is searched in; level 0 keeps its E untouched), phase 2 its own update from the segment
+// sums followed by the L - 1 - l decay-only steps of the later levels.  Each step is the arithmetic of :85-88.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restrict__ seg_cnt, float decay,
                         float omd, float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb,
                         float* E, uint16_t* __restrict__ E_bf16, float* __restrict__ ee_half,
-                        float* __restrict__ level_meta) {
+                        float* __restrict__ level_meta, int chain_phase) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int D4 = D >> 2;
@@ -26,9 +31,19 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
   constexpr bool EMA = MODE == 1;
   float denom = 1.f;
   if (MODE == 2) denom = seg_cnt[row];
-  if (EMA) {
+  // decay-only steps before / after the real one, and whether the real one runs
+  const int lvl_row = row / K_per, n_levels = K_total / K_per;
+  const int n_pre = (EMA && chain_phase == 1) ? lvl_row : 0;
+  const int n_post = (EMA && chain_phase == 2) ? n_levels - 1 - lvl_row : 0;
+  const bool real = EMA && chain_phase != 1;
+  const bool touch = EMA && (real || n_pre > 0);           // phase 1 leaves level 0 exactly as it is
+  const float zero_term = __fmul_rn(0.f, omd);             // n (1 - decay) of an empty column
+  if (touch) {
     // models/vq_vae.py:85: cs.mul_(decay).add_(n * (1 - decay)) -- two roundings, no fma contraction
-    const float cs = __fadd_rn(__fmul_rn(ema_cs[row], decay), __fmul_rn(seg_cnt[row], omd));
+    float cs = ema_cs[row];
+    for (int i = 0; i < n_pre; ++i) cs = __fadd_rn(__fmul_rn(cs, decay), zero_term);
+    if (real) cs = __fadd_rn(__fmul_rn(cs, decay), __fmul_rn(seg_cnt[row], omd));
+    for (int i = 0; i < n_post; ++i) cs = __fadd_rn(__fmul_rn(cs, decay), zero_term);
     __syncwarp();
     if (lane == 0) ema_cs[row] = cs;
     denom = __fadd_rn(cs, eps);
@@ -39,14 +54,23 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
   for (int c = lane; c < D4; c += 32) {
     const int64_t o = static_cast<int64_t>(row) * D4 + c;
     float4 e;
-    if (EMA) {
-      const float4 m = reinterpret_cast<const float4*>(ema_emb)[o];
-      const float4 s = reinterpret_cast<const float4*>(seg_sum)[o];
-      float4 n;
-      n.x = __fadd_rn(__fmul_rn(m.x, decay), __fmul_rn(s.x, omd));
-      n.y = __fadd_rn(__fmul_rn(m.y, decay), __fmul_rn(s.y, omd));
-      n.z = __fadd_rn(__fmul_rn(m.z, decay), __fmul_rn(s.z, omd));
-      n.w = __fadd_rn(__fmul_rn(m.w, decay), __fmul_rn(s.w, omd));
+    if (touch) {
+      float4 n = reinterpret_cast<const float4*>(ema_emb)[o];
+      for (int i = 0; i < n_pre; ++i) {
+        n.x = __fadd_rn(__fmul_rn(n.x, decay), zero_term); n.y = __fadd_rn(__fmul_rn(n.y, decay), zero_term);
+        n.z = __fadd_rn(__fmul_rn(n.z, decay), zero_term); n.w = __fadd_rn(__fmul_rn(n.w, decay), zero_term);
+      }
+      if (real) {
+        const float4 s = reinterpret_cast<const float4*>(seg_sum)[o];
+        n.x = __fadd_rn(__fmul_rn(n.x, decay), __fmul_rn(s.x, omd));
+        n.y = __fadd_rn(__fmul_rn(n.y, decay), __fmul_rn(s.y, omd));
+        n.z = __fadd_rn(__fmul_rn(n.z, decay), __fmul_rn(s.z, omd));
+        n.w = __fadd_rn(__fmul_rn(n.w, decay), __fmul_rn(s.w, omd));
+      }
+      for (int i = 0; i < n_post; ++i) {
+        n.x = __fadd_rn(__fmul_rn(n.x, decay), zero_term); n.y = __fadd_rn(__fmul_rn(n.y, decay), zero_term);
+        n.z = __fadd_rn(__fmul_rn(n.z, decay), zero_term); n.w = __fadd_rn(__fmul_rn(n.w, decay), zero_term);
+      }
       reinterpret_cast<float4*>(ema_emb)[o] = n;
       e.x = __fdiv_rn(n.x, denom); e.y = __fdiv_rn(n.y, denom);       // :88 E = es / (cs + eps)
       e.z = __fdiv_rn(n.z, denom); e.w = __fdiv_rn(n.w, denom);
@@ -165,7 +189,7 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
 
 int launch_codebook_refresh(int mode, const float* seg_sum, const float* seg_cnt, float decay, float omd,
                             float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb, float* E,
-                            uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s) {
+                            uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s, int chain_phase) {
   const int levels = K_total / K_per;
   cudaError_t e = cudaMemsetAsync(level_meta, 0, sizeof(float) * VQB200_LEVEL_META_FLOATS * levels, s);
   if (e != cudaSuccess) return status_of(e);
@@ -173,13 +197,13 @@ int launch_codebook_refresh(int mode, const float* seg_sum, const float* seg_cnt
   const int blocks = (K_total + wpb - 1) / wpb;
   if (mode == 1)
     codebook_refresh_kernel<1><<<blocks, wpb * 32, 0, s>>>(seg_sum, seg_cnt, decay, omd, eps, K_total, D,
-                                                          K_per, ema_cs, ema_emb, E, E_bf16, ee_half, level_meta);
+                                                          K_per, ema_cs, ema_emb, E, E_bf16, ee_half, level_meta, chain_phase);
   else if (mode == 2)
     codebook_refresh_kernel<2><<<blocks, wpb * 32, 0, s>>>(seg_sum, seg_cnt, 0.f, 0.f, 0.f, K_total, D, K_per,
-                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta);
+                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta, 0);
   else
     codebook_refresh_kernel<0><<<blocks, wpb * 32, 0, s>>>(nullptr, nullptr, 0.f, 0.f, 0.f, K_total, D, K_per,
-                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta);
+                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta, 0);
   return status_of(cudaGetLastError());
 }
 

@@ -56,20 +56,9 @@ struct RvqParams {
   int* hist;                    // [L * K_per]
   int* counters;                // [0] rows that took the exhaustive search, [1] rows the one-thread prune did not certify
   long long* trace;             // VQB200_DEBUG=5: CTA 0, first row tile: [role 0..2][level][event < 8] clock64 stamps
-  // ---- training mode (TRAIN): the local EMA update of models/vq_vae.py:251 / :77-89 after EVERY level, inside the kernel
-  float* E_rw;                  // = E
-  uint16_t* plane_bf16;         // [K_total, D] bf16 operand plane
-  uint16_t* plane_f16;          // [K_total, D] fp16 operand plane
-  float* ee_rw;                 // [2][K_total]  |e|^2/2 of the fp32 codes / of the bf16-rounded codes
-  float* level_meta_rw;         // [L][8] the cache's copy (left in its canonical state at the end)
-  float* meta_buf;              // [2][RQ_MAXL][8] level norms of the refreshed codebook, double-buffered by level parity
-  float* ema_cs;                // [K_total]
-  float* ema_emb;               // [K_total, D]
-  float* seg_sum;               // [K_total, D] zero on entry
-  float* seg_cnt;               // [K_total]    zero on entry
-  unsigned* grid_bar;           // zero on entry
-  float decay, omd, eps;
-  int K_total;
+  // training mode (SCATTER): the EMA segment sums of models/vq_vae.py:80-83, per level, zero on entry
+  float* seg_sum;               // [L * K_per, D]  sum of the residual rows that chose the code
+  float* seg_cnt;               // [L * K_per]     how many did
 };
 // roles: 0 = MMA warp, 1 = first scanning warp (warp 4), 2 = first helper warp (warp 2)
 #define RQ_TR(role, lvl, ev)                                                                               \
@@ -131,19 +120,9 @@ __device__ __forceinline__ void rq_scan(const uint32_t (&v)[32], uint32_t code0,
 // ---- one row of the tile: fp32 values (this lane's SL float4 slices) -> 16-bit operand row + margin.  Free
 // __forceinline__ functions, not lambdas: an out-of-line call would pass the row by address and park every row buffer
 // of the caller in local memory (each load then waits for its own store: measured 30 k cycles per level).
-__device__ __forceinline__ float rq_margin(bool bf16, int D, float ss, float sse, const float* meta) {
-  float m;
-  if (bf16) m = 2.f * static_cast<float>(D + 32) * 1.1920929e-7f * (sqrtf(ss) * 1.0001f) * meta[2] + 1e-30f;
-  else m = admission_margin_fp32(ss, sse, meta[0], meta[4], meta[5], D);
-  if (meta[1] != 0.f || !(ss < __int_as_float(0x7f800000)) || !(sse < __int_as_float(0x7f800000)))
-    m = __int_as_float(0x7fc00000);   // NaN: exhaustive search
-  return m;
-}
-// DEFER: the level norms are not known yet (training: the codebook is refreshed first) -- leave |r|^2 and |r - r~|^2 in
-// norms_out[r][2]; the margins are formed once the refreshed norms exist.
-template <int SL, bool BF16, int BM, bool DEFER = false>
+template <int SL, bool BF16, int BM>
 __device__ __forceinline__ void rq_emit_operand_row(uint8_t* a_tile, float* margin_s, int r, const float4 (&v)[SL],
-                                                    const float* meta, int lane, float* norms_out = nullptr) {
+                                                    const float* meta, int lane) {
   constexpr int D = SL * 128;
   float ss = 0.f, sse = 0.f;
 #pragma unroll
@@ -172,25 +151,26 @@ __device__ __forceinline__ void rq_emit_operand_row(uint8_t* a_tile, float* marg
   ss = warp_sum(ss);
   sse = warp_sum(sse);
   if (lane == 0) {
-    if (DEFER) { norms_out[r * 2] = ss; norms_out[r * 2 + 1] = sse; }
-    else margin_s[r] = rq_margin(BF16, D, ss, sse, meta);
+    float m;
+    if (BF16) m = 2.f * static_cast<float>(D + 32) * 1.1920929e-7f * (sqrtf(ss) * 1.0001f) * meta[2] + 1e-30f;
+    else m = admission_margin_fp32(ss, sse, meta[0], meta[4], meta[5], D);
+    if (meta[1] != 0.f || !(ss < __int_as_float(0x7f800000)) || !(sse < __int_as_float(0x7f800000)))
+      m = __int_as_float(0x7fc00000);   // NaN: exhaustive search
+    margin_s[r] = m;
   }
 }
 // one code row of the exact re-rank (fp32 codes; bf16_input mode: the rounded plane)
-template <bool CG>
-__device__ __forceinline__ float4 rq_ld4(const float4* p) { return CG ? __ldcg(p) : __ldg(p); }
-template <int SL, bool BF16, bool CG = false>
+template <int SL, bool BF16>
 __device__ __forceinline__ void rq_load_code_row(float4 (&ev)[SL], const float* E, const uint16_t* E_lp, int64_t gid, int lane) {
   constexpr int D = SL * 128;
 #pragma unroll
   for (int s = 0; s < SL; ++s) {
     if (BF16) {
-      const uint2 b = CG ? __ldcg(reinterpret_cast<const uint2*>(E_lp + gid * D + s * 128 + lane * 4))
-                         : *reinterpret_cast<const uint2*>(E_lp + gid * D + s * 128 + lane * 4);
+      const uint2 b = *reinterpret_cast<const uint2*>(E_lp + gid * D + s * 128 + lane * 4);
       ev[s] = make_float4(__uint_as_float(b.x << 16), __uint_as_float(b.x & 0xffff0000u),
                           __uint_as_float(b.y << 16), __uint_as_float(b.y & 0xffff0000u));
     } else {
-      ev[s] = rq_ld4<CG>(reinterpret_cast<const float4*>(E + gid * D + s * 128 + lane * 4));
+      ev[s] = __ldg(reinterpret_cast<const float4*>(E + gid * D + s * 128 + lane * 4));
     }
   }
 }
@@ -218,11 +198,9 @@ __device__ __forceinline__ double rq_exact_score(const float4 (&v)[SL], const fl
 }
 // exhaustive exact search of one level by the warp: d' = |e|^2/2 - r.e (fp32), packed (key, index) minimum -- the rule
 // of search_simt_kernel (lowest index on ties, a NaN distance wins).  Rare: kept out of line; it re-loads the row.
-// first_zero (training): K_per - local index of the level's first all-zero code (0 = none); the other all-zero codes are
-// skipped, as the refreshed cache marks them with |e|^2/2 = +inf (see codebook_refresh_kernel).
-template <int SL, bool BF16, bool CG = false>
+template <int SL, bool BF16>
 __device__ __noinline__ uint32_t rq_exhaustive(const float* row, const float* E, const uint16_t* E_lp, const float* ee_half,
-                                               int K_per, int l, int lane, int first_zero = 0) {
+                                               int K_per, int l, int lane) {
   uint64_t bestk = ~0ull;
   float4 x[SL];
 #pragma unroll
@@ -238,9 +216,8 @@ __device__ __noinline__ uint32_t rq_exhaustive(const float* row, const float* E,
     for (int u = 0; u < XB; ++u) {
       const int k = k0 + u < K_per ? k0 + u : K_per - 1;
       const int64_t gid = static_cast<int64_t>(l) * K_per + k;
-      eeh[u] = CG ? __ldcg(ee_half + gid) : ee_half[gid];
-      if (CG && eeh[u] == 0.f && first_zero > 0 && K_per - k != first_zero) eeh[u] = __int_as_float(0x7f800000);
-      rq_load_code_row<SL, BF16, CG>(e4[u], E, E_lp, gid, lane);
+      eeh[u] = ee_half[gid];
+      rq_load_code_row<SL, BF16>(e4[u], E, E_lp, gid, lane);
     }
     float dot[XB];
 #pragma unroll
@@ -264,112 +241,15 @@ __device__ __noinline__ uint32_t rq_exhaustive(const float* row, const float* E,
   return static_cast<uint32_t>(bestk & 0xffffffffull);
 }
 
-// ---- training mode helpers
-__device__ __forceinline__ unsigned rq_ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// Barrier across the (co-resident: cooperative launch, one CTA per SM) grid, entered by the fourteen worker warps of
-// every CTA.  Everything written before it is visible to every thread after it (gpu-scope fences on both sides; the
-// second one also drops this SM's L1 lines).
-__device__ __forceinline__ void rq_grid_barrier(unsigned* ctr, unsigned target) {
-  __threadfence();
-  rq_bar_workers();
-  if (threadIdx.x == 64) {
-    atomicAdd(ctr, 1u);
-    unsigned spins = 0;
-    while (rq_ld_acquire(ctr) < target)
-      if (++spins > (1u << 22)) __trap();                 // a protocol bug must fault, never hang the GPU
-    __threadfence();
-  }
-  rq_bar_workers();
-}
-
-// EMA update (models/vq_vae.py:85-89, for ALL codes of ALL levels) and cache refresh of the code rows gw, gw + GW, ... by
-// one warp each: the arithmetic of codebook_refresh_kernel<1> (vq_rowops.cu), reading the segment sums the row passes
-// of this level reduced into seg_sum / seg_cnt and zeroing them for the next level.  Level norms are max-reduced into
-// meta_acc (shared memory, [RQ_MAXL][8] ints).
-template <int SL>
-__device__ __forceinline__ void rq_refresh_codes(const RvqParams& p, int gw, int GW, int lane, int* meta_acc) {
-  constexpr int D4 = SL * 32;
-  float4* EM = reinterpret_cast<float4*>(p.ema_emb);
-  float4* SG = reinterpret_cast<float4*>(p.seg_sum);
-  float4* E4 = reinterpret_cast<float4*>(p.E_rw);
-  uint2* PB = reinterpret_cast<uint2*>(p.plane_bf16);
-  uint2* PH = reinterpret_cast<uint2*>(p.plane_f16);
-  for (int row = gw; row < p.K_total; row += GW) {
-    // :85 cs.mul_(decay).add_(n * (1 - decay)) -- two roundings, no fma contraction
-    const float cs = __fadd_rn(__fmul_rn(__ldcg(p.ema_cs + row), p.decay), __fmul_rn(__ldcg(p.seg_cnt + row), p.omd));
-    __syncwarp();
-    if (lane == 0) { p.ema_cs[row] = cs; p.seg_cnt[row] = 0.f; }
-    const float denom = __fadd_rn(cs, p.eps);
-    double acc = 0.0, accb = 0.0, accd = 0.0, acch = 0.0, accdh = 0.0;
-    bool bad = false;
-#pragma unroll
-    for (int sl = 0; sl < SL; ++sl) {
-      const int64_t o = static_cast<int64_t>(row) * D4 + sl * 32 + lane;
-      const float4 m = __ldcg(EM + o), sm = __ldcg(SG + o);
-      SG[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 n, e;
-      n.x = __fadd_rn(__fmul_rn(m.x, p.decay), __fmul_rn(sm.x, p.omd));
-      n.y = __fadd_rn(__fmul_rn(m.y, p.decay), __fmul_rn(sm.y, p.omd));
-      n.z = __fadd_rn(__fmul_rn(m.z, p.decay), __fmul_rn(sm.z, p.omd));
-      n.w = __fadd_rn(__fmul_rn(m.w, p.decay), __fmul_rn(sm.w, p.omd));
-      EM[o] = n;
-      e.x = __fdiv_rn(n.x, denom); e.y = __fdiv_rn(n.y, denom);       // :88 E = es / (cs + eps)
-      e.z = __fdiv_rn(n.z, denom); e.w = __fdiv_rn(n.w, denom);
-      E4[o] = e;
-      const __nv_bfloat16 b0 = __float2bfloat16_rn(e.x), b1 = __float2bfloat16_rn(e.y),
-                          b2 = __float2bfloat16_rn(e.z), b3 = __float2bfloat16_rn(e.w);
-      uint2 pk;
-      pk.x = static_cast<uint32_t>(__bfloat16_as_ushort(b0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b1)) << 16);
-      pk.y = static_cast<uint32_t>(__bfloat16_as_ushort(b2)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b3)) << 16);
-      PB[o] = pk;
-      const float f0 = __bfloat162float(b0), f1 = __bfloat162float(b1), f2 = __bfloat162float(b2), f3 = __bfloat162float(b3);
-      acc += static_cast<double>(e.x) * e.x + static_cast<double>(e.y) * e.y + static_cast<double>(e.z) * e.z +
-             static_cast<double>(e.w) * e.w;
-      accb += static_cast<double>(f0) * f0 + static_cast<double>(f1) * f1 + static_cast<double>(f2) * f2 +
-              static_cast<double>(f3) * f3;
-      {
-        const double d0 = e.x - f0, d1 = e.y - f1, d2 = e.z - f2, d3 = e.w - f3;
-        accd += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-      }
-      {
-        const uint16_t h0 = f16_bits_flush(e.x), h1 = f16_bits_flush(e.y), h2 = f16_bits_flush(e.z), h3 = f16_bits_flush(e.w);
-        uint2 ph;
-        ph.x = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
-        ph.y = static_cast<uint32_t>(h2) | (static_cast<uint32_t>(h3) << 16);
-        PH[o] = ph;
-        const double g0 = f16_bits_to_float(h0), g1 = f16_bits_to_float(h1), g2 = f16_bits_to_float(h2), g3 = f16_bits_to_float(h3);
-        acch += g0 * g0 + g1 * g1 + g2 * g2 + g3 * g3;
-        const double d0 = e.x - g0, d1 = e.y - g1, d2 = e.z - g2, d3 = e.w - g3;
-        accdh += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-      }
-      bad |= !(isfinite(e.x) && isfinite(e.y) && isfinite(e.z) && isfinite(e.w));
-    }
-    acc = warp_sum(acc); accb = warp_sum(accb); accd = warp_sum(accd); acch = warp_sum(acch); accdh = warp_sum(accdh);
-    bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0) {
-      p.ee_rw[row] = static_cast<float>(0.5 * acc);
-      p.ee_rw[p.K_total + row] = static_cast<float>(0.5 * accb);
-      const float kInfF = __int_as_float(0x7f800000);
-      const float n0 = static_cast<float>(sqrt(acc)) * 1.0000002f, n1 = static_cast<float>(sqrt(accb)) * 1.0000002f;
-      const float n3 = static_cast<float>(sqrt(accd)) * 1.0000002f;
-      const float n4 = static_cast<float>(sqrt(acch)) * 1.0000002f, n5 = static_cast<float>(sqrt(accdh)) * 1.0000002f;
-      int* ma = meta_acc + (row / p.K_per) * VQB200_LEVEL_META_FLOATS;
-      if (n0 == n0 && n0 < kInfF) atomicMax(ma + 0, __float_as_int(n0));
-      if (n1 == n1 && n1 < kInfF) atomicMax(ma + 2, __float_as_int(n1));
-      if (n3 == n3 && n3 < kInfF) atomicMax(ma + 3, __float_as_int(n3));
-      if (n4 == n4) atomicMax(ma + 4, __float_as_int(n4));
-      if (n5 == n5) atomicMax(ma + 5, __float_as_int(n5));
-      if (acc == 0.0) atomicMax(ma + 7, p.K_per - (row % p.K_per));     // the LOWEST all-zero code of the level
-      if (bad || !(acc == acc) || isinf(static_cast<float>(acc))) ma[1] = __float_as_int(1.0f);
-    }
-  }
-}
-
-template <int SL, bool BF16, int BM, int BN, bool TRAIN>
+// Training mode (SCATTER).  The reference updates the codebook after EVERY level (models/vq_vae.py:251 -> :77-89),
+// and each update touches ALL K_total codes: for the codes of another level it is a decay-only step (their one-hot
+// columns are empty: cs <- cs g, es <- es g, E <- es / (cs + eps)).  Level l is therefore searched against codes that
+// have seen l decay-only steps and nothing that depends on this batch -- so the codebook every level will be searched
+// against is known BEFORE the forward (refresh phase 1, vq_rowops.cu), the forward itself runs exactly as in eval mode
+// while it reduces the residual rows into the segment sums of their codes, and the real update of every level
+// followed by its L - 1 - l trailing decay-only steps is applied afterwards in one pass (refresh phase 2): bit for
+// bit the reference's sequence, with no synchronisation between levels.
+template <int SL, bool BF16, int BM, int BN, bool SCATTER>
 __global__ void __launch_bounds__(RQ_THREADS, 1)
 rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) {
   constexpr int D = SL * 128;
@@ -394,14 +274,13 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
   int* ctl_s = order_s + BM;                                                           // [0] hard rows, [1] grab counter
   const uint32_t bar0 = (misc + rq_misc_bytes(BM, BN) + 7u) & ~7u;
   const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * 8, bar_tfull = bar0 + 16 * 8, bar_tempty = bar0 + 18 * 8;
-  const uint32_t bar_afull = bar0 + 20 * 8, bar_go = bar0 + 21 * 8, tmem_slot = bar0 + 22 * 8;
+  const uint32_t bar_afull = bar0 + 20 * 8, tmem_slot = bar0 + 22 * 8;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, RQ_NEPI); }
     mbar_init(bar_afull, RQ_WORKERS);
-    mbar_init(bar_go, 1);
     for (int i = 0; i < 8; ++i) ctl_s[i] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -421,11 +300,7 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
     // ============================== TMA producer: codebook tiles of every level, in scan order ==============================
     uint32_t stage = 0, phase = 0;
     for (int it = 0; it < my_tiles; ++it)
-      for (int l = 0; l < p.L; ++l) {
-        if (TRAIN) {                                         // the level's operand plane is final (refreshed by the whole grid)
-          mbar_wait(bar_go, l & 1);
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-        }
+      for (int l = 0; l < p.L; ++l)
         for (int t = 0; t < p.code_tiles; ++t)
           for (int kb = 0; kb < KBLK; ++kb) {
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -436,7 +311,6 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
             __syncwarp();
             if (++stage == static_cast<uint32_t>(p.stages)) { stage = 0; phase ^= 1; }
           }
-      }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     uint32_t stage = 0, phase = 0, tg = 0, aseq = 0;
@@ -484,29 +358,15 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
     float* my_scratch = p.scratch + static_cast<int64_t>(blockIdx.x) * BM * D;
     float err_acc = 0.f;
 
-    // level norms of the codebook level l is searched against: the cache's (eval; training: level 0), or the buffer the
-    // refresh after level l - 1 filled
-    auto meta_of = [&](int l) -> const float* {
-      return (TRAIN && l > 0 ? p.meta_buf + (l & 1) * (RQ_MAXL * VQB200_LEVEL_META_FLOATS) : p.level_meta) +
-             l * VQB200_LEVEL_META_FLOATS;
-    };
     // ---- bias pre-load machinery of the scanning warps (as in search_tc_kernel)
     constexpr int BPL = WCOLS / 32;
     struct Bias { float v[BPL]; };
     auto load_bias = [&](int l, int t) -> Bias {
       Bias r;
-      int first_zero = 0;
-      if (TRAIN) first_zero = __float_as_int(__ldcg(meta_of(l) + 7));
 #pragma unroll
       for (int j = 0; j < BPL; ++j) {
         const int c = t * BN + cs * WCOLS + lane * BPL + j;
-        if (TRAIN) {
-          float e = (t >= 0 && c < p.K_per) ? __ldcg(p.ee_half + l * p.K_per + c) : -kNegInf;
-          if (e == 0.f && first_zero > 0 && p.K_per - c != first_zero) e = -kNegInf;   // duplicate all-zero code: skipped
-          r.v[j] = -e;
-        } else {
-          r.v[j] = (t >= 0 && c < p.K_per) ? -p.ee_half[l * p.K_per + c] : kNegInf;
-        }
+        r.v[j] = (t >= 0 && c < p.K_per) ? -p.ee_half[l * p.K_per + c] : kNegInf;
       }
       return r;
     };
@@ -541,7 +401,7 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
     };
     int t_ahead = -1, l_ahead = 0;
     Bias bias_next{};
-    if (scanner && !TRAIN) {
+    if (scanner) {
       for (uint32_t b = 0; b < 2; ++b) {
         int ll;
         const int tt = la_next(ll);
@@ -556,8 +416,33 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
 
     uint8_t* a_tile = gen + (a_smem - base);
     uint32_t tg = 0, aseq = 0;
-    unsigned gbar = 0;                                      // grid barriers passed (training)
-    if (TRAIN && warp == 2 && lane == 0) mbar_arrive(bar_go);   // level 0 reads the codebook as it was handed in
+    // SCATTER: runs of rows (in this warp's order) that chose the same code are summed in registers and cost ONE set of
+    // reductions (a collapsed level sends every row to one code: thousands of reductions on 128 addresses otherwise)
+    float4 run[SCATTER ? SL : 1];
+    int run_gid = -1, run_cnt = 0;
+    auto run_flush = [&]() {
+      if (!SCATTER || run_gid < 0) return;
+#pragma unroll
+      for (int s = 0; s < (SCATTER ? SL : 1); ++s)
+        red_add_v4(p.seg_sum + static_cast<int64_t>(run_gid) * D + s * 128 + lane * 4, run[s]);
+      if (lane == 0) {
+        atomicAdd(p.seg_cnt + run_gid, static_cast<float>(run_cnt));
+        if (p.hist) atomicAdd(p.hist + run_gid, run_cnt);
+      }
+      run_gid = -1;
+    };
+    auto run_add = [&](int gid, const float4 (&v)[SL]) {
+      if (!SCATTER) return;
+      if (gid != run_gid) {
+        run_flush();
+        run_gid = gid; run_cnt = 0;
+#pragma unroll
+        for (int s = 0; s < (SCATTER ? SL : 1); ++s) run[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      ++run_cnt;
+#pragma unroll
+      for (int s = 0; s < (SCATTER ? SL : 1); ++s) { run[s].x += v[s].x; run[s].y += v[s].y; run[s].z += v[s].z; run[s].w += v[s].w; }
+    };
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
       const int64_t row0 = static_cast<int64_t>(tile) * BM;
@@ -598,29 +483,12 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
           float best = kNegInf;
           float thr = margin == margin ? -3.0e38f : margin;  // lowest finite value: -inf chunks are never admitted
           int cnt = 0;
-          if (TRAIN) {
-            // the accumulator buffers of the level's first two tiles are armed here, once the refreshed |e|^2/2 exist
-            // (eval arms them two tiles ahead, across the level boundary)
-            for (int t = 0; t < 2 && t < p.code_tiles; ++t) {
-              preload(load_bias(l, t), (tg + t) & 1);
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_tempty + 8 * ((tg + t) & 1));
-            }
-          }
           for (int t = 0; t < p.code_tiles; ++t, ++tg) {
             const uint32_t b = tg & 1;
-            Bias bias;
-            int t_cur_ahead;
-            if (TRAIN) {
-              t_cur_ahead = t + 2 < p.code_tiles ? t + 2 : -1;
-              bias = load_bias(l, t_cur_ahead);
-            } else {
-              bias = bias_next;
-              t_cur_ahead = t_ahead;
-              t_ahead = la_next(l_ahead);
-              bias_next = load_bias(l_ahead, t_ahead);
-            }
+            const Bias bias = bias_next;
+            const int t_cur_ahead = t_ahead;
+            t_ahead = la_next(l_ahead);
+            bias_next = load_bias(l_ahead, t_ahead);
             mbar_wait(bar_tfull + 8 * b, (tg >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + tcol + b * BN;
@@ -632,11 +500,9 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
               tc_wait_ld();
               if (ch == WCOLS / 32 - 1) {
                 if (t_cur_ahead >= 0) preload(bias, b);
-                if (!TRAIN || t_cur_ahead >= 0) {             // training: the next level arms its own first buffers
-                  tc_fence_before();
-                  __syncwarp();
-                  if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
               }
               rq_scan(v, code_t + ch * 32, margin, best, thr, cnt, rec);
             }
@@ -724,8 +590,7 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
           const int ncodes = __shfl_sync(0xffffffffu, pre, 31);
           uint32_t pick;
           if (bad || ncodes < 1 || ncodes > RQ_LIST) {       // exhaustive exact search
-            pick = rq_exhaustive<SL, BF16, TRAIN>(res_row, p.E, p.E_lp, p.ee_half, p.K_per, l, lane,
-                                                  TRAIN ? __float_as_int(__ldcg(meta_of(l) + 7)) : 0);
+            pick = rq_exhaustive<SL, BF16>(res_row, p.E, p.E_lp, p.ee_half, p.K_per, l, lane);
             if (lane == 0 && p.counters) atomicAdd(p.counters, 1);
           } else {                                            // exact re-rank of the survivors
             int at = pre - __popc(mk);
@@ -744,7 +609,7 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
 #pragma unroll
               for (int u = 0; u < CB; ++u) {
                 code[u] = my_list[c0i + u < ncodes ? c0i + u : ncodes - 1];
-                rq_load_code_row<SL, BF16, TRAIN>(ev[u], p.E, p.E_lp, static_cast<int64_t>(l) * p.K_per + code[u], lane);
+                rq_load_code_row<SL, BF16>(ev[u], p.E, p.E_lp, static_cast<int64_t>(l) * p.K_per + code[u], lane);
               }
 #pragma unroll
               for (int u = 0; u < CB; ++u) {
@@ -771,112 +636,7 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
         }
 
         const float* meta_next = p.level_meta + (l + 1 < p.L ? l + 1 : l) * VQB200_LEVEL_META_FLOATS;
-        if (TRAIN) {
-          // ---------------- training: residual update + z_q accumulation + EMA segment sums, then the refresh ----------------
-          // z_q is accumulated level by level from the codes as they are BEFORE this level's update (:248 -> :251); the
-          // residual rows fl(r) enter the segment sums of their codes (:80-83), runs of one code summed in registers
-          // first (a collapsed level sends every row to one code: thousands of reductions on 128 addresses otherwise).
-          const bool last = l + 1 == p.L;
-          float4 run[SL];
-          int run_gid = -1, run_cnt = 0;
-          auto flush = [&]() {
-            if (run_gid < 0) return;
-#pragma unroll
-            for (int s = 0; s < SL; ++s)
-              red_add_v4(p.seg_sum + static_cast<int64_t>(run_gid) * D + s * 128 + lane * 4, run[s]);
-            if (lane == 0) {
-              atomicAdd(p.seg_cnt + run_gid, static_cast<float>(run_cnt));
-              if (p.hist) atomicAdd(p.hist + run_gid, run_cnt);
-            }
-          };
-          for (int r = w; r < BM; r += RQ_WORKERS) {
-            const int64_t grow = row0 + r;
-            if (grow >= p.n_rows) {
-              if (lane == 0) { best_s[r * 2] = 0.f; best_s[r * 2 + 1] = 0.f; }
-              continue;
-            }
-            const int gid = static_cast<int>(res_s[l * BM + r]);
-            float4 v[SL], e4[SL];
-#pragma unroll
-            for (int s = 0; s < SL; ++s) {
-              v[s] = reinterpret_cast<const float4*>(res_src + r * D)[s * 32 + lane];
-              e4[s] = __ldcg(reinterpret_cast<const float4*>(p.E + static_cast<int64_t>(gid) * D) + s * 32 + lane);
-            }
-            if (gid != run_gid) {
-              flush();
-              run_gid = gid; run_cnt = 0;
-#pragma unroll
-              for (int s = 0; s < SL; ++s) run[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            ++run_cnt;
-#pragma unroll
-            for (int s = 0; s < SL; ++s) { run[s].x += v[s].x; run[s].y += v[s].y; run[s].z += v[s].z; run[s].w += v[s].w; }
-#pragma unroll
-            for (int s = 0; s < SL; ++s) {
-              float4* zq_p = reinterpret_cast<float4*>(p.zq_out + grow * D) + s * 32 + lane;
-              float4 q = e4[s];
-              if (l > 0) {
-                const float4 a = __ldcg(zq_p);
-                q.x = __fadd_rn(a.x, q.x); q.y = __fadd_rn(a.y, q.y); q.z = __fadd_rn(a.z, q.z); q.w = __fadd_rn(a.w, q.w);
-              }
-              *zq_p = q;
-              if (!last) {
-                v[s].x = __fsub_rn(v[s].x, e4[s].x); v[s].y = __fsub_rn(v[s].y, e4[s].y);
-                v[s].z = __fsub_rn(v[s].z, e4[s].z); v[s].w = __fsub_rn(v[s].w, e4[s].w);
-                reinterpret_cast<float4*>(my_scratch + r * D)[s * 32 + lane] = v[s];
-              } else {
-                const float4 zz = ld_stream(reinterpret_cast<const float4*>(p.z + grow * D) + s * 32 + lane);
-                float4 df;
-                df.x = __fsub_rn(q.x, zz.x); df.y = __fsub_rn(q.y, zz.y); df.z = __fsub_rn(q.z, zz.z); df.w = __fsub_rn(q.w, zz.w);
-                if (p.zq_st_out)
-                  st_stream(reinterpret_cast<float4*>(p.zq_st_out + grow * D) + s * 32 + lane,
-                            make_float4(__fadd_rn(zz.x, df.x), __fadd_rn(zz.y, df.y), __fadd_rn(zz.z, df.z), __fadd_rn(zz.w, df.w)));
-                err_acc = fmaf(df.x, df.x, err_acc); err_acc = fmaf(df.y, df.y, err_acc);
-                err_acc = fmaf(df.z, df.z, err_acc); err_acc = fmaf(df.w, df.w, err_acc);
-              }
-            }
-            if (!last) rq_emit_operand_row<SL, BF16, BM, true>(a_tile, margin_s, r, v, nullptr, lane, best_s);
-          }
-          flush();
-          // ---- every CTA has reduced its rows and is done reading the codebook: refresh ALL codes (:85-89)
-          int* meta_acc = cnt_s;                             // [RQ_MAXL][8]: the records are dead until the next scan
-          rq_grid_barrier(p.grid_bar, ++gbar * gridDim.x);
-          const int wt = static_cast<int>(threadIdx.x) - 64;
-          if (wt < RQ_MAXL * VQB200_LEVEL_META_FLOATS) {
-            meta_acc[wt] = 0;
-            // this level's norms have been read by everyone: their buffer is free for the refresh after the NEXT level
-            if (blockIdx.x == 0) p.meta_buf[(l & 1) * (RQ_MAXL * VQB200_LEVEL_META_FLOATS) + wt] = 0.f;
-          }
-          rq_bar_workers();
-          rq_refresh_codes<SL>(p, static_cast<int>(blockIdx.x) * RQ_WORKERS + w, static_cast<int>(gridDim.x) * RQ_WORKERS, lane, meta_acc);
-          rq_bar_workers();
-          float* meta_w = p.meta_buf + ((l + 1) & 1) * (RQ_MAXL * VQB200_LEVEL_META_FLOATS);   // norms of the refreshed codebook
-          if (wt < p.L * VQB200_LEVEL_META_FLOATS && meta_acc[wt] != 0) {
-            if ((wt & 7) == 1) meta_w[wt] = 1.0f;
-            else atomicMax(reinterpret_cast<int*>(meta_w) + wt, meta_acc[wt]);
-          }
-          rq_grid_barrier(p.grid_bar, ++gbar * gridDim.x);
-          // duplicate all-zero codes of a level leave the search (|e|^2/2 = +inf), as codebook_refresh_kernel marks them
-          for (int row = static_cast<int>(blockIdx.x) * RQ_WORKERS + w; row < p.K_total; row += static_cast<int>(gridDim.x) * RQ_WORKERS) {
-            if (lane == 0 && __ldcg(p.ee_rw + row) == 0.f) {
-              const int first = __float_as_int(__ldcg(meta_w + (row / p.K_per) * VQB200_LEVEL_META_FLOATS + 7));
-              if (first > 0 && p.K_per - (row % p.K_per) != first) {
-                p.ee_rw[row] = -kNegInf;
-                p.ee_rw[p.K_total + row] = -kNegInf;
-              }
-            }
-          }
-          if (!last) {
-            if (wt < BM) {
-              float mt[VQB200_LEVEL_META_FLOATS];
-#pragma unroll
-              for (int i = 0; i < 6; ++i) mt[i] = __ldcg(meta_w + (l + 1) * VQB200_LEVEL_META_FLOATS + i);
-              margin_s[wt] = rq_margin(BF16, D, best_s[wt * 2], best_s[wt * 2 + 1], mt);
-            }
-          } else if (blockIdx.x == 0 && wt < p.L * VQB200_LEVEL_META_FLOATS) {
-            p.level_meta_rw[wt] = meta_w[wt];                // the cache's copy, in its canonical place
-          }
-        } else if (l + 1 < p.L) {
+        if (l + 1 < p.L) {
           // ---------------- next residual fl(r - e) (models/vq_vae.py:258) ----------------
           // A row (two at D <= 256) at a time per warp, the residual row and its code row in flight together; the new
           // residual goes to the CTA's scratch tile (L2), to the operand tile and into the next level's margin.
@@ -902,6 +662,7 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
             for (int u = 0; u < RB; ++u) {
               if (rr[u] >= BM) continue;
               const bool valid = row0 + rr[u] < p.n_rows;
+              if (valid) run_add(static_cast<int>(res_s[l * BM + rr[u]]), v[u]);
 #pragma unroll
               for (int s = 0; s < SL; ++s) {
                 if (valid) {
@@ -921,7 +682,13 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
           for (int r = w; r < BM; r += RQ_WORKERS) {
             const int64_t grow = row0 + r;
             if (grow >= p.n_rows) continue;
-            if (p.hist && lane < p.L) atomicAdd(p.hist + res_s[lane * BM + r], 1);
+            if (!SCATTER && p.hist && lane < p.L) atomicAdd(p.hist + res_s[lane * BM + r], 1);
+            if (SCATTER) {
+              float4 v[SL];
+#pragma unroll
+              for (int s = 0; s < SL; ++s) v[s] = reinterpret_cast<const float4*>(res_src + r * D)[s * 32 + lane];
+              run_add(static_cast<int>(res_s[l * BM + r]), v);
+            }
 #pragma unroll
             for (int s0 = 0; s0 < SL; s0 += SS) {
               float4 zz[SS], q[SS];
@@ -970,13 +737,13 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
             }
           }
         }
+        run_flush();
         if (warp == 4) RQ_TR(1, l, 4);
         if (warp == 2) RQ_TR(2, l, 3);
         if (l + 1 < p.L) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_afull);
-          if (TRAIN && warp == 2 && lane == 0) mbar_arrive(bar_go);   // the TMA producer may fetch the refreshed level
         } else {
           rq_bar_workers();                                  // res_s / records are reused by the next tile
         }
@@ -1005,17 +772,12 @@ struct RqConfig { int BM, BN, stages, grid, smem; };
 
 // Tile shape of a launch.  BM = 64 when the batch has so few 128-row tiles that most of a second wave of SMs would
 // idle (VQB200_RVQ_BM=64|128 overrides); BN = 256 wherever the operand tile leaves room for >= 3 ring stages.
-// Training mode needs every row tile resident at once (the grid synchronises between levels): one tile per CTA.
-static bool rq_config(int64_t N, int D, RqConfig* c, bool train = false) {
+static bool rq_config(int64_t N, int D, RqConfig* c) {
   const int64_t tiles128 = (N + 127) / 128;
   int bm = tiles128 * 4 <= kNumSMs * 3 ? 64 : 128;
   if (const char* e = std::getenv("VQB200_RVQ_BM")) {
     if (e[0] == '6') bm = 64;
     else if (e[0] == '1') bm = 128;
-  }
-  if (train) {
-    if ((N + 63) / 64 > kNumSMs) bm = 128;
-    if ((N + bm - 1) / bm > kNumSMs) return false;
   }
   int bn = (bm == 64 || D <= 384) ? 256 : 128;
   int stages = 8;
@@ -1048,9 +810,7 @@ bool rvq_fused_supported(int64_t N, int K_per, int D, int L) {
 bool rvq_fused_train_supported(int64_t N, int K_per, int D, int L) {
   const char* g = std::getenv("VQB200_NO_RVQ_FUSED_TRAIN");
   if (g && g[0] == '1') return false;
-  if (!rvq_fused_supported(N, K_per, D, L)) return false;
-  RqConfig c;
-  return rq_config(N, D, &c, true);
+  return rvq_fused_supported(N, K_per, D, L);
 }
 
 size_t rvq_fused_workspace_bytes(int64_t N, int D) {
@@ -1060,60 +820,69 @@ size_t rvq_fused_workspace_bytes(int64_t N, int D) {
   return 256 + (a > b ? a : b) * D * 4;
 }
 
-// training workspace: [0, 1024) counters, grid barrier, level-norm buffers | seg_sum | seg_cnt | residual scratch tiles
+// training workspace: [0, 256) counters | seg_sum | seg_cnt | residual scratch tiles
 static size_t rq_train_seg_bytes(int K_total, int D) {
   return (static_cast<size_t>(K_total) * D * 4 + static_cast<size_t>(K_total) * 4 + 255) / 256 * 256;
 }
 size_t rvq_fused_train_workspace_bytes(int64_t N, int K_per, int D, int L) {
-  return 1024 + rq_train_seg_bytes(K_per * L, D) + rvq_fused_workspace_bytes(N, D);
+  return rq_train_seg_bytes(K_per * L, D) + rvq_fused_workspace_bytes(N, D);
 }
 
-template <int SL, int BM, int BN, bool TRAIN>
+template <int SL, int BM, int BN, bool SCATTER>
 static int launch_rq(const CUtensorMap& map_e, const RvqParams& p, bool bf, int grid, int smem, cudaStream_t s) {
   static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[current_device_slot()];
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(rvq_fused_kernel<SL, false, BM, BN, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(rvq_fused_kernel<SL, false, BM, BN, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(rvq_fused_kernel<SL, true, BM, BN, TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+      e = cudaFuncSetAttribute(rvq_fused_kernel<SL, true, BM, BN, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
     if (e != cudaSuccess) return status_of(e);
     attr_done = true;
   }
   timing_mark_begin(s);
-  cudaError_t e = cudaSuccess;
-  if (TRAIN) {
-    // the grid synchronises between levels: every CTA must be resident (one per SM, grid <= SM count) -- cooperative launch
-    void* args[2] = {const_cast<CUtensorMap*>(&map_e), const_cast<RvqParams*>(&p)};
-    const void* fn = bf ? reinterpret_cast<const void*>(rvq_fused_kernel<SL, true, BM, BN, TRAIN>)
-                        : reinterpret_cast<const void*>(rvq_fused_kernel<SL, false, BM, BN, TRAIN>);
-    e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(RQ_THREADS), args, smem, s);
-  } else {
-    if (bf) rvq_fused_kernel<SL, true, BM, BN, TRAIN><<<grid, RQ_THREADS, smem, s>>>(map_e, p);
-    else rvq_fused_kernel<SL, false, BM, BN, TRAIN><<<grid, RQ_THREADS, smem, s>>>(map_e, p);
-  }
+  if (bf) rvq_fused_kernel<SL, true, BM, BN, SCATTER><<<grid, RQ_THREADS, smem, s>>>(map_e, p);
+  else rvq_fused_kernel<SL, false, BM, BN, SCATTER><<<grid, RQ_THREADS, smem, s>>>(map_e, p);
   timing_mark_end(s);
-  return status_of(e != cudaSuccess ? e : cudaGetLastError());
+  return status_of(cudaGetLastError());
 }
 
-template <int SL, bool TRAIN>
+template <int SL, bool SCATTER>
 static int launch_rq_shape(const CUtensorMap& map_e, const RvqParams& p, bool bf, const RqConfig& c, cudaStream_t s) {
-  if (c.BM == 64) return launch_rq<SL, 64, 256, TRAIN>(map_e, p, bf, c.grid, c.smem, s);
-  if constexpr (SL == 4) return launch_rq<SL, 128, 128, TRAIN>(map_e, p, bf, c.grid, c.smem, s);
-  else return launch_rq<SL, 128, 256, TRAIN>(map_e, p, bf, c.grid, c.smem, s);
+  if (c.BM == 64) return launch_rq<SL, 64, 256, SCATTER>(map_e, p, bf, c.grid, c.smem, s);
+  if constexpr (SL == 4) return launch_rq<SL, 128, 128, SCATTER>(map_e, p, bf, c.grid, c.smem, s);
+  else return launch_rq<SL, 128, 256, SCATTER>(map_e, p, bf, c.grid, c.smem, s);
 }
 
-static int rq_launch_common(RvqParams& p, const RqConfig& c, bool train, const void* E_lp, int K_per, int L, int D, bool bf,
-                            cudaStream_t s) {
-  p.row_tiles = static_cast<int>((p.n_rows + c.BM - 1) / c.BM);
+// seg_sum / seg_cnt non-null: training mode (the caller refreshes the codebook before and after, see cabi.cu)
+int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
+                     const float* level_meta, int K_per, int L, int mode, int64_t* idx_out, float* zq_out,
+                     float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes,
+                     cudaStream_t s, float* seg_sum, float* seg_cnt) {
+  if (!rvq_fused_supported(N, K_per, D, L)) return VQB200_ESHAPE;
+  if (workspace_bytes < rvq_fused_workspace_bytes(N, D)) return VQB200_EWORKSPACE;
+  const bool bf = mode == VQB200_MODE_BF16_INPUT, scatter = seg_sum != nullptr;
+  RqConfig c;
+  if (!rq_config(N, D, &c)) return VQB200_ESHAPE;
+  RvqParams p{};
+  p.n_rows = N; p.D = D; p.K_per = K_per; p.L = L; p.mode = mode;
+  p.row_tiles = static_cast<int>((N + c.BM - 1) / c.BM);
   p.code_tiles = (K_per + c.BN - 1) / c.BN;
   p.stages = c.stages;
   // kind::f16 instruction descriptor: D = fp32, A = B = bf16 (bf16_input) or fp16, K-major, N = BN, M = BM
   p.idesc = (1u << 4) | (bf ? ((1u << 7) | (1u << 10)) : 0u) | ((static_cast<uint32_t>(c.BN) >> 3) << 17) |
             ((static_cast<uint32_t>(c.BM) >> 4) << 24);
+  p.z = z; p.E = E; p.E_lp = E_lp; p.ee_half = ee_half; p.level_meta = level_meta;
+  p.seg_sum = seg_sum; p.seg_cnt = seg_cnt;
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  p.counters = reinterpret_cast<int*>(w);
+  p.scratch = reinterpret_cast<float*>(w + 256);
+  p.idx_out = idx_out; p.zq_out = zq_out; p.zq_st_out = zq_st_out; p.sqerr_sum = sqerr_sum; p.hist = hist;
   CUtensorMap map_e;
   if (!make_tensor_map_2d(&map_e, E_lp, static_cast<int64_t>(K_per) * L, D, c.BN,
                           bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2))
     return VQB200_EDRIVER;
+  cudaError_t e = cudaMemsetAsync(p.counters, 0, 2 * sizeof(int), s);
+  if (e != cudaSuccess) return status_of(e);
   const char* dbg = std::getenv("VQB200_DEBUG");
   p.trace = nullptr;
   if (dbg && dbg[0] == '5') {
@@ -1121,7 +890,7 @@ static int rq_launch_common(RvqParams& p, const RqConfig& c, bool train, const v
     cudaMemset(p.trace, 0, 3 * RQ_MAXL * 8 * sizeof(long long));
   }
   int st;
-  if (train) {
+  if (scatter) {
     switch (D / 128) {
       case 1: st = launch_rq_shape<1, true>(map_e, p, bf, c, s); break;
       case 2: st = launch_rq_shape<2, true>(map_e, p, bf, c, s); break;
@@ -1141,7 +910,7 @@ static int rq_launch_common(RvqParams& p, const RqConfig& c, bool train, const v
     long long t0 = 0;
     for (int i = 0; i < 3 * RQ_MAXL * 8; ++i) if (p.trace[i] && (!t0 || p.trace[i] < t0)) t0 = p.trace[i];
     static const char* names[3] = {"mma ", "scan", "help"};
-    fprintf(stderr, "[vqb200] rvq fused%s: BM=%d BN=%d stages=%d grid=%d smem=%d\n", train ? " (training)" : "", c.BM, c.BN,
+    fprintf(stderr, "[vqb200] rvq fused%s: BM=%d BN=%d stages=%d grid=%d smem=%d\n", scatter ? " (training)" : "", c.BM, c.BN,
             c.stages, c.grid, c.smem);
     for (int l = 0; l < L; ++l)
       for (int r = 0; r < 3; ++r) {
@@ -1157,27 +926,8 @@ static int rq_launch_common(RvqParams& p, const RqConfig& c, bool train, const v
   return st;
 }
 
-int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
-                     const float* level_meta, int K_per, int L, int mode, int64_t* idx_out, float* zq_out,
-                     float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes,
-                     cudaStream_t s) {
-  if (!rvq_fused_supported(N, K_per, D, L)) return VQB200_ESHAPE;
-  if (workspace_bytes < rvq_fused_workspace_bytes(N, D)) return VQB200_EWORKSPACE;
-  const bool bf = mode == VQB200_MODE_BF16_INPUT;
-  RqConfig c;
-  if (!rq_config(N, D, &c)) return VQB200_ESHAPE;
-  RvqParams p{};
-  p.n_rows = N; p.D = D; p.K_per = K_per; p.L = L; p.mode = mode;
-  p.z = z; p.E = E; p.E_lp = E_lp; p.ee_half = ee_half; p.level_meta = level_meta;
-  uint8_t* w = static_cast<uint8_t*>(workspace);
-  p.counters = reinterpret_cast<int*>(w);
-  p.scratch = reinterpret_cast<float*>(w + 256);
-  p.idx_out = idx_out; p.zq_out = zq_out; p.zq_st_out = zq_st_out; p.sqerr_sum = sqerr_sum; p.hist = hist;
-  cudaError_t e = cudaMemsetAsync(p.counters, 0, 2 * sizeof(int), s);
-  if (e != cudaSuccess) return status_of(e);
-  return rq_launch_common(p, c, false, E_lp, K_per, L, D, bf, s);
-}
-
+// Training-mode forward: refresh phase 1 -> the persistent kernel with segment sums -> refresh phase 2 (see the kernel's
+// header comment for why this is the reference's level-by-level update sequence).
 int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
                            float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
                            float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
@@ -1186,29 +936,21 @@ int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t*
   if (workspace_bytes < rvq_fused_train_workspace_bytes(N, K_per, D, L)) return VQB200_EWORKSPACE;
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
   const int K_total = K_per * L;
-  RqConfig c;
-  if (!rq_config(N, D, &c, true)) return VQB200_ESHAPE;
-  RvqParams p{};
-  p.n_rows = N; p.D = D; p.K_per = K_per; p.L = L; p.mode = mode;
-  p.z = z; p.E = E; p.level_meta = level_meta;
-  p.plane_bf16 = E_lp_planes;
-  p.plane_f16 = E_lp_planes + static_cast<size_t>(K_total) * D;
-  p.E_lp = bf ? p.plane_bf16 : p.plane_f16;
-  p.ee_half = bf ? ee_half + K_total : ee_half;
-  p.E_rw = E; p.ee_rw = ee_half; p.level_meta_rw = level_meta;
-  p.ema_cs = ema_cs; p.ema_emb = ema_emb; p.decay = decay; p.omd = omd; p.eps = eps; p.K_total = K_total;
   uint8_t* w = static_cast<uint8_t*>(workspace);
-  p.counters = reinterpret_cast<int*>(w);
-  p.grid_bar = reinterpret_cast<unsigned*>(w + 64);
-  p.meta_buf = reinterpret_cast<float*>(w + 256);              // 2 x RQ_MAXL x 8 floats = 512 bytes
-  p.seg_sum = reinterpret_cast<float*>(w + 1024);
-  p.seg_cnt = p.seg_sum + static_cast<size_t>(K_total) * D;
+  float* seg_sum = reinterpret_cast<float*>(w);
+  float* seg_cnt = seg_sum + static_cast<size_t>(K_total) * D;
   const size_t seg_bytes = rq_train_seg_bytes(K_total, D);
-  p.scratch = reinterpret_cast<float*>(w + 1024 + seg_bytes + 256);
-  p.idx_out = idx_out; p.zq_out = zq_out; p.zq_st_out = zq_st_out; p.sqerr_sum = sqerr_sum; p.hist = hist;
-  cudaError_t e = cudaMemsetAsync(w, 0, 1024 + seg_bytes, s);
+  cudaError_t e = cudaMemsetAsync(w, 0, seg_bytes, s);
   if (e != cudaSuccess) return status_of(e);
-  return rq_launch_common(p, c, true, p.E_lp, K_per, L, D, bf, s);
+  int st = launch_codebook_refresh(1, seg_sum, seg_cnt, decay, omd, eps, K_total, D, K_per, ema_cs, ema_emb, E, E_lp_planes,
+                                   ee_half, level_meta, s, /*chain_phase=*/1);
+  if (st != VQB200_OK) return st;
+  const uint16_t* plane = E_lp_planes + (bf ? 0 : static_cast<size_t>(K_total) * D);
+  st = launch_rvq_fused(z, N, D, E, plane, bf ? ee_half + K_total : ee_half, level_meta, K_per, L, mode, idx_out, zq_out,
+                        zq_st_out, sqerr_sum, hist, w + seg_bytes, workspace_bytes - seg_bytes, s, seg_sum, seg_cnt);
+  if (st != VQB200_OK) return st;
+  return launch_codebook_refresh(1, seg_sum, seg_cnt, decay, omd, eps, K_total, D, K_per, ema_cs, ema_emb, E, E_lp_planes,
+                                 ee_half, level_meta, s, /*chain_phase=*/2);
 }
 
 }  // namespace vqb

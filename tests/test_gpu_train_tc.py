@@ -120,10 +120,11 @@ def run_case(vq, dev, name, expect_fused, graph=False):
 
 
 def test_config5_training_steps_on_tensor_path(vq, dev):
-    """BASELINE configs[4]: K_per = 1024, D = 512, L = 4, N = 8192 through vqb200_rvq_train_forward -- ONE persistent
-    kernel (csrc/vq_rvq_fused.cu, training mode: search, residual, EMA segment sums, the update of ALL codes and the
-    cache refresh after every level behind grid-wide barriers)."""
-    assert vq._cabi.lib.vqb200_rvq_train_launches(8192, 1024, 512, 4, 0) == 1
+    """BASELINE configs[4]: K_per = 1024, D = 512, L = 4, N = 8192 through vqb200_rvq_train_forward -- three launches:
+    the decay-only updates every level's codes receive from the earlier levels (known before the forward), ONE persistent
+    kernel for all levels that also reduces the EMA segment sums (csrc/vq_rvq_fused.cu), then every level's own update
+    and its trailing decay-only steps."""
+    assert vq._cabi.lib.vqb200_rvq_train_launches(8192, 1024, 512, 4, 0) == 3
     run_case(vq, dev, "c5_train", expect_fused=False)
 
 
@@ -160,10 +161,10 @@ def test_persistent_training_kernel_matches_level_pipeline(vq, dev, monkeypatch,
             outs.append((npy(idx), npy(zq).reshape(N, D), npy(st).reshape(N, D), npy(stats), float(q.last_commit)))
         torch.cuda.synchronize()
         return outs, npy(q.embedding), npy(q.ema_embedding), npy(q.ema_cluster_size), npy(q._ep_usage)
-    assert lib.vqb200_rvq_train_launches(N, K_per, D, L, 0) == 1
+    assert lib.vqb200_rvq_train_launches(N, K_per, D, L, 0) == 3
     a = run()
     monkeypatch.setenv("VQB200_NO_RVQ_FUSED_TRAIN", "1")
-    assert lib.vqb200_rvq_train_launches(N, K_per, D, L, 0) > 1
+    assert lib.vqb200_rvq_train_launches(N, K_per, D, L, 0) > 3
     b = run()
     for step, (x, y) in enumerate(zip(a[0], b[0])):
         same = (x[0].reshape(L, N) == y[0].reshape(L, N)).all(0)
