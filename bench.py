@@ -478,7 +478,10 @@ def run_b200(args, w, with_cpu=True):
         step_gbs = N * (12.0 * D + 8.0 * L) / (ms_step * 1e-3) / 1e9
         roof["step_achieved"] = step_gbs
         roof["step_frac"] = step_gbs / hbm
+    persistent = L > 1 and bool(lib.vqb200_rvq_fused_supported(N, K, D, L, mode))
     kname = ("quantize_fused_kernel (tcgen05 distance+argmin+gather, one pass)" if fused else
+             "rvq_fused_kernel (persistent: every level's tcgen05 search, exact re-rank, residual update and the outputs "
+             "in one launch" + ("; training: + EMA segment sums)" if train else ")") if persistent else
              "search_tc2_kernel / search_tc_kernel (tcgen05 distance+argmin; cta_group::2 pairs for large N)" if on_tc
              else "search_simt_kernel")
     roof.update({"traffic": traffic, "kernel": kname,

@@ -33,7 +33,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 14
+#define VQB200_ABI_VERSION 15
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -274,6 +274,15 @@ VQB200_API int vqb200_relayout_indices(const int64_t* idx_level_major, int Q, in
  * (scripts/decode_with_vqvae.py:110-130; models/vq_vae.py:1404-1418). */
 VQB200_API int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok, int Q, const float* E,
                              int K_total, int D, float* zq_out, void* stream);
+
+/* Token-major ids [n_tok * Q] -> decoder memory [n_tok, H] = LayerNorm(from_code(z_q)) (models/vq_vae.py:749,
+ * "from_code + mem_ln after K2").  from_code is linear, so with the projected table
+ * P = E W^T ([K_total, H], the caller rebuilds it when the codebook or the weight changes) the Linear is a gather of Q
+ * rows of P per token plus the bias; the LayerNorm (biased variance, eps, optional affine) runs on the row in registers.
+ * No GEMM over the tokens and z_q never reaches memory.  H % 4 == 0, H <= 1024; bias / ln_weight / ln_bias may be NULL. */
+VQB200_API int vqb200_indices_to_memory(const void* idx, int idx_elem_bytes, int64_t n_tok, int Q, const float* P,
+                             int K_total, int H, const float* bias, const float* ln_weight, const float* ln_bias,
+                             float ln_eps, float* memory_out, void* stream);
 
 /* Codebook-sharded search support: a (distance, index) pair packed into one
  * orderable uint64 so that an all-reduce(MIN) performs a tie-stable min-loc.

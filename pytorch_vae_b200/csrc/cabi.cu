@@ -499,6 +499,18 @@ int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok,
                                   static_cast<cudaStream_t>(stream));
 }
 
+int vqb200_indices_to_memory(const void* idx, int idx_elem_bytes, int64_t n_tok, int Q, const float* P, int K_total,
+                             int H, const float* bias, const float* ln_weight, const float* ln_bias, float ln_eps,
+                             float* memory_out, void* stream) {
+  VQ_REQUIRE(Q > 0 && n_tok >= 0 && K_total > 0 && H > 0, VQB200_EINVAL);
+  VQ_REQUIRE(n_tok == 0 || (idx && P && memory_out), VQB200_EINVAL);
+  VQ_REQUIRE(H % 4 == 0 && H <= 1024, VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(P) && aligned16(memory_out) && aligned16(bias) && aligned16(ln_weight) && aligned16(ln_bias),
+             VQB200_EALIGN);
+  return launch_indices_to_memory(idx, idx_elem_bytes, n_tok, Q, P, K_total, H, bias, ln_weight, ln_bias, ln_eps,
+                                  memory_out, static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_rvq_finalize(const float* z, const int64_t* idx_level_major, int64_t level_stride, int64_t N, int D, int L,
                         const float* E, int K_total, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
                         void* stream) {

@@ -201,6 +201,9 @@ int launch_soft_assign(const float* z, int64_t N, int D, const float* E, int K, 
                        cudaStream_t s);
 int launch_indices_to_latent(const void* idx, int bytes, int64_t n_tok, int Q, const float* E, int K_total, int D,
                              float* out, cudaStream_t s);
+int launch_indices_to_memory(const void* idx, int bytes, int64_t n_tok, int Q, const float* P, int K_total, int H,
+                             const float* bias, const float* ln_w, const float* ln_b, float ln_eps, float* out,
+                             cudaStream_t s);
 int launch_minloc_unpack(const uint64_t* p, int64_t N, int64_t* out, cudaStream_t s);
 int launch_pack_exact(const float* z, int64_t N, int D, const float* E, int K_total, const int64_t* idx, uint64_t* packed,
                       cudaStream_t s);

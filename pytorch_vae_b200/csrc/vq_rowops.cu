@@ -697,6 +697,94 @@ int launch_indices_to_latent(const void* idx, int bytes, int64_t n_tok, int Q, c
   return status_of(cudaGetLastError());
 }
 
+// --------------------------------------------------------------------------------------------
+// indices -> decoder memory (models/vq_vae.py:749: memory = mem_ln(from_code(z_q)), scripts/decode_with_vqvae.py:110-130)
+// from_code is linear, so from_code(sum_q E[i_q]) = sum_q (E W^T)[i_q] + b: with the projected table P = E W^T
+// ([K_total, H], rebuilt only when the codebook or the weight changes) the Linear over N tokens becomes a gather of Q
+// rows per token -- no GEMM, no z_q round trip -- and the LayerNorm runs on the row while it is in registers.
+// One warp per token, H <= 1024 (8 float4 slices per lane).
+// --------------------------------------------------------------------------------------------
+constexpr int MEM_SLICES = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+indices_to_memory_kernel(const T* __restrict__ idx, int64_t n_tok, int Q, const float4* __restrict__ P, int K_total,
+                         int H4, const float4* __restrict__ bias, const float4* __restrict__ ln_w,
+                         const float4* __restrict__ ln_b, float ln_eps, float4* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const float inv_h = 1.f / static_cast<float>(H4 * 4);
+  for (int64_t tok = warp0; tok < n_tok; tok += nwarps) {
+    float4 acc[MEM_SLICES];
+#pragma unroll
+    for (int j = 0; j < MEM_SLICES; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < Q; ++q) {                           // level order 0..Q-1
+      const int64_t k = static_cast<int64_t>(idx[tok * Q + q]);
+      if (k < 0 || k >= K_total) continue;
+#pragma unroll
+      for (int j = 0; j < MEM_SLICES; ++j) {
+        const int c = lane + 32 * j;
+        if (c < H4) {
+          const float4 e = __ldg(P + k * H4 + c);
+          acc[j].x += e.x; acc[j].y += e.y; acc[j].z += e.z; acc[j].w += e.w;
+        }
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < MEM_SLICES; ++j) {
+      const int c = lane + 32 * j;
+      if (c < H4) {
+        if (bias) { const float4 b = __ldg(bias + c); acc[j].x += b.x; acc[j].y += b.y; acc[j].z += b.z; acc[j].w += b.w; }
+        sum += (acc[j].x + acc[j].y) + (acc[j].z + acc[j].w);
+      }
+    }
+    const float mean = warp_sum(sum) * inv_h;
+    float var = 0.f;
+#pragma unroll
+    for (int j = 0; j < MEM_SLICES; ++j) {
+      const int c = lane + 32 * j;
+      if (c < H4) {
+        const float dx = acc[j].x - mean, dy = acc[j].y - mean, dz = acc[j].z - mean, dw = acc[j].w - mean;
+        var += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(var) * inv_h + ln_eps);      // biased variance, as nn.LayerNorm
+#pragma unroll
+    for (int j = 0; j < MEM_SLICES; ++j) {
+      const int c = lane + 32 * j;
+      if (c < H4) {
+        float4 o = make_float4((acc[j].x - mean) * rstd, (acc[j].y - mean) * rstd, (acc[j].z - mean) * rstd, (acc[j].w - mean) * rstd);
+        if (ln_w) { const float4 g = __ldg(ln_w + c); o.x *= g.x; o.y *= g.y; o.z *= g.z; o.w *= g.w; }
+        if (ln_b) { const float4 b = __ldg(ln_b + c); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+        st_stream(out + tok * H4 + c, o);
+      }
+    }
+  }
+}
+
+int launch_indices_to_memory(const void* idx, int bytes, int64_t n_tok, int Q, const float* P, int K_total, int H,
+                             const float* bias, const float* ln_w, const float* ln_b, float ln_eps, float* out,
+                             cudaStream_t s) {
+  if (n_tok == 0) return VQB200_OK;
+  if (H % 4 != 0 || H > MEM_SLICES * 128) return VQB200_ESHAPE;
+  const int H4 = H >> 2;
+  int64_t blocks = (n_tok + 7) / 8;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  const unsigned g = static_cast<unsigned>(blocks);
+  auto Pv = reinterpret_cast<const float4*>(P);
+  auto B = reinterpret_cast<const float4*>(bias);
+  auto W = reinterpret_cast<const float4*>(ln_w);
+  auto Lb = reinterpret_cast<const float4*>(ln_b);
+  auto O = reinterpret_cast<float4*>(out);
+  if (bytes == VQB200_IDX_I16) indices_to_memory_kernel<int16_t><<<g, 256, 0, s>>>(static_cast<const int16_t*>(idx), n_tok, Q, Pv, K_total, H4, B, W, Lb, ln_eps, O);
+  else if (bytes == VQB200_IDX_I32) indices_to_memory_kernel<int32_t><<<g, 256, 0, s>>>(static_cast<const int32_t*>(idx), n_tok, Q, Pv, K_total, H4, B, W, Lb, ln_eps, O);
+  else if (bytes == VQB200_IDX_I64) indices_to_memory_kernel<int64_t><<<g, 256, 0, s>>>(static_cast<const int64_t*>(idx), n_tok, Q, Pv, K_total, H4, B, W, Lb, ln_eps, O);
+  else return VQB200_EINVAL;
+  return status_of(cudaGetLastError());
+}
+
 __global__ void minloc_unpack_kernel(const uint64_t* __restrict__ p, int64_t N, int64_t* __restrict__ out) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < N; i += stride)

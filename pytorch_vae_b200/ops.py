@@ -415,6 +415,30 @@ def indices_to_latent(idx: torch.Tensor, E: torch.Tensor, Q: int) -> torch.Tenso
 
 
 @_on_device
+def indices_to_memory(idx: torch.Tensor, P: torch.Tensor, Q: int, bias=None, ln_weight=None, ln_bias=None,
+                      ln_eps: float = 1e-5) -> torch.Tensor:
+    """Token-major ids [n_tok*Q] -> LayerNorm(sum_q P[id_q] + bias) [n_tok, H], P = E @ W_from_code^T (see
+    include/vq_b200.h: the from_code Linear over the tokens becomes a gather, models/vq_vae.py:749)."""
+    _need_cuda(idx, P)
+    _f32c(P, "projected codebook")
+    for name, t in (("bias", bias), ("ln_weight", ln_weight), ("ln_bias", ln_bias)):
+        if t is not None:
+            _f32c(t, name)
+    if idx.dtype not in _IDX_BYTES:
+        raise RuntimeError(f"indices must be int16/int32/int64, got {idx.dtype}")
+    idx = idx.contiguous().view(-1)
+    if idx.numel() % Q != 0:
+        raise ValueError(f"flattened indices length {idx.numel()} is not divisible by num_quantizers={Q}")
+    n_tok = idx.numel() // Q
+    out = torch.empty(n_tok, P.shape[1], dtype=torch.float32, device=P.device)
+    check(lib.vqb200_indices_to_memory(ptr(idx), _IDX_BYTES[idx.dtype], n_tok, Q, ptr(P), P.shape[0], P.shape[1],
+                                       ptr(bias), ptr(ln_weight), ptr(ln_bias), float(ln_eps), ptr(out), stream_ptr()),
+          "vqb200_indices_to_memory")
+    _count(1)
+    return out
+
+
+@_on_device
 def search_packed(z, E_slice, ee_half_slice, idx_offset, packed_out):
     """Codebook-sharded search: packed[n] = key(d) << 32 | (idx_offset + argmin) over this shard's codes."""
     _need_cuda(z, E_slice, packed_out)

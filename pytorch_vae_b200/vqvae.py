@@ -223,12 +223,49 @@ class VQVAE(nn.Module):
         return z
 
     def decode(self, z_for_decode: Tensor, mask: Optional[Tensor] = None) -> Tensor:
-        B = z_for_decode.size(0)
+        return self._decode_memory(self.mem_ln(self.from_code(z_for_decode)), mask)
+
+    def _decode_memory(self, memory: Tensor, mask: Optional[Tensor]) -> Tensor:
+        B = memory.size(0)
         L = mask.size(1) if mask is not None else self.max_seq_len
-        memory = self.mem_ln(self.from_code(z_for_decode))
         q = self.query_embed.weight[:L].unsqueeze(0).expand(B, L, -1) + self.pos_enc[:, :L, :]
         h = self.decoder(tgt=q, memory=memory, tgt_key_padding_mask=(~mask) if mask is not None else None)
         return torch.cat([self.head_xyz(h), self.head_ss(h)], dim=-1)
+
+    # ---- indices -> decoder memory without z_q and without a GEMM over the tokens (SURVEY.md section 8f rank 1:
+    # "from_code + mem_ln after K2"; the inference path of scripts/decode_with_vqvae.py:110-130 + models/vq_vae.py:749)
+    @torch.no_grad()
+    def projected_codebook(self) -> Tensor:
+        """P = embedding @ from_code.weight^T  [K_total, hidden]: from_code(sum_q E[i_q]) = sum_q P[i_q] + bias.
+        Rebuilt only when the codebook or the weight has changed (tensor version counters)."""
+        q = self.quantizer
+        key = (q.embedding._version, self.from_code.weight._version, q.embedding.data_ptr(), self.from_code.weight.data_ptr())
+        cached = getattr(self, "_proj_cache", None)
+        if cached is None or cached[0] != key:
+            P = (q.embedding.double() @ self.from_code.weight.double().t()).float().contiguous()   # once per version
+            object.__setattr__(self, "_proj_cache", (key, P))
+            cached = self._proj_cache
+        return cached[1]
+
+    @torch.no_grad()
+    def memory_from_indices(self, indices: Tensor) -> Tensor:
+        """Token-major global ids [B, M*Q] / [B, M, Q] -> memory [B, M, hidden] = mem_ln(from_code(z_q)) in ONE
+        gather + LayerNorm kernel (inference only: no gradient)."""
+        q = self.quantizer
+        Q = int(q.num_quantizers)
+        B = indices.size(0)
+        idx = indices.reshape(B, -1)
+        if idx.size(1) % Q != 0:
+            raise ValueError(f"index row length {idx.size(1)} is not divisible by num_quantizers={Q}")
+        mem = ops.indices_to_memory(idx, self.projected_codebook(), Q, self.from_code.bias,
+                                    self.mem_ln.weight if self.mem_ln.elementwise_affine else None,
+                                    self.mem_ln.bias if self.mem_ln.elementwise_affine else None, self.mem_ln.eps)
+        return mem.view(B, idx.size(1) // Q, -1)
+
+    @torch.no_grad()
+    def decode_indices(self, indices: Tensor, mask: Optional[Tensor] = None) -> Tensor:
+        """decode(indices_to_latent(indices)) without forming the latent."""
+        return self._decode_memory(self.memory_from_indices(indices), mask)
 
     # ---------------------------------------------------------------- forward: the quantizer call site
     def forward(self, x: Tensor, mask: Optional[Tensor] = None, **kwargs) -> List[Tensor]:
