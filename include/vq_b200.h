@@ -33,7 +33,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 15
+#define VQB200_ABI_VERSION 16
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -274,6 +274,28 @@ VQB200_API int vqb200_relayout_indices(const int64_t* idx_level_major, int Q, in
  * (scripts/decode_with_vqvae.py:110-130; models/vq_vae.py:1404-1418). */
 VQB200_API int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok, int Q, const float* E,
                              int K_total, int D, float* zq_out, void* stream);
+
+/* The training forward of a residual codebook in two halves, for data-parallel training with the EMA segment sums
+ * all-reduced over ranks: the reference runs one EMA update per level and each touches all
+ * K_total codes, but for the codes of ANOTHER level it is a decay-only step -- so level l is searched against codes that
+ * depend on nothing computed in this step, and the whole forward can run before ONE exchange of the segment sums:
+ *   begin : the decay-only steps of the earlier levels (level l: l of them), then every level in one persistent
+ *           kernel (search, exact re-rank, residual, outputs as vqb200_rvq_forward) which also reduces the residual
+ *           rows into seg_sum [K_total, D] / seg_cnt [K_total] (zeroed by the call);
+ *   (the caller all-reduces seg_sum / seg_cnt over its ranks)
+ *   finish: every level's own update from its segment sums and the decay-only steps of the later levels; codebook
+ *           cache refreshed.  begin + finish with nothing in between = vqb200_rvq_train_forward, bit for bit.
+ * Shapes: vqb200_rvq_train_fused_supported (D in {128, 256, 384, 512}, K_per >= 128, 2 <= L <= 8, N <= 65536). */
+VQB200_API int vqb200_rvq_train_fused_supported(int64_t N, int K_per, int D, int L, int mode);
+VQB200_API size_t vqb200_rvq_train_begin_workspace_bytes(int64_t N, int K_per, int D, int L, int mode);
+VQB200_API int vqb200_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                           float* level_meta, int K_per, int L, int mode, float decay, float one_minus_decay, float eps,
+                           float* ema_cluster_size, float* ema_embedding, int64_t* idx_out, float* zq_out,
+                           float* zq_st_out, double* sqerr_sum, int32_t* hist, float* seg_sum, float* seg_cnt,
+                           void* workspace, size_t workspace_bytes, void* stream);
+VQB200_API int vqb200_rvq_train_finish(const float* seg_sum, const float* seg_cnt, float decay, float one_minus_decay,
+                            float eps, int K_per, int L, int D, float* ema_cluster_size, float* ema_embedding, float* E,
+                            uint16_t* E_lp_planes, float* ee_half, float* level_meta, void* stream);
 
 /* Token-major ids [n_tok * Q] -> decoder memory [n_tok, H] = LayerNorm(from_code(z_q)) (models/vq_vae.py:749,
  * "from_code + mem_ln after K2").  from_code is linear, so with the projected table

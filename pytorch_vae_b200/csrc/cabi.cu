@@ -254,6 +254,49 @@ int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_
   return launch_st_loss(z, zq_out, N * D, zq_st_out, sqerr_sum, s);
 }
 
+// ---- the same forward in two halves around the point where ranks exchange their segment sums (all-reduced EMA):
+// ONE exchange per step instead of one per level -- a level is searched against codes that have only seen decay-only
+// updates from the earlier levels of the step (csrc/vq_rvq_fused.cu), so no search waits for another rank's rows.
+int vqb200_rvq_train_fused_supported(int64_t N, int K_per, int D, int L, int mode) {
+  (void)mode;
+  return rvq_fused_train_supported(N, K_per, D, L) ? 1 : 0;
+}
+
+size_t vqb200_rvq_train_begin_workspace_bytes(int64_t N, int K_per, int D, int L, int mode) {
+  (void)K_per; (void)L; (void)mode;
+  return rvq_align(rvq_fused_workspace_bytes(N, D));
+}
+
+int vqb200_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                           float* level_meta, int K_per, int L, int mode, float decay, float one_minus_decay, float eps,
+                           float* ema_cluster_size, float* ema_embedding, int64_t* idx_out, float* zq_out,
+                           float* zq_st_out, double* sqerr_sum, int32_t* hist, float* seg_sum, float* seg_cnt,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  VQ_REQUIRE(N > 0 && K_per > 0 && L >= 1 && L <= VQB200_MAX_LEVELS, VQB200_EINVAL);
+  VQ_REQUIRE(z && idx_out && E && E_lp_planes && ee_half && level_meta && ema_cluster_size && ema_embedding && zq_out &&
+                 seg_sum && seg_cnt && workspace, VQB200_EINVAL);
+  VQ_REQUIRE(mode == VQB200_MODE_FP32_EXACT || mode == VQB200_MODE_BF16_INPUT, VQB200_EINVAL);
+  VQ_REQUIRE(rvq_fused_train_supported(N, K_per, D, L), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(E_lp_planes) && aligned16(zq_out) && aligned16(zq_st_out) &&
+                 aligned16(ema_embedding) && aligned16(seg_sum) && (reinterpret_cast<uintptr_t>(workspace) & 255u) == 0,
+             VQB200_EALIGN);
+  return launch_rvq_train_begin(z, N, D, E, E_lp_planes, ee_half, level_meta, K_per, L, mode, decay, one_minus_decay, eps,
+                                ema_cluster_size, ema_embedding, idx_out, zq_out, zq_st_out, sqerr_sum, hist, seg_sum, seg_cnt,
+                                workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int vqb200_rvq_train_finish(const float* seg_sum, const float* seg_cnt, float decay, float one_minus_decay, float eps,
+                            int K_per, int L, int D, float* ema_cluster_size, float* ema_embedding, float* E,
+                            uint16_t* E_lp_planes, float* ee_half, float* level_meta, void* stream) {
+  VQ_REQUIRE(K_per > 0 && L >= 1 && L <= VQB200_MAX_LEVELS, VQB200_EINVAL);
+  VQ_REQUIRE(seg_sum && seg_cnt && ema_cluster_size && ema_embedding && E && E_lp_planes && ee_half && level_meta,
+             VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(seg_sum) && aligned16(ema_embedding) && aligned16(E) && aligned16(E_lp_planes), VQB200_EALIGN);
+  return launch_rvq_train_finish(seg_sum, seg_cnt, decay, one_minus_decay, eps, K_per, L, D, ema_cluster_size, ema_embedding,
+                                 E, E_lp_planes, ee_half, level_meta, static_cast<cudaStream_t>(stream));
+}
+
 // One training level up to the point where ranks exchange their segment sums: search -> gather -> scatter-add.
 int vqb200_rvq_train_level(const float* residual, int64_t N, int D, const float* E, const uint16_t* E_lp_planes,
                            const float* ee_half, const float* level_meta, int K_per, int L, int level, int mode,

@@ -159,6 +159,14 @@ int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uin
 // training mode: refresh phase 1 -> the same kernel reducing the EMA segment sums -> refresh phase 2 (three launches)
 bool rvq_fused_train_supported(int64_t N, int K_per, int D, int L);
 size_t rvq_fused_train_workspace_bytes(int64_t N, int K_per, int D, int L);
+int launch_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                           float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
+                           float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
+                           double* sqerr_sum, int32_t* hist, float* seg_sum, float* seg_cnt, void* workspace,
+                           size_t workspace_bytes, cudaStream_t s);
+int launch_rvq_train_finish(const float* seg_sum, const float* seg_cnt, float decay, float omd, float eps, int K_per, int L,
+                            int D, float* ema_cs, float* ema_emb, float* E, uint16_t* E_lp_planes, float* ee_half,
+                            float* level_meta, cudaStream_t s);
 int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
                            float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
                            float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,

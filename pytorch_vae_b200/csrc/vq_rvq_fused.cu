@@ -926,31 +926,54 @@ int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uin
   return st;
 }
 
-// Training-mode forward: refresh phase 1 -> the persistent kernel with segment sums -> refresh phase 2 (see the kernel's
-// header comment for why this is the reference's level-by-level update sequence).
+// Training-mode forward in two halves around the point where ranks may exchange their segment sums:
+//   begin : refresh phase 1 -> the persistent kernel, reducing the residual rows into seg_sum / seg_cnt (zeroed here)
+//   finish: refresh phase 2 from the (possibly all-reduced) segment sums
+// (see the kernel's header comment for why this is the reference's level-by-level update sequence).
+int launch_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                           float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
+                           float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
+                           double* sqerr_sum, int32_t* hist, float* seg_sum, float* seg_cnt, void* workspace,
+                           size_t workspace_bytes, cudaStream_t s) {
+  if (!rvq_fused_train_supported(N, K_per, D, L)) return VQB200_ESHAPE;
+  if (workspace_bytes < rvq_fused_workspace_bytes(N, D)) return VQB200_EWORKSPACE;
+  const bool bf = mode == VQB200_MODE_BF16_INPUT;
+  const int K_total = K_per * L;
+  cudaError_t e = cudaMemsetAsync(seg_sum, 0, static_cast<size_t>(K_total) * D * 4, s);
+  if (e == cudaSuccess) e = cudaMemsetAsync(seg_cnt, 0, static_cast<size_t>(K_total) * 4, s);
+  if (e != cudaSuccess) return status_of(e);
+  int st = launch_codebook_refresh(1, seg_sum, seg_cnt, decay, omd, eps, K_total, D, K_per, ema_cs, ema_emb, E, E_lp_planes,
+                                   ee_half, level_meta, s, /*chain_phase=*/1);
+  if (st != VQB200_OK) return st;
+  const uint16_t* plane = E_lp_planes + (bf ? 0 : static_cast<size_t>(K_total) * D);
+  return launch_rvq_fused(z, N, D, E, plane, bf ? ee_half + K_total : ee_half, level_meta, K_per, L, mode, idx_out, zq_out,
+                          zq_st_out, sqerr_sum, hist, workspace, workspace_bytes, s, seg_sum, seg_cnt);
+}
+
+int launch_rvq_train_finish(const float* seg_sum, const float* seg_cnt, float decay, float omd, float eps, int K_per, int L,
+                            int D, float* ema_cs, float* ema_emb, float* E, uint16_t* E_lp_planes, float* ee_half,
+                            float* level_meta, cudaStream_t s) {
+  return launch_codebook_refresh(1, seg_sum, seg_cnt, decay, omd, eps, K_per * L, D, K_per, ema_cs, ema_emb, E, E_lp_planes,
+                                 ee_half, level_meta, s, /*chain_phase=*/2);
+}
+
 int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
                            float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
                            float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
                            double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes, cudaStream_t s) {
   if (!rvq_fused_train_supported(N, K_per, D, L)) return VQB200_ESHAPE;
   if (workspace_bytes < rvq_fused_train_workspace_bytes(N, K_per, D, L)) return VQB200_EWORKSPACE;
-  const bool bf = mode == VQB200_MODE_BF16_INPUT;
   const int K_total = K_per * L;
   uint8_t* w = static_cast<uint8_t*>(workspace);
   float* seg_sum = reinterpret_cast<float*>(w);
   float* seg_cnt = seg_sum + static_cast<size_t>(K_total) * D;
   const size_t seg_bytes = rq_train_seg_bytes(K_total, D);
-  cudaError_t e = cudaMemsetAsync(w, 0, seg_bytes, s);
-  if (e != cudaSuccess) return status_of(e);
-  int st = launch_codebook_refresh(1, seg_sum, seg_cnt, decay, omd, eps, K_total, D, K_per, ema_cs, ema_emb, E, E_lp_planes,
-                                   ee_half, level_meta, s, /*chain_phase=*/1);
+  const int st = launch_rvq_train_begin(z, N, D, E, E_lp_planes, ee_half, level_meta, K_per, L, mode, decay, omd, eps, ema_cs,
+                                        ema_emb, idx_out, zq_out, zq_st_out, sqerr_sum, hist, seg_sum, seg_cnt, w + seg_bytes,
+                                        workspace_bytes - seg_bytes, s);
   if (st != VQB200_OK) return st;
-  const uint16_t* plane = E_lp_planes + (bf ? 0 : static_cast<size_t>(K_total) * D);
-  st = launch_rvq_fused(z, N, D, E, plane, bf ? ee_half + K_total : ee_half, level_meta, K_per, L, mode, idx_out, zq_out,
-                        zq_st_out, sqerr_sum, hist, w + seg_bytes, workspace_bytes - seg_bytes, s, seg_sum, seg_cnt);
-  if (st != VQB200_OK) return st;
-  return launch_codebook_refresh(1, seg_sum, seg_cnt, decay, omd, eps, K_total, D, K_per, ema_cs, ema_emb, E, E_lp_planes,
-                                 ee_half, level_meta, s, /*chain_phase=*/2);
+  return launch_rvq_train_finish(seg_sum, seg_cnt, decay, omd, eps, K_per, L, D, ema_cs, ema_emb, E, E_lp_planes, ee_half,
+                                 level_meta, s);
 }
 
 }  // namespace vqb

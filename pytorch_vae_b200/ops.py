@@ -141,6 +141,39 @@ def rvq_train_forward(z, E, cache: CodebookCache, mode, decay, eps, ema_cluster_
     _count(lib.vqb200_rvq_train_launches(N, K, D, L, mode))
 
 
+def rvq_train_fused_supported(N, K_per, D, L, mode) -> bool:
+    return bool(lib.vqb200_rvq_train_fused_supported(N, K_per, D, L, mode))
+
+
+@_on_device
+def rvq_train_begin(z, E, cache: CodebookCache, mode, decay, eps, ema_cluster_size, ema_embedding, idx_out, zq_out,
+                    seg_sum, seg_cnt, zq_st_out=None, sqerr_sum=None, hist=None):
+    """First half of the training forward (see include/vq_b200.h): every level searched, outputs written, this rank's
+    EMA segment sums in ``seg_sum`` / ``seg_cnt``; ``rvq_train_finish`` applies the updates after the exchange."""
+    _need_cuda(z, E, idx_out, zq_out, seg_sum, seg_cnt)
+    _f32c(z, "z")
+    N, D = z.shape
+    K, L = cache.K_per, cache.levels
+    ws_bytes = lib.vqb200_rvq_train_begin_workspace_bytes(N, K, D, L, mode)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+    check(lib.vqb200_rvq_train_begin(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), ptr(cache.ee_half), ptr(cache.level_meta),
+                                     K, L, mode, float(decay), float(1 - decay), float(eps), ptr(ema_cluster_size),
+                                     ptr(ema_embedding), ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum),
+                                     ptr(hist), ptr(seg_sum), ptr(seg_cnt), ptr(ws), ws_bytes, stream_ptr()),
+          "vqb200_rvq_train_begin")
+    _count(4)
+
+
+@_on_device
+def rvq_train_finish(seg_sum, seg_cnt, E, cache: CodebookCache, decay, eps, ema_cluster_size, ema_embedding):
+    D = E.shape[1]
+    check(lib.vqb200_rvq_train_finish(ptr(seg_sum), ptr(seg_cnt), float(decay), float(1 - decay), float(eps),
+                                      cache.K_per, cache.levels, D, ptr(ema_cluster_size), ptr(ema_embedding), ptr(E),
+                                      ptr(cache.E_bf16), ptr(cache.ee_half), ptr(cache.level_meta), stream_ptr()),
+          "vqb200_rvq_train_finish")
+    _count(1)
+
+
 @_on_device
 def rvq_train_level(residual, E, cache: CodebookCache, level, mode, idx_out, zq_out, residual_out, hist, seg_sum,
                     seg_cnt):

@@ -401,6 +401,15 @@ class VectorQuantizerEMA(nn.Module):
             # point (search, gather, scatter-add), the all-reduce, and the EMA finalize
             seg = torch.empty(self.K * D + self.K, dtype=torch.float32, device=flat.device)
             seg_sum, seg_cnt = seg[: self.K * D], seg[self.K * D:]
+            if lstride == n and ops.rvq_train_fused_supported(n, self.K_per, D, L, mode):
+                # ONE exchange per step: no level's search depends on this step's segment sums (include/vq_b200.h)
+                ops.rvq_train_begin(flat, E, cache, mode, self.decay, self.eps, self.ema_cluster_size, self.ema_embedding,
+                                    idx_levels[0], z_q, seg_sum, seg_cnt, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist)
+                torch.distributed.all_reduce(seg)
+                ops.rvq_train_finish(seg_sum, seg_cnt, E, cache, self.decay, self.eps, self.ema_cluster_size,
+                                     self.ema_embedding)
+                cache.key = (self.embedding.data_ptr(), self.embedding._version)
+                return
             for level in range(L):
                 nxt = spare[level % 2] if level < L - 1 else None
                 ops.rvq_train_level(residual, E, cache, level, mode, idx_levels[level], z_q, nxt, hist, seg_sum, seg_cnt)

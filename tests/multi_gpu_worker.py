@@ -64,6 +64,42 @@ def row_sharded_stats(dev, rank, world):
         print("row_sharded_stats ok", flush=True)
 
 
+def allreduced_ema_training(dev, rank, world):
+    """Data-parallel training with the EMA segment sums all-reduced (ema_sync="allreduce", ONE exchange per step through
+    vqb200_rvq_train_begin / _finish): every rank ends each step with the codebook a single GPU gets from the
+    concatenated batch; indices of a rank's rows equal that run's slice (step 0 exactly; later steps except near-ties)."""
+    import pytorch_vae_b200 as vq
+    from pytorch_vae_b200 import sharding as S
+    K_per, D, L, B, M = 1024, 512, 4, 128, 64
+    gen = torch.Generator(device=dev).manual_seed(21)
+    E = torch.randn(K_per * L, D, device=dev, generator=gen) / np.sqrt(D)
+    for l in range(1, L):
+        E[l * K_per:(l + 1) * K_per] *= 0.6 ** l
+    zs = [torch.randn(B, M, D, device=dev, generator=gen) for _ in range(3)]
+    assert vq.ops.rvq_train_fused_supported(B * M // world, K_per, D, L, 0)
+    q1 = vq.VectorQuantizerEMA(K_per, D, num_quantizers=L, print_init=False, decay=0.98).to(dev).train()
+    q1.embedding.copy_(E)
+    q2 = vq.VectorQuantizerEMA(K_per, D, num_quantizers=L, print_init=False, decay=0.98).to(dev).train()
+    q2.embedding.copy_(E)
+    q2.ema_sync = "allreduce"
+    a, b = S.shard_rows(B, world, rank)
+    n1, n2 = B * M, (b - a) * M
+    for step, z in enumerate(zs):
+        idx1 = q1(z, do_ema_update=True)[2].view(L, n1)
+        idx2 = q2(z[a:b].contiguous(), do_ema_update=True)[2].view(L, n2)
+        same = (idx2 == idx1[:, a * M:b * M]).all(0).float().mean().item()
+        assert same == 1.0 if step == 0 else same > 0.99, (step, same)
+        scale = float(q1.ema_embedding.abs().max())
+        assert torch.allclose(q2.ema_cluster_size, q1.ema_cluster_size, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(q2.ema_embedding, q1.ema_embedding, rtol=1e-4, atol=2e-6 * scale + 1e-7)
+        assert torch.allclose(q2.embedding, q1.embedding, rtol=1e-4, atol=2e-6 * float(q1.embedding.abs().max()) + 1e-7)
+    gathered = [torch.empty_like(q2.embedding) for _ in range(world)]
+    dist.all_gather(gathered, q2.embedding)
+    assert all(torch.equal(g, q2.embedding) for g in gathered)    # every rank holds the same codebook, bit for bit
+    if rank == 0:
+        print("allreduced_ema_training ok", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -76,5 +112,7 @@ if __name__ == "__main__":
             sharded_search(dev, rank, world)
         if what in ("row_sharded_stats", "all"):
             row_sharded_stats(dev, rank, world)
+        if what in ("allreduced_ema_training", "all"):
+            allreduced_ema_training(dev, rank, world)
     finally:
         dist.destroy_process_group()

@@ -464,15 +464,18 @@ def test_packed_statistics_equal_direct(vq, dev):
     np.testing.assert_allclose(npy(a), npy(b), rtol=1e-6)
 
 
-def test_allreduced_ema_training_path_equals_local_on_one_rank(vq, dev, monkeypatch):
-    """The multi-GPU training path (per level: one library call up to the exchange point, all-reduce, EMA finalize)
-    with the all-reduce stubbed to the identity must reproduce the single-call local path."""
+@pytest.mark.parametrize("K_per,D,one_exchange", [(256, 128, True), (96, 64, False)])
+def test_allreduced_ema_training_path_equals_local_on_one_rank(vq, dev, monkeypatch, K_per, D, one_exchange):
+    """The multi-GPU training paths -- ONE exchange per step around the persistent kernel (vqb200_rvq_train_begin /
+    _finish) where it takes the shape, else per level: one library call up to the exchange point, all-reduce, EMA
+    finalize -- with the all-reduce stubbed to the identity must reproduce the single-call local path."""
     import torch.distributed as dist
     from synth import large_case_inputs
-    E, z = large_case_inputs(91, 256, 128, 3, 16, 64)
+    E, z = large_case_inputs(91, K_per, D, 3, 16, 64)
+    assert vq.ops.rvq_train_fused_supported(16 * 64, K_per, D, 3, 0) == one_exchange
 
     def run(allreduce):
-        q = vq.VectorQuantizerEMA(256, 128, num_quantizers=3, print_init=False, decay=0.9).to(dev).train()
+        q = vq.VectorQuantizerEMA(K_per, D, num_quantizers=3, print_init=False, decay=0.9).to(dev).train()
         q.embedding.copy_(T(E, dev))
         if allreduce:
             q.ema_sync = "allreduce"

@@ -339,3 +339,20 @@ def test_row_sharded_statistics_two_gpus_nccl():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "row_sharded_stats ok" in r.stdout
+
+
+def test_allreduced_ema_training_two_gpus_nccl():
+    """Training at the stage-2 shape on two GPUs with the EMA segment sums all-reduced ONCE per step (the persistent
+    kernel between vqb200_rvq_train_begin and _finish): both ranks end every step with the codebook one GPU gets from
+    the whole batch.  Skipped on one GPU."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29633",
+                        os.path.join(root, "tests", "multi_gpu_worker.py"), "allreduced_ema_training"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "allreduced_ema_training ok" in r.stdout
