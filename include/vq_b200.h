@@ -210,6 +210,20 @@ VQB200_API int vqb200_stats_pack(const int32_t* hist, int K_total, const double*
 VQB200_API int vqb200_stats_finalize_packed(const double* packed, int K_total, int levels, int D, float* ep_usage,
                                  float* ep_cnt, float* stats_out, void* stream);
 
+/* The same exchange WITHOUT a collective library call on the step path: pack -> exchange over NVLink / NVSwitch peer
+ * memory -> reduce -> finalize in ONE kernel (north star: "only the scalar loss and the code-usage histogram are
+ * all-reduced").  Every rank passes peer_buffers, a DEVICE array of `world` pointers to the ranks' symmetric buffers
+ * (the same allocation mapped into every process, e.g. torch.distributed._symmetric_memory; each
+ * vqb200_stats_exchange_buffer_bytes(K_total, world) long and ZEROED once before the first call, with a barrier after
+ * the zeroing).  A rank pushes its pack into its slot of every rank's buffer, raises a flag there, waits for all
+ * flags of the epoch and sums the slots in rank order, so every rank obtains bit-identical statistics; the epoch counter
+ * lives in the buffer (graph-replayable).  All ranks must call in the same order.  spin_limit: polls of a flag before
+ * the kernel traps (0 = wait for ever). */
+VQB200_API size_t vqb200_stats_exchange_buffer_bytes(int K_total, int world);
+VQB200_API int vqb200_stats_exchange(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, int levels,
+                          int D, const uint64_t* peer_buffers, int rank, int world, uint64_t spin_limit,
+                          float* ep_usage, float* ep_cnt, float* stats_out, void* stream);
+
 /* EMA codebook update, part 1: segment sums.  Replaces the dense one-hot GEMM of
  * models/vq_vae.py:81-83.  seg_sum [K_total, D] and seg_cnt [K_total] are zeroed by the caller. */
 VQB200_API int vqb200_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D,

@@ -483,6 +483,19 @@ int vqb200_stats_finalize_packed(const double* packed, int K_total, int levels, 
                                       static_cast<cudaStream_t>(stream));
 }
 
+size_t vqb200_stats_exchange_buffer_bytes(int K_total, int world) {
+  return (K_total > 0 && world > 0) ? stats_exchange_buffer_bytes(K_total, world) : 0;
+}
+
+int vqb200_stats_exchange(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, int levels, int D,
+                          const uint64_t* peer_buffers, int rank, int world, uint64_t spin_limit, float* ep_usage,
+                          float* ep_cnt, float* stats_out, void* stream) {
+  VQ_REQUIRE(hist && peer_buffers && stats_out && K_total > 0 && levels > 0 && D > 0, VQB200_EINVAL);
+  return launch_stats_exchange(hist, K_total, sqerr_sum, n_elems, levels, D, peer_buffers, rank, world,
+                               static_cast<unsigned long long>(spin_limit), ep_usage, ep_cnt, stats_out,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_scatter_add(const float* z, const int64_t* idx, const uint8_t* row_mask, int64_t N, int D, int K_total,
                        float* seg_sum, float* seg_cnt, void* stream) {
   VQ_REQUIRE(N >= 0 && K_total > 0 && seg_sum && seg_cnt, VQB200_EINVAL);

@@ -189,6 +189,10 @@ int launch_gather(const float* z, const float* E, const int64_t* idx, int64_t N,
 int launch_st_loss(const float* z, const float* zq, int64_t n_elems, float* st, double* sqerr_sum, cudaStream_t s);
 int launch_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
                           double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out, cudaStream_t s);
+size_t stats_exchange_buffer_bytes(int K_total, int world);
+int launch_stats_exchange(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, int levels, int D,
+                          const uint64_t* peer_bufs, int rank, int world, unsigned long long spin_limit, float* ep_usage,
+                          float* ep_cnt, float* stats_out, cudaStream_t s);
 int launch_stats_pack(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, double* out,
                       cudaStream_t s);
 int launch_stats_finalize_packed(const double* packed, int K_total, int levels, int D, float* ep_usage, float* ep_cnt,

@@ -494,6 +494,127 @@ stats_finalize_kernel(const int32_t* __restrict__ hist_i, const double* __restri
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Global statistics over the ranks of one NVLink / NVSwitch domain in ONE kernel (no NCCL call on the step path):
+// pack -> exchange over peer memory -> reduce -> finalize.  Every rank owns a symmetric buffer (the same layout on every
+// GPU, mapped into every process: torch.distributed._symmetric_memory):
+//     [0, 256)            flags: uint32 flag[r] = last epoch rank r's payload arrived for
+//     [256, 264)          this rank's epoch counter (device-resident so that a CUDA graph can replay the kernel)
+//     [512, ...)          two payload areas (epoch parity) of world x (K_total + 2) doubles, then the reduced pack
+// Push model: a rank writes its payload [sum sq err | element count | histogram] into slot[rank] of EVERY rank's buffer
+// (NVLink stores), fences at system scope, raises flag[rank] on every rank, waits until all of its own flags show the
+// epoch, and sums the slots in rank order -- so all ranks obtain bit-identical statistics.  Two areas are enough: a
+// rank can only finish epoch e after every rank has pushed epoch e, i.e. after every rank finished reading e - 1.
+// --------------------------------------------------------------------------------------------
+constexpr int XCH_FLAG_BYTES = 256, XCH_HDR_BYTES = 512, XCH_MAX_WORLD = 64;
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(1024)
+stats_exchange_kernel(const int32_t* __restrict__ hist_i, int K_total, const double* __restrict__ sqerr_sum,
+                      double n_elems, double positions_per_elem, const uint64_t* __restrict__ peer_bufs, int rank,
+                      int world, unsigned long long spin_limit, float* ep_usage, float* ep_cnt,
+                      float* __restrict__ stats_out) {
+  __shared__ uint32_t s_epoch;
+  __shared__ double red[32], red2[32];
+  __shared__ double s_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint8_t* mine = reinterpret_cast<uint8_t*>(peer_bufs[rank]);
+  if (tid == 0) {
+    uint32_t* ctr = reinterpret_cast<uint32_t*>(mine + XCH_FLAG_BYTES);
+    s_epoch = ++(*ctr);                                     // every rank calls in the same order: the counters agree
+  }
+  __syncthreads();
+  const uint32_t epoch = s_epoch;
+  const int slot = K_total + 2;
+  const size_t area_off = XCH_HDR_BYTES + static_cast<size_t>(epoch & 1u) * world * slot * sizeof(double);
+  // 1. push this rank's payload into slot[rank] of every rank's buffer
+  for (int p = 0; p < world; ++p) {
+    double* dst = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(peer_bufs[p]) + area_off) + static_cast<size_t>(rank) * slot;
+    for (int i = tid; i < slot; i += blockDim.x)
+      dst[i] = i == 0 ? (sqerr_sum ? *sqerr_sum : 0.0) : (i == 1 ? n_elems : static_cast<double>(hist_i[i - 2]));
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2. raise this rank's flag everywhere; 3. wait for every rank's payload
+  if (tid < world) st_release_sys(reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(peer_bufs[tid])) + rank, epoch);
+  if (tid < world) {
+    const uint32_t* f = reinterpret_cast<const uint32_t*>(mine) + tid;
+    unsigned long long spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(f) - epoch) < 0)
+      if (spin_limit && ++spins > spin_limit) __trap();     // a rank that never arrives must fault, not hang the GPU
+  }
+  __syncthreads();
+  // 4. reduce the slots in rank order (bit-identical on every rank)
+  const double* src = reinterpret_cast<const double*>(mine + area_off);
+  double* pack = reinterpret_cast<double*>(mine + XCH_HDR_BYTES + 2 * static_cast<size_t>(world) * slot * sizeof(double));
+  for (int i = tid; i < slot; i += blockDim.x) {
+    double s = 0.0;
+    for (int p = 0; p < world; ++p) s += __ldcv(src + static_cast<size_t>(p) * slot + i);
+    pack[i] = s;
+  }
+  __syncthreads();
+  // 5. finalize (the arithmetic of stats_finalize_kernel<true>)
+  double t = 0.0;
+  for (int k = tid; k < K_total; k += blockDim.x) t += static_cast<double>(__double2ll_rn(pack[2 + k]));
+  t = warp_sum(t);
+  if (lane == 0) red[warp] = t;
+  __syncthreads();
+  if (warp == 0) {
+    double v = (lane < (blockDim.x >> 5)) ? red[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) s_total = v < 1.0 ? 1.0 : v;
+  }
+  __syncthreads();
+  const double total = s_total;
+  double h = 0.0, dead = 0.0;
+  for (int k = tid; k < K_total; k += blockDim.x) {
+    const long long c = __double2ll_rn(pack[2 + k]);
+    if (c > 0) { const double pr = static_cast<double>(c) / total; h += pr * log(pr); }
+    else dead += 1.0;
+    if (ep_usage) ep_usage[k] += static_cast<float>(c);
+  }
+  __syncthreads();
+  h = warp_sum(h);
+  dead = warp_sum(dead);
+  if (lane == 0) { red[warp] = h; red2[warp] = dead; }
+  __syncthreads();
+  if (warp == 0) {
+    double a = (lane < (blockDim.x >> 5)) ? red[lane] : 0.0;
+    double b = (lane < (blockDim.x >> 5)) ? red2[lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      const bool any = b < static_cast<double>(K_total);
+      stats_out[0] = any ? static_cast<float>(exp(-a)) : 0.f;
+      stats_out[1] = static_cast<float>(b / static_cast<double>(K_total));
+      stats_out[2] = static_cast<float>(pack[0] / (pack[1] < 1.0 ? 1.0 : pack[1]));
+      if (ep_cnt) ep_cnt[0] += static_cast<float>(rint(pack[1] * positions_per_elem));
+    }
+  }
+}
+
+size_t stats_exchange_buffer_bytes(int K_total, int world) {
+  return XCH_HDR_BYTES + (2 * static_cast<size_t>(world) + 1) * (K_total + 2) * sizeof(double);
+}
+
+int launch_stats_exchange(const int32_t* hist, int K_total, const double* sqerr_sum, double n_elems, int levels, int D,
+                          const uint64_t* peer_bufs, int rank, int world, unsigned long long spin_limit, float* ep_usage,
+                          float* ep_cnt, float* stats_out, cudaStream_t s) {
+  if (world < 1 || world > XCH_MAX_WORLD || rank < 0 || rank >= world) return VQB200_EINVAL;
+  stats_exchange_kernel<<<1, 1024, 0, s>>>(hist, K_total, sqerr_sum, n_elems,
+                                           static_cast<double>(levels) / static_cast<double>(D), peer_bufs, rank, world,
+                                           spin_limit, ep_usage, ep_cnt, stats_out);
+  return status_of(cudaGetLastError());
+}
+
 int launch_stats_finalize(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
                           double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out, cudaStream_t s) {
   stats_finalize_kernel<false><<<1, 1024, 0, s>>>(hist, nullptr, K_total, count_add, sqerr_sum, inv_elems, ep_usage,

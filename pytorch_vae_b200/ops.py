@@ -321,6 +321,17 @@ def stats_finalize_packed(packed, K_total, levels, D, ep_usage, ep_cnt, stats_ou
 
 
 @_on_device
+def stats_exchange(hist, sqerr_sum, n_elems, K_total, levels, D, peer_ptrs_dev: int, rank: int, world: int, ep_usage,
+                   ep_cnt, stats_out, spin_limit: int = 1 << 27):
+    """pack -> exchange over peer memory -> reduce -> finalize in one kernel (include/vq_b200.h).  ``peer_ptrs_dev``
+    is the device address of the array of the ranks' symmetric-buffer pointers."""
+    check(lib.vqb200_stats_exchange(ptr(hist), int(K_total), ptr(sqerr_sum), float(n_elems), int(levels), int(D),
+                                    int(peer_ptrs_dev), int(rank), int(world), int(spin_limit), ptr(ep_usage),
+                                    ptr(ep_cnt), ptr(stats_out), stream_ptr()), "vqb200_stats_exchange")
+    _count(1)
+
+
+@_on_device
 def scatter_add(z, idx, row_mask, seg_sum, seg_cnt):
     _need_cuda(z, idx, seg_sum)
     _f32c(z, "z")

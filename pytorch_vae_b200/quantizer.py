@@ -112,6 +112,9 @@ class VectorQuantizerEMA(nn.Module):
         # updates from its own shard), "allreduce" = segment sums summed over ranks before the EMA.
         self.ema_sync = "local"
         self.stats_sync = False
+        # how the statistics of stats_sync travel: "peer" = one kernel over NVLink peer memory (symmetric buffers; falls
+        # back to NCCL when they cannot be set up), "nccl" = pack kernel -> all-reduce -> finalize kernel
+        self.stats_exchange = os.environ.get("VQB200_STATS_EXCHANGE", "peer")
 
         # same nine buffers, same order, same init law as models/vq_vae.py:50-62
         self.register_buffer("embedding", torch.randn(self.K, self.D) * (1.0 / math.sqrt(self.D)))
@@ -562,6 +565,11 @@ class VectorQuantizerEMA(nn.Module):
             # global statistics: ONE small all-reduce instead of the reference's per-rank
             # perplexities averaged by sync_dist.  pack kernel -> NCCL -> finalize on the reduced pack: three
             # launches on the step path (the 4 KB reduction sits inside a 0.4 ms step at the c2 shape)
+            ex = sharding.PeerStatsExchange.get(hist.device, self.K) if self.stats_exchange == "peer" else None
+            if ex is not None:                                  # ONE kernel over NVLink peer memory, no NCCL call
+                ops.stats_exchange(hist, sqerr, n_elems, self.K, self.num_quantizers, self.D, ex.peer_ptrs_dev, ex.rank,
+                                   ex.world, self._ep_usage, self._ep_cnt, stats3)
+                return
             pack = torch.empty(self.K + 2, dtype=torch.float64, device=hist.device)
             ops.stats_pack(hist, sqerr, n_elems, pack)
             torch.distributed.all_reduce(pack)

@@ -35,6 +35,42 @@ def dist_ready() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+class PeerStatsExchange:
+    """Symmetric buffers for ``ops.stats_exchange`` (one NVLink / NVSwitch domain): the statistics all-reduce of the
+    forward as ONE kernel over peer memory instead of pack kernel -> NCCL -> finalize kernel.  Built lazily, once per
+    (device, K_total); ``None`` from ``get`` when symmetric memory cannot be set up (other backend, no peer access),
+    in which case the caller keeps the NCCL path."""
+
+    _cache = {}
+
+    def __init__(self, device, K_total: int):
+        import torch.distributed._symmetric_memory as symm
+        from ._cabi import lib
+        world = dist.get_world_size()
+        nbytes = int(lib.vqb200_stats_exchange_buffer_bytes(int(K_total), world))
+        self.buf = symm.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        self.hdl = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.buf.zero_()
+        torch.cuda.current_stream(device).synchronize()
+        dist.barrier()                                          # every rank's flags and epoch counter are zero
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        self.peer_ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+
+    @classmethod
+    def get(cls, device, K_total: int):
+        key = (str(device), int(K_total))
+        if key not in cls._cache:
+            try:
+                if dist.get_backend() != "nccl" or torch.device(device).type != "cuda":
+                    raise RuntimeError("peer memory needs CUDA devices")
+                cls._cache[key] = cls(device, K_total)
+            except Exception as e:                              # noqa: BLE001 -- any set-up failure: keep NCCL
+                import warnings
+                warnings.warn(f"peer-memory statistics exchange unavailable ({type(e).__name__}: {e}); using NCCL")
+                cls._cache[key] = None
+        return cls._cache[key]
+
+
 def allreduce_stats(sqerr_sum: torch.Tensor, n_elems: int, hist: torch.Tensor, group=None):
     """ONE all-reduce of ``[sum sq err | element count | histogram]`` (float64: counts stay exact to 2^53).
 

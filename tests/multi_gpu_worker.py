@@ -50,16 +50,27 @@ def row_sharded_stats(dev, rank, world):
     with torch.no_grad():
         st, zq, idx, stats = q1(z, do_ema_update=False)
     a, b = S.shard_rows(N // 64, world, rank)
-    q2 = vq.VectorQuantizerEMA(K, D, print_init=False).to(dev).eval()
-    q2.embedding.copy_(E)
-    q2.stats_sync = True
-    with torch.no_grad():
-        st2, zq2, idx2, stats2 = q2(z[a:b].contiguous(), do_ema_update=False)
-    torch.cuda.synchronize()
-    assert torch.equal(idx2, idx[a:b]) and torch.equal(zq2, zq[a:b])
-    assert torch.allclose(stats2, stats, rtol=1e-5), (stats2, stats)
-    assert torch.equal(q2._ep_usage, q1._ep_usage) and float(q2._ep_cnt) == float(q1._ep_cnt) == N
-    assert abs(float(q2.last_commit) - float(q1.last_commit)) < 1e-5 * float(q1.last_commit)
+    seen = {}
+    for how in ("peer", "nccl"):                                  # one kernel over NVLink peer memory / pack -> NCCL -> finalize
+        q2 = vq.VectorQuantizerEMA(K, D, print_init=False).to(dev).eval()
+        q2.embedding.copy_(E)
+        q2.stats_sync = True
+        q2.stats_exchange = how
+        for rep in range(3):                                      # epochs 1..3: both payload areas and their reuse
+            with torch.no_grad():
+                st2, zq2, idx2, stats2 = q2(z[a:b].contiguous(), do_ema_update=False)
+            torch.cuda.synchronize()
+            assert torch.equal(idx2, idx[a:b]) and torch.equal(zq2, zq[a:b])
+            assert torch.allclose(stats2, stats, rtol=1e-5), (how, rep, stats2, stats)
+            assert abs(float(q2.last_commit) - float(q1.last_commit)) < 1e-5 * float(q1.last_commit)
+        assert torch.equal(q2._ep_usage, 3 * q1._ep_usage) and float(q2._ep_cnt) == 3 * float(q1._ep_cnt) == 3 * N
+        seen[how] = stats2.clone()
+        both = [torch.empty_like(stats2) for _ in range(world)]
+        dist.all_gather(both, stats2)
+        assert all(torch.equal(g, stats2) for g in both), how     # every rank holds the same statistics, bit for bit
+    if S.PeerStatsExchange.get(dev, K) is None and rank == 0:
+        print("row_sharded_stats: peer memory unavailable on this box, NCCL path only", flush=True)
+    assert torch.allclose(seen["peer"], seen["nccl"], rtol=1e-6)
     if rank == 0:
         print("row_sharded_stats ok", flush=True)
 
