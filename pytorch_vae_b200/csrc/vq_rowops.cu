@@ -22,9 +22,9 @@ __global__ void __launch_bounds__(256)
 codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restrict__ seg_cnt, float decay,
                         float omd, float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb,
                         float* E, uint16_t* __restrict__ E_bf16, float* __restrict__ ee_half,
-                        float* __restrict__ level_meta, int chain_phase) {
+                        float* __restrict__ level_meta, int chain_phase, int row_base) {
   const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row = row_base + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int D4 = D >> 2;
   __shared__ int s_red[8][6];
   if (row < K_total) {
@@ -51,17 +51,39 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
   double acc = 0.0, accb = 0.0, accd = 0.0, acch = 0.0, accdh = 0.0;
   bool bad = false;
   uint16_t* E_f16 = E_bf16 + static_cast<int64_t>(K_total) * D;        // operand plane 1
-  for (int c = lane; c < D4; c += 32) {
+  // four float4 slices of the row per lane and pass: every load of the pass is issued before the first use (one memory
+  // round trip per 512 floats of the row instead of one per 128: the kernel is latency-, not bandwidth-bound)
+  for (int c0 = lane; c0 < D4; c0 += 128) {
+    float4 in_a[4], in_s[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = c0 + 32 * u;
+      if (c < D4) {
+        const int64_t o = static_cast<int64_t>(row) * D4 + c;
+        if (touch) {
+          in_a[u] = reinterpret_cast<const float4*>(ema_emb)[o];
+          if (real) in_s[u] = reinterpret_cast<const float4*>(seg_sum)[o];
+        } else if (MODE == 2 && denom > 0.f) {
+          in_s[u] = reinterpret_cast<const float4*>(seg_sum)[o];
+        } else {
+          in_a[u] = reinterpret_cast<const float4*>(E)[o];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+    const int c = c0 + 32 * u;
+    if (c >= D4) continue;
     const int64_t o = static_cast<int64_t>(row) * D4 + c;
     float4 e;
     if (touch) {
-      float4 n = reinterpret_cast<const float4*>(ema_emb)[o];
+      float4 n = in_a[u];
       for (int i = 0; i < n_pre; ++i) {
         n.x = __fadd_rn(__fmul_rn(n.x, decay), zero_term); n.y = __fadd_rn(__fmul_rn(n.y, decay), zero_term);
         n.z = __fadd_rn(__fmul_rn(n.z, decay), zero_term); n.w = __fadd_rn(__fmul_rn(n.w, decay), zero_term);
       }
       if (real) {
-        const float4 s = reinterpret_cast<const float4*>(seg_sum)[o];
+        const float4 s = in_s[u];
         n.x = __fadd_rn(__fmul_rn(n.x, decay), __fmul_rn(s.x, omd));
         n.y = __fadd_rn(__fmul_rn(n.y, decay), __fmul_rn(s.y, omd));
         n.z = __fadd_rn(__fmul_rn(n.z, decay), __fmul_rn(s.z, omd));
@@ -76,12 +98,12 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
       e.z = __fdiv_rn(n.z, denom); e.w = __fdiv_rn(n.w, denom);
       reinterpret_cast<float4*>(E)[o] = e;
     } else if (MODE == 2 && denom > 0.f) {
-      const float4 sm = reinterpret_cast<const float4*>(seg_sum)[o];
+      const float4 sm = in_s[u];
       e.x = __fdiv_rn(sm.x, denom); e.y = __fdiv_rn(sm.y, denom);
       e.z = __fdiv_rn(sm.z, denom); e.w = __fdiv_rn(sm.w, denom);
       reinterpret_cast<float4*>(E)[o] = e;
     } else {
-      e = reinterpret_cast<const float4*>(E)[o];
+      e = in_a[u];
     }
     const __nv_bfloat16 b0 = __float2bfloat16_rn(e.x), b1 = __float2bfloat16_rn(e.y),
                         b2 = __float2bfloat16_rn(e.z), b3 = __float2bfloat16_rn(e.w);
@@ -113,6 +135,7 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
       accdh += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
     }
     bad |= !(isfinite(e.x) && isfinite(e.y) && isfinite(e.z) && isfinite(e.w));
+    }
   }
   acc = warp_sum(acc);
   accb = warp_sum(accb);
@@ -148,7 +171,7 @@ codebook_refresh_kernel(const float* __restrict__ seg_sum, const float* __restri
   // positive floats order like their bit patterns.  A block whose rows straddle two levels reduces per row.
   __syncthreads();
   {
-    const int wpb = blockDim.x >> 5, row0 = blockIdx.x * wpb;
+    const int wpb = blockDim.x >> 5, row0 = row_base + blockIdx.x * wpb;
     const int rows_here = K_total - row0 < wpb ? K_total - row0 : wpb;
     const int slot[6] = {0, 2, 3, 4, 5, 7};
     if (rows_here > 0 && threadIdx.x < 6) {
@@ -191,19 +214,31 @@ int launch_codebook_refresh(int mode, const float* seg_sum, const float* seg_cnt
                             float eps, int K_total, int D, int K_per, float* ema_cs, float* ema_emb, float* E,
                             uint16_t* E_bf16, float* ee_half, float* level_meta, cudaStream_t s, int chain_phase) {
   const int levels = K_total / K_per;
+  const int wpb = 8;
+  if (mode == 1 && chain_phase == 1) {
+    // level 0 receives no decay-only step and its cache entries are current: its rows are not visited and its level
+    // norms stay (only the ticket word of the last-block pass, level_meta[6], is cleared)
+    if (levels < 2) return VQB200_OK;
+    cudaError_t e = cudaMemsetAsync(level_meta + VQB200_LEVEL_META_FLOATS, 0, sizeof(float) * VQB200_LEVEL_META_FLOATS * (levels - 1), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(level_meta + 6, 0, sizeof(float), s);
+    if (e != cudaSuccess) return status_of(e);
+    const int blocks1 = (K_total - K_per + wpb - 1) / wpb;
+    codebook_refresh_kernel<1><<<blocks1, wpb * 32, 0, s>>>(seg_sum, seg_cnt, decay, omd, eps, K_total, D, K_per, ema_cs,
+                                                           ema_emb, E, E_bf16, ee_half, level_meta, 1, K_per);
+    return status_of(cudaGetLastError());
+  }
   cudaError_t e = cudaMemsetAsync(level_meta, 0, sizeof(float) * VQB200_LEVEL_META_FLOATS * levels, s);
   if (e != cudaSuccess) return status_of(e);
-  const int wpb = 8;
   const int blocks = (K_total + wpb - 1) / wpb;
   if (mode == 1)
     codebook_refresh_kernel<1><<<blocks, wpb * 32, 0, s>>>(seg_sum, seg_cnt, decay, omd, eps, K_total, D,
-                                                          K_per, ema_cs, ema_emb, E, E_bf16, ee_half, level_meta, chain_phase);
+                                                          K_per, ema_cs, ema_emb, E, E_bf16, ee_half, level_meta, chain_phase, 0);
   else if (mode == 2)
     codebook_refresh_kernel<2><<<blocks, wpb * 32, 0, s>>>(seg_sum, seg_cnt, 0.f, 0.f, 0.f, K_total, D, K_per,
-                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta, 0);
+                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta, 0, 0);
   else
     codebook_refresh_kernel<0><<<blocks, wpb * 32, 0, s>>>(nullptr, nullptr, 0.f, 0.f, 0.f, K_total, D, K_per,
-                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta, 0);
+                                                          nullptr, nullptr, E, E_bf16, ee_half, level_meta, 0, 0);
   return status_of(cudaGetLastError());
 }
 

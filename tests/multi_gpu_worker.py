@@ -105,9 +105,9 @@ def allreduced_ema_training(dev, rank, world):
         if not (same == 1.0 if step == 0 else same > 0.98):
             problems.append(f"step {step}: only {same:.4f} of the rows agree with the single-GPU run")
         scale = float(q1.ema_embedding.abs().max())
-        if not torch.allclose(q2.ema_cluster_size, q1.ema_cluster_size, rtol=1e-5, atol=1e-6):
-            problems.append(f"step {step}: ema_cluster_size differs")
         if step == 0:                                             # (later steps inherit the moved near-ties)
+            if not torch.allclose(q2.ema_cluster_size, q1.ema_cluster_size, rtol=1e-5, atol=1e-6):
+                problems.append(f"step {step}: ema_cluster_size differs")
             if not torch.allclose(q2.ema_embedding, q1.ema_embedding, rtol=1e-4, atol=2e-6 * scale + 1e-7):
                 problems.append(f"step {step}: ema_embedding differs")
             if not torch.allclose(q2.embedding, q1.embedding, rtol=1e-4, atol=2e-6 * float(q1.embedding.abs().max()) + 1e-7):
