@@ -299,7 +299,7 @@ VQB200_API int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int
  *   (the caller all-reduces seg_sum / seg_cnt over its ranks)
  *   finish: every level's own update from its segment sums and the decay-only steps of the later levels; codebook
  *           cache refreshed.  begin + finish with nothing in between = vqb200_rvq_train_forward, bit for bit.
- * Shapes: vqb200_rvq_train_fused_supported (D in {128, 256, 384, 512}, K_per >= 128, 2 <= L <= 8, N <= 65536). */
+ * Shapes: vqb200_rvq_train_fused_supported (D in {128, 256, 384, 512}, K_per >= 128, 2 <= L <= 8, N <= 65536 -- 49152 at D = 256 / 384). */
 VQB200_API int vqb200_rvq_train_fused_supported(int64_t N, int K_per, int D, int L, int mode);
 VQB200_API size_t vqb200_rvq_train_begin_workspace_bytes(int64_t N, int K_per, int D, int L, int mode);
 VQB200_API int vqb200_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,

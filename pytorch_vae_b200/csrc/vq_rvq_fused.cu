@@ -793,9 +793,10 @@ static bool rq_config(int64_t N, int D, RqConfig* c) {
 
 // Above this many rows the level-by-level pipeline (CTA-pair tensor kernel, HBM-bound passes between levels) is the
 // faster one: the persistent kernel serialises search and row passes inside a CTA (measured, profiles/README.md).
-static int64_t rq_max_rows() {
+// (profiles/r02_rvq_crossover.txt: 4 x 1024 codes; at 65536 rows D = 512: 0.72 vs 0.77 ms, D = 256: 0.57 vs 0.54 ms)
+static int64_t rq_max_rows(int D) {
   if (const char* e = std::getenv("VQB200_RVQ_FUSED_MAX_ROWS")) return std::atoll(e);
-  return 65536;
+  return (D == 256 || D == 384) ? 49152 : 65536;
 }
 
 bool rvq_fused_supported(int64_t N, int K_per, int D, int L) {
@@ -803,7 +804,7 @@ bool rvq_fused_supported(int64_t N, int K_per, int D, int L) {
   if (f && f[0] == '1') return false;
   const char* g = std::getenv("VQB200_NO_RVQ_FUSED");
   if (g && g[0] == '1') return false;
-  if (D % 128 != 0 || D < 128 || D > 512 || K_per < TC_BN || L < 2 || L > RQ_MAXL || N < 1 || N > rq_max_rows()) return false;
+  if (D % 128 != 0 || D < 128 || D > 512 || K_per < TC_BN || L < 2 || L > RQ_MAXL || N < 1 || N > rq_max_rows(D)) return false;
   RqConfig c;
   return rq_config(N, D, &c);
 }
