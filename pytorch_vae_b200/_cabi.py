@@ -16,7 +16,7 @@ MODE_FP32_EXACT = 0
 MODE_BF16_INPUT = 1
 MAX_LEVELS = 32
 LEVEL_META_FLOATS = 8
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 _p = C.c_void_p
 _i = C.c_int
@@ -46,6 +46,8 @@ SIGNATURES = {
     "vqb200_rvq_train_finish": (_i, [_p, _p, C.c_float, C.c_float, C.c_float, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "vqb200_stats_exchange_buffer_bytes": (_sz, [_i, _i]),
     "vqb200_stats_exchange": (_i, [_p, _i, _p, C.c_double, _i, _i, _p, _i, _i, C.c_uint64, _p, _p, _p, _p]),
+    "vqb200_softmax_rows_workspace_bytes": (_sz, [_i64, _i]),
+    "vqb200_softmax_rows": (_i, [_p, _i64, _i, _p, _p, _i, C.c_float, _p, _p, _p, _p, _sz, _p]),
     "vqb200_indices_to_memory": (_i, [_p, _i, _i64, _i, _p, _i, _i, _p, _p, _p, C.c_float, _p, _p]),
     "vqb200_rvq_forward": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "vqb200_rvq_train_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),

@@ -555,6 +555,20 @@ int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok,
                                   static_cast<cudaStream_t>(stream));
 }
 
+size_t vqb200_softmax_rows_workspace_bytes(int64_t N, int K) { return softmax_rows_workspace_bytes(N, K); }
+
+int vqb200_softmax_rows(const float* z, int64_t N, int D, const float* E, const float* beta, int K, float alpha,
+                        float* row_stats, float* probs_out, float* p_sum, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  VQ_REQUIRE(N >= 0 && K > 0, VQB200_EINVAL);
+  VQ_REQUIRE(N == 0 || (z && E && workspace && (probs_out || p_sum || row_stats)), VQB200_EINVAL);
+  VQ_REQUIRE(shape_ok(D), VQB200_ESHAPE);
+  VQ_REQUIRE(aligned16(z) && aligned16(E) && aligned16(probs_out) && (reinterpret_cast<uintptr_t>(workspace) & 7u) == 0,
+             VQB200_EALIGN);
+  return launch_softmax_rows(z, N, D, E, beta, K, alpha, row_stats, probs_out, p_sum, workspace, workspace_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
 int vqb200_indices_to_memory(const void* idx, int idx_elem_bytes, int64_t n_tok, int Q, const float* P, int K_total,
                              int H, const float* bias, const float* ln_weight, const float* ln_bias, float ln_eps,
                              float* memory_out, void* stream) {

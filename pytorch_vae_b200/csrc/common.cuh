@@ -213,6 +213,11 @@ int launch_soft_assign(const float* z, int64_t N, int D, const float* E, int K, 
                        cudaStream_t s);
 int launch_indices_to_latent(const void* idx, int bytes, int64_t n_tok, int Q, const float* E, int K_total, int D,
                              float* out, cudaStream_t s);
+// tiled row softmax fused with its logits' contraction (vq_softmax.cu)
+size_t softmax_rows_workspace_bytes(int64_t N, int K);
+int launch_softmax_rows(const float* z, int64_t N, int D, const float* E, const float* beta, int K, float alpha,
+                        float* row_stats, float* P_out, float* p_sum, void* workspace, size_t workspace_bytes,
+                        cudaStream_t s);
 int launch_indices_to_memory(const void* idx, int bytes, int64_t n_tok, int Q, const float* P, int K_total, int H,
                              const float* bias, const float* ln_w, const float* ln_b, float ln_eps, float* out,
                              cudaStream_t s);

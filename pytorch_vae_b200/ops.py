@@ -373,8 +373,56 @@ def rvq_finalize(z, idx_level0, level_stride, L, E, zq_out=None, zq_st_out=None,
 
 
 @_on_device
-def usage_probs(z, E):
-    """(p_code [K], row_stats [N, 2]): p_code = mean_n softmax_k(z_n . e_k) (models/vq_vae.py:1305-1307)."""
+def softmax_rows(z, E, alpha: float, beta=None, want_probs: bool = True, p_sum=None, row_stats=None):
+    """probs[n, k] = softmax_k(alpha * z_n . e_k + beta[k]) through the tiled two-sweep kernel (include/vq_b200.h).
+    Returns the [N, K] probabilities (``None`` with ``want_probs=False``); ``p_sum`` [K] receives their column sums."""
+    _need_cuda(z, E)
+    _f32c(z, "z")
+    _f32c(E, "embedding")
+    N, D = z.shape
+    K = E.shape[0]
+    P = torch.empty(N, K, dtype=torch.float32, device=z.device) if want_probs else None
+    ws_bytes = lib.vqb200_softmax_rows_workspace_bytes(N, K)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=z.device)
+    check(lib.vqb200_softmax_rows(ptr(z), N, D, ptr(E), ptr(beta), K, float(alpha), ptr(row_stats), ptr(P), ptr(p_sum),
+                                  ptr(ws), ws_bytes, stream_ptr()), "vqb200_softmax_rows")
+    _count(2)
+    return P
+
+
+def _matmul_fp32(a, b):
+    """Plain library GEMM in full fp32 (never TF32, whatever the process-wide switch says)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        return a @ b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@_on_device
+def usage_probs(z, E, keep_probs: bool = False):
+    """(p_code [K], probs [N, K] or None): p_code = mean_n softmax_k(z_n . e_k) (models/vq_vae.py:1305-1307).
+    ``keep_probs`` also returns the probabilities (the backward needs them)."""
+    N = z.shape[0]
+    p_sum = torch.zeros(E.shape[0], dtype=torch.float32, device=z.device)
+    P = softmax_rows(z, E, 1.0, None, want_probs=keep_probs, p_sum=p_sum)
+    return p_sum / max(N, 1), P
+
+
+def usage_probs_backward_from_probs(P, E, grad_p):
+    """grad_z_n = (1/N) sum_j P_nj (g_j - sum_k P_nk g_k) e_j from the saved probabilities: elementwise passes over
+    [N, K] and one plain fp32 GEMM."""
+    N = P.shape[0]
+    rowdot = P @ grad_p                                   # [N]
+    dS = P * (grad_p.unsqueeze(0) - rowdot.unsqueeze(1))
+    dS.mul_(1.0 / max(N, 1))
+    return _matmul_fp32(dS, E)
+
+
+@_on_device
+def usage_probs_warp(z, E):
+    """The first implementation (one warp per row, nothing stored): (p_code [K], row_stats [N, 2])."""
     _need_cuda(z, E)
     _f32c(z, "z")
     _f32c(E, "embedding")
@@ -399,7 +447,29 @@ def usage_probs_backward(z, E, row_stats, grad_p):
 
 @_on_device
 def soft_assign(z, E, tau: float, out=None):
-    """z_soft = softmax(-|z - e|^2 / tau) @ E (models/vq_vae.py:838-843), online softmax, nothing materialised."""
+    """z_soft = softmax(-|z - e|^2 / tau) @ E (models/vq_vae.py:838-843): the tiled row-softmax kernel
+    (logits 2 z.e / tau - |e|^2 / tau: the row constant cancels) and one plain fp32 GEMM probs @ E.  The reference
+    materialises the [N, K, D] differences; this stores the [N, K] probabilities only."""
+    _need_cuda(z, E)
+    _f32c(z, "z")
+    _f32c(E, "embedding")
+    if z.shape[1] > 512:
+        raise RuntimeError("soft_assign: D <= 512")
+    if z.shape[0] == 0:
+        return torch.empty_like(z) if out is None else out
+    t = max(float(tau), 1e-8)
+    beta = (E * E).sum(1).mul_(-1.0 / t)
+    P = softmax_rows(z, E, 2.0 / t, beta)
+    res = _matmul_fp32(P, E)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+@_on_device
+def soft_assign_warp(z, E, tau: float, out=None):
+    """The first implementation: one warp per row, online softmax, nothing materialised (vqb200_soft_assign)."""
     _need_cuda(z, E)
     _f32c(z, "z")
     _f32c(E, "embedding")

@@ -585,14 +585,16 @@ class _UsageProbsFn(torch.autograd.Function):
     def forward(ctx, z_flat, E):
         z = z_flat.detach().contiguous()
         Ed = E.detach().contiguous()
-        p_code, row_stats = ops.usage_probs(z, Ed)
-        ctx.save_for_backward(z, Ed, row_stats)
+        need = bool(ctx.needs_input_grad[0])
+        p_code, probs = ops.usage_probs(z, Ed, keep_probs=need)
+        if need:
+            ctx.save_for_backward(probs, Ed)
         return p_code
 
     @staticmethod
     def backward(ctx, g):
-        z, Ed, row_stats = ctx.saved_tensors
-        return ops.usage_probs_backward(z, Ed, row_stats, g.to(torch.float32).contiguous()), None
+        probs, Ed = ctx.saved_tensors
+        return ops.usage_probs_backward_from_probs(probs, Ed, g.to(torch.float32).contiguous()), None
 
 
 class _CommitFn(torch.autograd.Function):

@@ -113,3 +113,28 @@ def test_usage_probs_matches_oracle(vq, K, D, N):
     np.testing.assert_allclose(p.detach().cpu().numpy(), op, rtol=2e-5, atol=1e-8)
     scale = np.abs(ograd).max()
     np.testing.assert_allclose(zt.grad.cpu().numpy(), ograd, rtol=1e-3, atol=1e-4 * scale)
+
+
+@pytest.mark.parametrize("K,D,N,tau", [(512, 64, 4096, 0.5), (1000, 128, 1111, 2.0), (1024, 512, 700, 0.7), (37, 20, 65, 1.0),
+                                        (130, 36, 129, 0.3)])
+def test_tiled_softmax_paths_match_first_version(vq, K, D, N, tau):
+    """The tiled two-sweep kernel (vqb200_softmax_rows, + a plain fp32 GEMM) against the first implementation (one warp per
+    row, online softmax, nothing stored): soft assignment, usage probabilities and their gradient."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(K + N)
+    E = torch.randn(K, D, device=dev, generator=g) / np.sqrt(D)
+    z = E[torch.randint(0, K, (N,), device=dev, generator=g)] + 0.3 / np.sqrt(D) * torch.randn(N, D, device=dev, generator=g)
+    a = vq.ops.soft_assign(z, E, tau)
+    b = vq.ops.soft_assign_warp(z, E, tau)
+    torch.testing.assert_close(a, b, rtol=3e-5, atol=3e-6)
+    P = vq.ops.softmax_rows(z, E, 1.0)
+    assert P.shape == (N, K)
+    torch.testing.assert_close(P.sum(1), torch.ones(N, device=dev), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(P, torch.softmax((z.double() @ E.double().t()), dim=1).float(), rtol=2e-5, atol=1e-8)
+    p1, Pk = vq.ops.usage_probs(z, E, keep_probs=True)
+    p2, rs = vq.ops.usage_probs_warp(z, E)
+    torch.testing.assert_close(p1, p2, rtol=2e-5, atol=1e-8)
+    gp = torch.randn(K, device=dev, generator=g)
+    g1 = vq.ops.usage_probs_backward_from_probs(Pk, E, gp)
+    g2 = vq.ops.usage_probs_backward(z, E, rs, gp)
+    torch.testing.assert_close(g1, g2, rtol=1e-3, atol=1e-4 * float(g2.abs().max()))
