@@ -141,6 +141,35 @@ def test_extra_entry_points_refuse_cpu_tensors():
         vq.GraphedTrainStep(q.eval(), torch.randn(2, 4, 16))  # needs training mode (and CUDA)
     with pytest.raises(RuntimeError):
         vq.ops.rvq_finalize(torch.randn(4, 16), torch.zeros(4, dtype=torch.int64), 4, 1, torch.randn(8, 16))
+    # round-2 entry points: tiled row softmax, indices -> decoder memory, the mirror model's decode_indices
+    with pytest.raises(RuntimeError):
+        vq.ops.softmax_rows(torch.randn(4, 16), torch.randn(8, 16), 1.0)
+    with pytest.raises(RuntimeError):
+        vq.ops.soft_assign(torch.randn(4, 16), torch.randn(8, 16), 1.0)
+    with pytest.raises(RuntimeError):
+        vq.ops.indices_to_memory(torch.zeros(4, dtype=torch.int64), torch.randn(8, 16), 1)
+    from pytorch_vae_b200.vqvae import VQVAE
+    m = VQVAE(hidden_dim=32, code_dim=16, codebook_size=8, latent_tokens=4, max_seq_len=8, num_layers=1, num_heads=2,
+              tokenizer_layers=1, tokenizer_heads=2, print_init=False)
+    assert m.projected_codebook().shape == (8, 32)              # the table itself is host-side algebra ...
+    with pytest.raises(RuntimeError):
+        m.memory_from_indices(torch.zeros(1, 4, dtype=torch.int64))   # ... the gather + LayerNorm kernel is not
+
+
+def test_persistent_kernel_shape_rules_without_a_gpu():
+    """Which residual shapes run as ONE persistent kernel (csrc/vq_rvq_fused.cu) and what a training forward launches."""
+    lib = vq._cabi.lib
+    assert lib.vqb200_rvq_fused_supported(8192, 1024, 512, 4, 0) == 1
+    assert lib.vqb200_rvq_fused_supported(65536, 1024, 512, 4, 0) == 1 and lib.vqb200_rvq_fused_supported(65537, 1024, 512, 4, 0) == 0
+    assert lib.vqb200_rvq_fused_supported(49152, 1024, 256, 4, 0) == 1 and lib.vqb200_rvq_fused_supported(65536, 1024, 256, 4, 0) == 0
+    assert lib.vqb200_rvq_fused_supported(8192, 1024, 64, 4, 0) == 0            # D = 64: level pipeline
+    assert lib.vqb200_rvq_fused_supported(8192, 64, 512, 4, 0) == 0             # fewer codes than one tile
+    assert lib.vqb200_rvq_fused_supported(8192, 1024, 512, 1, 0) == 0 and lib.vqb200_rvq_fused_supported(8192, 1024, 512, 9, 0) == 0
+    assert lib.vqb200_rvq_train_fused_supported(8192, 1024, 512, 4, 0) == 1
+    assert lib.vqb200_rvq_train_launches(8192, 1024, 512, 4, 0) == 3            # refresh, persistent kernel, refresh
+    assert lib.vqb200_rvq_train_workspace_bytes(8192, 1024, 512, 4, 0) >= 4096 * 512 * 4 + 4096 * 4 + 128 * 64 * 512 * 4
+    assert lib.vqb200_stats_exchange_buffer_bytes(4096, 8) == 512 + 17 * 4098 * 8
+    assert lib.vqb200_softmax_rows_workspace_bytes(8192, 1024) >= 8192 * 8
 
 
 def test_launch_and_workspace_accounting_without_a_gpu():
