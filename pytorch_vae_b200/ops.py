@@ -138,6 +138,11 @@ def rvq_train_forward(z, E, cache: CodebookCache, mode, decay, eps, ema_cluster_
                                        ptr(ema_cluster_size), ptr(ema_embedding), ptr(idx_out), ptr(zq_out),
                                        ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws), ws_bytes, stream_ptr()),
           "vqb200_rvq_train_forward")
+    if lib.vqb200_rvq_train_fused_supported(N, K, D, L, mode):
+        # persistent kernel: its counters follow the segment sums in the workspace (diagnostics, read lazily)
+        global last_rvq_workspace
+        seg_bytes = ((K * L * D * 4 + K * L * 4) + 255) // 256 * 256
+        last_rvq_workspace = ws[seg_bytes:]
     _count(lib.vqb200_rvq_train_launches(N, K, D, L, mode))
 
 
