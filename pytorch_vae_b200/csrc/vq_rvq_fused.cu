@@ -192,9 +192,7 @@ __device__ __forceinline__ double rq_exact_score(const float4 (&v)[SL], const fl
       ee = fma(static_cast<double>(e4[q]), static_cast<double>(e4[q]), ee);
     }
   }
-  dot = warp_sum(dot);
-  ee = warp_sum(ee);
-  return dot - 0.5 * ee;
+  return warp_sum(dot - 0.5 * ee);                         // one reduction per candidate (bit-identical codes still tie exactly)
 }
 // exhaustive exact search of one level by the warp: d' = |e|^2/2 - r.e (fp32), packed (key, index) minimum -- the rule
 // of search_simt_kernel (lowest index on ties, a NaN distance wins).  Rare: kept out of line; it re-loads the row.

@@ -359,7 +359,14 @@ class VectorQuantizerEMA(nn.Module):
                 self._ema_update(flat, idx, valid_u8)
             return
         residual = flat
-        spare = [torch.empty(n, D, dtype=torch.float32, device=flat.device) for _ in range(min(2, L - 1))]
+        class _Spare:                                       # residual ping-pong buffers of the level-by-level paths,
+            bufs = None                                     # allocated only when one of them runs
+
+            def __getitem__(self, i):
+                if self.bufs is None:
+                    self.bufs = [torch.empty(n, D, dtype=torch.float32, device=flat.device) for _ in range(min(2, L - 1))]
+                return self.bufs[i]
+        spare = _Spare()
         lstride = (idx_levels[1].data_ptr() - idx_levels[0].data_ptr()) // 8 if L > 1 else n
         even = all(idx_levels[l].data_ptr() == idx_levels[0].data_ptr() + 8 * l * lstride for l in range(L))
         if not do_ema and L <= 8 and even and lstride >= n:
