@@ -33,7 +33,7 @@ extern "C" {
 #define VQB200_API
 #endif
 
-#define VQB200_ABI_VERSION 17
+#define VQB200_ABI_VERSION 18
 #define VQB200_MAX_LEVELS 32
 #define VQB200_LEVEL_META_FLOATS 8 /* per level: [0] max|e|, [1] non-finite flag, [2] max|bf16(e)|,
                                       [3] max|e - bf16(e)|, [4] max|f16(e)|, [5] max|e - f16(e)|, [6..7] internal (dead-code de-duplication) */
@@ -301,6 +301,22 @@ VQB200_API int vqb200_relayout_indices(const int64_t* idx_level_major, int Q, in
  * (scripts/decode_with_vqvae.py:110-130; models/vq_vae.py:1404-1418). */
 VQB200_API int vqb200_indices_to_latent(const void* idx, int idx_elem_bytes, int64_t n_tok, int Q, const float* E,
                              int K_total, int D, float* zq_out, void* stream);
+
+/* vqb200_rvq_forward / vqb200_rvq_train_forward followed by vqb200_stats_finalize(hist, K_per * L, count_add, sqerr_sum,
+ * inv_elems, ep_usage, ep_cnt, stats_out) -- inside the persistent kernel where it runs (its last CTA to finish turns
+ * the histogram into the statistics: one launch fewer on a 0.14 ms forward), as a separate launch elsewhere.
+ * hist, sqerr_sum and stats_out are required. */
+VQB200_API int vqb200_rvq_forward_stats(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp,
+                             const float* ee_half, const float* ee_half_bf16, const float* level_meta, int K_per, int L,
+                             int mode, int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum,
+                             int32_t* hist, void* workspace, size_t workspace_bytes, float count_add, double inv_elems,
+                             float* ep_usage, float* ep_cnt, float* stats_out, void* stream);
+VQB200_API int vqb200_rvq_train_forward_stats(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes,
+                                   float* ee_half, float* level_meta, int K_per, int L, int mode, float decay,
+                                   float one_minus_decay, float eps, float* ema_cluster_size, float* ema_embedding,
+                                   int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                                   void* workspace, size_t workspace_bytes, float count_add, double inv_elems,
+                                   float* ep_usage, float* ep_cnt, float* stats_out, void* stream);
 
 /* The training forward of a residual codebook in two halves, for data-parallel training with the EMA segment sums
  * all-reduced over ranks: the reference runs one EMA update per level and each touches all

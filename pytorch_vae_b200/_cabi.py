@@ -16,7 +16,7 @@ MODE_FP32_EXACT = 0
 MODE_BF16_INPUT = 1
 MAX_LEVELS = 32
 LEVEL_META_FLOATS = 8
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 _p = C.c_void_p
 _i = C.c_int
@@ -39,6 +39,10 @@ SIGNATURES = {
     "vqb200_rvq_forward_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "vqb200_rvq_forward_launches": (_i, [_i64, _i, _i, _i, _i]),
     "vqb200_rvq_fused_supported": (_i, [_i64, _i, _i, _i, _i]),
+    "vqb200_rvq_forward_stats": (_i, [_p, _i64, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz,
+                                      C.c_float, C.c_double, _p, _p, _p, _p]),
+    "vqb200_rvq_train_forward_stats": (_i, [_p, _i64, _i, _p, _p, _p, _p, _i, _i, _i, C.c_float, C.c_float, C.c_float,
+                                            _p, _p, _p, _p, _p, _p, _p, _p, _sz, C.c_float, C.c_double, _p, _p, _p, _p]),
     "vqb200_rvq_train_fused_supported": (_i, [_i64, _i, _i, _i, _i]),
     "vqb200_rvq_train_begin_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "vqb200_rvq_train_begin": (_i, [_p, _i64, _i, _p, _p, _p, _p, _i, _i, _i, C.c_float, C.c_float, C.c_float, _p, _p,

@@ -121,10 +121,10 @@ int vqb200_rvq_forward_launches(int64_t N, int K_per, int D, int L, int mode) {
   return per_search + (L - 1) * (per_search - chunks) + (L - 1) + 1;
 }
 
-int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
-                       const float* ee_half_bf16, const float* level_meta, int K_per, int L, int mode,
-                       int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
-                       void* workspace, size_t workspace_bytes, void* stream) {
+static int rvq_forward_impl(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
+                            const float* ee_half_bf16, const float* level_meta, int K_per, int L, int mode,
+                            int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                            void* workspace, size_t workspace_bytes, void* stream, const RvqStatsTail* tail) {
   VQ_REQUIRE(N >= 0 && K_per > 0 && L >= 1 && L <= 8, VQB200_EINVAL);
   if (N == 0) return VQB200_OK;
   VQ_REQUIRE(z && idx_out && E && E_lp && ee_half && ee_half_bf16 && level_meta && workspace, VQB200_EINVAL);
@@ -137,7 +137,7 @@ int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const u
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
   if (rvq_fused_supported(N, K_per, D, L))                // every level inside ONE persistent kernel
     return launch_rvq_fused(z, N, D, E, E_lp, bf ? ee_half_bf16 : ee_half, level_meta, K_per, L, mode, idx_out, zq_out,
-                            zq_st_out, sqerr_sum, hist, workspace, workspace_bytes, s);
+                            zq_st_out, sqerr_sum, hist, workspace, workspace_bytes, s, nullptr, nullptr, tail);
   const bool tc = tc_supported(N, K_per, D);
   const int K_total = K_per * L;
   uint8_t* w = static_cast<uint8_t*>(workspace);
@@ -176,7 +176,30 @@ int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const u
       residual = nxt;
     }
   }
-  return launch_rvq_finalize(z, idx_out, N, N, D, L, E, K_total, zq_out, zq_st_out, sqerr_sum, hist, s);
+  int st = launch_rvq_finalize(z, idx_out, N, N, D, L, E, K_total, zq_out, zq_st_out, sqerr_sum, hist, s);
+  if (st == VQB200_OK && tail && tail->stats_out && hist)   // shapes the persistent kernel does not take: a separate launch
+    st = launch_stats_finalize(hist, K_total, tail->count_add, sqerr_sum, tail->inv_elems, tail->ep_usage, tail->ep_cnt,
+                               tail->stats_out, s);
+  return st;
+}
+
+int vqb200_rvq_forward(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
+                       const float* ee_half_bf16, const float* level_meta, int K_per, int L, int mode,
+                       int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  return rvq_forward_impl(z, N, D, E, E_lp, ee_half, ee_half_bf16, level_meta, K_per, L, mode, idx_out, zq_out, zq_st_out,
+                          sqerr_sum, hist, workspace, workspace_bytes, stream, nullptr);
+}
+
+int vqb200_rvq_forward_stats(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
+                             const float* ee_half_bf16, const float* level_meta, int K_per, int L, int mode,
+                             int64_t* idx_out, float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist,
+                             void* workspace, size_t workspace_bytes, float count_add, double inv_elems, float* ep_usage,
+                             float* ep_cnt, float* stats_out, void* stream) {
+  VQ_REQUIRE(N > 0 && hist && sqerr_sum && stats_out, VQB200_EINVAL);
+  const RvqStatsTail tail{stats_out, ep_usage, ep_cnt, count_add, inv_elems};
+  return rvq_forward_impl(z, N, D, E, E_lp, ee_half, ee_half_bf16, level_meta, K_per, L, mode, idx_out, zq_out, zq_st_out,
+                          sqerr_sum, hist, workspace, workspace_bytes, stream, &tail);
 }
 
 // ---- the training-mode residual forward with a LOCAL EMA update after every level, in ONE call ----
@@ -193,11 +216,11 @@ int vqb200_rvq_train_launches(int64_t N, int K_per, int D, int L, int mode) {
   return L * (vqb200_search_launches(N, K_per, D, mode) + 3) + 1;      // + gather, scatter-add, EMA finalize; st_loss
 }
 
-int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
-                             float* level_meta, int K_per, int L, int mode, float decay, float one_minus_decay,
-                             float eps, float* ema_cluster_size, float* ema_embedding, int64_t* idx_out,
-                             float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+static int rvq_train_forward_impl(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                                  float* level_meta, int K_per, int L, int mode, float decay, float one_minus_decay,
+                                  float eps, float* ema_cluster_size, float* ema_embedding, int64_t* idx_out,
+                                  float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace,
+                                  size_t workspace_bytes, void* stream, const RvqStatsTail* tail) {
   VQ_REQUIRE(N >= 0 && K_per > 0 && L >= 1 && L <= VQB200_MAX_LEVELS, VQB200_EINVAL);
   if (N == 0) return VQB200_OK;
   VQ_REQUIRE(z && idx_out && E && E_lp_planes && ee_half && level_meta && ema_cluster_size && ema_embedding &&
@@ -211,7 +234,7 @@ int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_
   if (rvq_fused_train_supported(N, K_per, D, L))          // refresh phase 1 -> every level in ONE kernel -> refresh phase 2
     return launch_rvq_fused_train(z, N, D, E, E_lp_planes, ee_half, level_meta, K_per, L, mode, decay, one_minus_decay, eps,
                                   ema_cluster_size, ema_embedding, idx_out, zq_out, zq_st_out, sqerr_sum, hist, workspace,
-                                  workspace_bytes, s);
+                                  workspace_bytes, s, tail);
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
   const bool tc = tc_supported(N, K_per, D);
   const int K_total = K_per * L;
@@ -251,7 +274,34 @@ int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_
     if (st != VQB200_OK) return st;
     if (nxt) residual = nxt;
   }
-  return launch_st_loss(z, zq_out, N * D, zq_st_out, sqerr_sum, s);
+  int st = launch_st_loss(z, zq_out, N * D, zq_st_out, sqerr_sum, s);
+  if (st == VQB200_OK && tail && tail->stats_out && hist)
+    st = launch_stats_finalize(hist, K_total, tail->count_add, sqerr_sum, tail->inv_elems, tail->ep_usage, tail->ep_cnt,
+                               tail->stats_out, s);
+  return st;
+}
+
+int vqb200_rvq_train_forward(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                             float* level_meta, int K_per, int L, int mode, float decay, float one_minus_decay,
+                             float eps, float* ema_cluster_size, float* ema_embedding, int64_t* idx_out,
+                             float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  return rvq_train_forward_impl(z, N, D, E, E_lp_planes, ee_half, level_meta, K_per, L, mode, decay, one_minus_decay, eps,
+                                ema_cluster_size, ema_embedding, idx_out, zq_out, zq_st_out, sqerr_sum, hist, workspace,
+                                workspace_bytes, stream, nullptr);
+}
+
+int vqb200_rvq_train_forward_stats(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
+                                   float* level_meta, int K_per, int L, int mode, float decay, float one_minus_decay,
+                                   float eps, float* ema_cluster_size, float* ema_embedding, int64_t* idx_out,
+                                   float* zq_out, float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace,
+                                   size_t workspace_bytes, float count_add, double inv_elems, float* ep_usage,
+                                   float* ep_cnt, float* stats_out, void* stream) {
+  VQ_REQUIRE(N > 0 && hist && sqerr_sum && stats_out, VQB200_EINVAL);
+  const RvqStatsTail tail{stats_out, ep_usage, ep_cnt, count_add, inv_elems};
+  return rvq_train_forward_impl(z, N, D, E, E_lp_planes, ee_half, level_meta, K_per, L, mode, decay, one_minus_decay, eps,
+                                ema_cluster_size, ema_embedding, idx_out, zq_out, zq_st_out, sqerr_sum, hist, workspace,
+                                workspace_bytes, stream, &tail);
 }
 
 // ---- the same forward in two halves around the point where ranks exchange their segment sums (all-reduced EMA):

@@ -115,6 +115,69 @@ __device__ __forceinline__ float2 f16x2_bits_to_float2(uint32_t b) {
   return __half22float2(*reinterpret_cast<const __half2*>(&b));
 }
 
+// perplexity / dead ratio / mean squared error from an int32 histogram, by ONE thread block of any size that is a
+// multiple of 32 (models/vq_vae.py:209-222,267-280); ep_usage [K_total] += usage, ep_cnt [1] += count_add (either NULL).
+__device__ __forceinline__ void stats_finalize_block(const int32_t* hist, int K_total, float count_add, const double* sqerr_sum,
+                                                     double inv_elems, float* ep_usage, float* ep_cnt, float* stats_out) {
+  __shared__ double sf_red[32], sf_red2[32];
+  __shared__ double sf_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // up to SF_REG bins per thread stay in registers for both passes (their loads in flight together); larger codebooks
+  // re-read the tail from L2
+  constexpr int SF_REG = 8;
+  int c_reg[SF_REG];
+#pragma unroll
+  for (int u = 0; u < SF_REG; ++u) {
+    const int k = tid + u * static_cast<int>(blockDim.x);
+    c_reg[u] = k < K_total ? __ldcg(hist + k) : 0;
+  }
+  double t = 0.0;
+#pragma unroll
+  for (int u = 0; u < SF_REG; ++u) t += static_cast<double>(c_reg[u]);
+  for (int k = tid + SF_REG * static_cast<int>(blockDim.x); k < K_total; k += blockDim.x) t += static_cast<double>(__ldcg(hist + k));
+  t = warp_sum(t);
+  if (lane == 0) sf_red[warp] = t;
+  __syncthreads();
+  if (warp == 0) {
+    double v = lane < nwarps ? sf_red[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) sf_total = v < 1.0 ? 1.0 : v;             // total.clamp_min(1.0)
+  }
+  __syncthreads();
+  const double total = sf_total;
+  double h = 0.0, dead = 0.0;
+  auto bin = [&](int k, int ci) {
+    const long long c = ci;
+    if (c > 0) { const double pr = static_cast<double>(c) / total; h += pr * log(pr); }
+    else dead += 1.0;
+    if (ep_usage) ep_usage[k] += static_cast<float>(c);
+  };
+#pragma unroll
+  for (int u = 0; u < SF_REG; ++u) {
+    const int k = tid + u * static_cast<int>(blockDim.x);
+    if (k < K_total) bin(k, c_reg[u]);
+  }
+  for (int k = tid + SF_REG * static_cast<int>(blockDim.x); k < K_total; k += blockDim.x) bin(k, __ldcg(hist + k));
+  __syncthreads();
+  h = warp_sum(h);
+  dead = warp_sum(dead);
+  if (lane == 0) { sf_red[warp] = h; sf_red2[warp] = dead; }
+  __syncthreads();
+  if (warp == 0) {
+    double a = lane < nwarps ? sf_red[lane] : 0.0;
+    double b = lane < nwarps ? sf_red2[lane] : 0.0;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) {
+      const bool any = b < static_cast<double>(K_total);
+      stats_out[0] = any ? static_cast<float>(exp(-a)) : 0.f;
+      stats_out[1] = static_cast<float>(b / static_cast<double>(K_total));
+      stats_out[2] = sqerr_sum ? static_cast<float>(__ldcg(sqerr_sum) * inv_elems) : 0.f;
+      if (ep_cnt) ep_cnt[0] += count_add;
+    }
+  }
+}
+
 void timing_mark_begin(cudaStream_t s);
 void timing_mark_end(cudaStream_t s);
 int launch_search_simt(const float* z, const int32_t* row_list, int64_t n_rows, int D, const float* E,
@@ -149,13 +212,21 @@ int launch_search_tc(const float* z, int64_t N, int D, const float* E, const uin
                      const float* ee_half_bf16, const float* level_meta, int K, int mode, int64_t idx_offset,
                      int64_t* idx_out, void* workspace, size_t workspace_bytes, cudaStream_t s,
                      const GatherArgs* ga = nullptr, const PrepArgs* prep = nullptr);
+// optional statistics tail of the persistent kernel (the arguments of vqb200_stats_finalize)
+struct RvqStatsTail {
+  float* stats_out;
+  float* ep_usage;
+  float* ep_cnt;
+  float count_add;
+  double inv_elems;
+};
 // persistent residual-VQ forward, all levels in one kernel (vq_rvq_fused.cu)
 bool rvq_fused_supported(int64_t N, int K_per, int D, int L);
 size_t rvq_fused_workspace_bytes(int64_t N, int D);
 int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
                      const float* level_meta, int K_per, int L, int mode, int64_t* idx_out, float* zq_out,
                      float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes,
-                     cudaStream_t s, float* seg_sum = nullptr, float* seg_cnt = nullptr);
+                     cudaStream_t s, float* seg_sum = nullptr, float* seg_cnt = nullptr, const RvqStatsTail* tail = nullptr);
 // training mode: refresh phase 1 -> the same kernel reducing the EMA segment sums -> refresh phase 2 (three launches)
 bool rvq_fused_train_supported(int64_t N, int K_per, int D, int L);
 size_t rvq_fused_train_workspace_bytes(int64_t N, int K_per, int D, int L);
@@ -163,14 +234,15 @@ int launch_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t*
                            float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
                            float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
                            double* sqerr_sum, int32_t* hist, float* seg_sum, float* seg_cnt, void* workspace,
-                           size_t workspace_bytes, cudaStream_t s);
+                           size_t workspace_bytes, cudaStream_t s, const RvqStatsTail* tail = nullptr);
 int launch_rvq_train_finish(const float* seg_sum, const float* seg_cnt, float decay, float omd, float eps, int K_per, int L,
                             int D, float* ema_cs, float* ema_emb, float* E, uint16_t* E_lp_planes, float* ee_half,
                             float* level_meta, cudaStream_t s);
 int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
                            float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
                            float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
-                           double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes, cudaStream_t s);
+                           double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                           const RvqStatsTail* tail = nullptr);
 bool fused_supported(int64_t N, int K, int D);
 size_t fused_workspace_bytes(int64_t N);
 int launch_quantize_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_bf16, const float* ee_half,

@@ -59,6 +59,13 @@ struct RvqParams {
   // training mode (SCATTER): the EMA segment sums of models/vq_vae.py:80-83, per level, zero on entry
   float* seg_sum;               // [L * K_per, D]  sum of the residual rows that chose the code
   float* seg_cnt;               // [L * K_per]     how many did
+  // statistics tail (optional): the LAST CTA to finish turns the histogram into perplexity / dead ratio / mean squared
+  // error (the stats_finalize kernel of the separate path) -- one launch fewer on a 0.14 ms forward
+  float* stats_out;             // [3] or NULL
+  float* ep_usage;              // [L * K_per] or NULL
+  float* ep_cnt;                // [1] or NULL
+  float count_add;
+  double inv_elems;
 };
 // roles: 0 = MMA warp, 1 = first scanning warp (warp 4), 2 = first helper warp (warp 2)
 #define RQ_TR(role, lvl, ev)                                                                               \
@@ -760,6 +767,18 @@ rvq_fused_kernel(const __grid_constant__ CUtensorMap tmap_e, const RvqParams p) 
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * BN) : "memory");
   }
+  if (p.stats_out) {
+    // every CTA's histogram / squared-error reductions precede its ticket; the last one sees them all
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.counters + 2, 1) == static_cast<int>(gridDim.x) - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      stats_finalize_block(p.hist, p.K_per * p.L, p.count_add, p.sqerr_sum, p.inv_elems, p.ep_usage, p.ep_cnt, p.stats_out);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -767,6 +786,8 @@ static int rq_smem_bytes(int BM, int BN, int D, int stages) {
   return 1024 + BM * D * 2 + stages * BN * TC_KB * 2 + rq_misc_bytes(BM, BN) + 8 + 24 * 8 + 64;
 }
 
+// dynamic shared memory the kernel may ask for: the 227 KB of the SM minus its static shared memory (statistics tail)
+constexpr int RQ_SMEM_LIMIT = TC_SMEM_LIMIT - 1024;
 struct RqConfig { int BM, BN, stages, grid, smem; };
 
 // Tile shape of a launch.  BM = 64 when the batch has so few 128-row tiles that most of a second wave of SMs would
@@ -780,8 +801,8 @@ static bool rq_config(int64_t N, int D, RqConfig* c) {
   }
   int bn = (bm == 64 || D <= 384) ? 256 : 128;
   int stages = 8;
-  while (stages > 3 && rq_smem_bytes(bm, bn, D, stages) > TC_SMEM_LIMIT) --stages;
-  if (rq_smem_bytes(bm, bn, D, stages) > TC_SMEM_LIMIT) return false;
+  while (stages > 3 && rq_smem_bytes(bm, bn, D, stages) > RQ_SMEM_LIMIT) --stages;
+  if (rq_smem_bytes(bm, bn, D, stages) > RQ_SMEM_LIMIT) return false;
   const int64_t tiles = (N + bm - 1) / bm;
   c->BM = bm; c->BN = bn; c->stages = stages;
   c->grid = static_cast<int>(tiles < kNumSMs ? tiles : kNumSMs);
@@ -833,9 +854,9 @@ static int launch_rq(const CUtensorMap& map_e, const RvqParams& p, bool bf, int 
   static bool attr_done_dev[64] = {};
   bool& attr_done = attr_done_dev[current_device_slot()];
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(rvq_fused_kernel<SL, false, BM, BN, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(rvq_fused_kernel<SL, false, BM, BN, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_LIMIT);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(rvq_fused_kernel<SL, true, BM, BN, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT);
+      e = cudaFuncSetAttribute(rvq_fused_kernel<SL, true, BM, BN, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, RQ_SMEM_LIMIT);
     if (e != cudaSuccess) return status_of(e);
     attr_done = true;
   }
@@ -857,7 +878,7 @@ static int launch_rq_shape(const CUtensorMap& map_e, const RvqParams& p, bool bf
 int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,
                      const float* level_meta, int K_per, int L, int mode, int64_t* idx_out, float* zq_out,
                      float* zq_st_out, double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes,
-                     cudaStream_t s, float* seg_sum, float* seg_cnt) {
+                     cudaStream_t s, float* seg_sum, float* seg_cnt, const RvqStatsTail* tail) {
   if (!rvq_fused_supported(N, K_per, D, L)) return VQB200_ESHAPE;
   if (workspace_bytes < rvq_fused_workspace_bytes(N, D)) return VQB200_EWORKSPACE;
   const bool bf = mode == VQB200_MODE_BF16_INPUT, scatter = seg_sum != nullptr;
@@ -873,6 +894,10 @@ int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uin
             ((static_cast<uint32_t>(c.BM) >> 4) << 24);
   p.z = z; p.E = E; p.E_lp = E_lp; p.ee_half = ee_half; p.level_meta = level_meta;
   p.seg_sum = seg_sum; p.seg_cnt = seg_cnt;
+  if (tail && tail->stats_out && hist) {
+    p.stats_out = tail->stats_out; p.ep_usage = tail->ep_usage; p.ep_cnt = tail->ep_cnt;
+    p.count_add = tail->count_add; p.inv_elems = tail->inv_elems;
+  }
   uint8_t* w = static_cast<uint8_t*>(workspace);
   p.counters = reinterpret_cast<int*>(w);
   p.scratch = reinterpret_cast<float*>(w + 256);
@@ -881,7 +906,7 @@ int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uin
   if (!make_tensor_map_2d(&map_e, E_lp, static_cast<int64_t>(K_per) * L, D, c.BN,
                           bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2))
     return VQB200_EDRIVER;
-  cudaError_t e = cudaMemsetAsync(p.counters, 0, 2 * sizeof(int), s);
+  cudaError_t e = cudaMemsetAsync(p.counters, 0, 4 * sizeof(int), s);
   if (e != cudaSuccess) return status_of(e);
   const char* dbg = std::getenv("VQB200_DEBUG");
   p.trace = nullptr;
@@ -934,7 +959,7 @@ int launch_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t*
                            float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
                            float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
                            double* sqerr_sum, int32_t* hist, float* seg_sum, float* seg_cnt, void* workspace,
-                           size_t workspace_bytes, cudaStream_t s) {
+                           size_t workspace_bytes, cudaStream_t s, const RvqStatsTail* tail) {
   if (!rvq_fused_train_supported(N, K_per, D, L)) return VQB200_ESHAPE;
   if (workspace_bytes < rvq_fused_workspace_bytes(N, D)) return VQB200_EWORKSPACE;
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
@@ -947,7 +972,7 @@ int launch_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t*
   if (st != VQB200_OK) return st;
   const uint16_t* plane = E_lp_planes + (bf ? 0 : static_cast<size_t>(K_total) * D);
   return launch_rvq_fused(z, N, D, E, plane, bf ? ee_half + K_total : ee_half, level_meta, K_per, L, mode, idx_out, zq_out,
-                          zq_st_out, sqerr_sum, hist, workspace, workspace_bytes, s, seg_sum, seg_cnt);
+                          zq_st_out, sqerr_sum, hist, workspace, workspace_bytes, s, seg_sum, seg_cnt, tail);
 }
 
 int launch_rvq_train_finish(const float* seg_sum, const float* seg_cnt, float decay, float omd, float eps, int K_per, int L,
@@ -960,7 +985,8 @@ int launch_rvq_train_finish(const float* seg_sum, const float* seg_cnt, float de
 int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t* E_lp_planes, float* ee_half,
                            float* level_meta, int K_per, int L, int mode, float decay, float omd, float eps,
                            float* ema_cs, float* ema_emb, int64_t* idx_out, float* zq_out, float* zq_st_out,
-                           double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+                           double* sqerr_sum, int32_t* hist, void* workspace, size_t workspace_bytes, cudaStream_t s,
+                           const RvqStatsTail* tail) {
   if (!rvq_fused_train_supported(N, K_per, D, L)) return VQB200_ESHAPE;
   if (workspace_bytes < rvq_fused_train_workspace_bytes(N, K_per, D, L)) return VQB200_EWORKSPACE;
   const int K_total = K_per * L;
@@ -970,7 +996,7 @@ int launch_rvq_fused_train(const float* z, int64_t N, int D, float* E, uint16_t*
   const size_t seg_bytes = rq_train_seg_bytes(K_total, D);
   const int st = launch_rvq_train_begin(z, N, D, E, E_lp_planes, ee_half, level_meta, K_per, L, mode, decay, omd, eps, ema_cs,
                                         ema_emb, idx_out, zq_out, zq_st_out, sqerr_sum, hist, seg_sum, seg_cnt, w + seg_bytes,
-                                        workspace_bytes - seg_bytes, s);
+                                        workspace_bytes - seg_bytes, s, tail);
   if (st != VQB200_OK) return st;
   return launch_rvq_train_finish(seg_sum, seg_cnt, decay, omd, eps, K_per, L, D, ema_cs, ema_emb, E, E_lp_planes, ee_half,
                                  level_meta, s);

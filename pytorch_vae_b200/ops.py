@@ -106,18 +106,30 @@ def search(z: torch.Tensor, E: torch.Tensor, cache: CodebookCache, level: int, m
 
 @_on_device
 def rvq_forward(z, E, cache: CodebookCache, mode: int, idx_out, zq_out=None, zq_st_out=None, sqerr_sum=None,
-                hist=None):
-    """Eval-mode residual forward (all levels, finalize included) in one library call."""
+                hist=None, stats=None):
+    """Eval-mode residual forward (all levels, finalize included) in one library call.  ``stats`` =
+    ``(count_add, inv_elems, ep_usage, ep_cnt, stats_out)``: the statistics of ``stats_finalize`` in the same call (inside
+    the persistent kernel where it runs)."""
     _need_cuda(z, E, idx_out)
     _f32c(z, "z")
     N, D = z.shape
     K, L = cache.K_per, cache.levels
     ws_bytes = lib.vqb200_rvq_forward_workspace_bytes(N, K, D, L, mode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-    check(lib.vqb200_rvq_forward(ptr(z), N, D, ptr(E), cache.operand_ptr(mode, 0), cache.ee_half.data_ptr(),
-                                 cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, L, mode,
-                                 ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws),
-                                 ws_bytes, stream_ptr()), "vqb200_rvq_forward")
+    if stats is not None:
+        count_add, inv_elems, ep_usage, ep_cnt, stats_out = stats
+        check(lib.vqb200_rvq_forward_stats(ptr(z), N, D, ptr(E), cache.operand_ptr(mode, 0), cache.ee_half.data_ptr(),
+                                           cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, L,
+                                           mode, ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist),
+                                           ptr(ws), ws_bytes, float(count_add), float(inv_elems), ptr(ep_usage),
+                                           ptr(ep_cnt), ptr(stats_out), stream_ptr()), "vqb200_rvq_forward_stats")
+        if not lib.vqb200_rvq_fused_supported(N, K, D, L, mode):
+            _count(1)
+    else:
+        check(lib.vqb200_rvq_forward(ptr(z), N, D, ptr(E), cache.operand_ptr(mode, 0), cache.ee_half.data_ptr(),
+                                     cache.ee_half.data_ptr() + cache.K_total * 4, ptr(cache.level_meta), K, L, mode,
+                                     ptr(idx_out), ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws),
+                                     ws_bytes, stream_ptr()), "vqb200_rvq_forward")
     global last_rvq_workspace
     last_rvq_workspace = ws           # persistent kernel: counters[0] = rows that took its exhaustive search (read lazily)
     _count(lib.vqb200_rvq_forward_launches(N, K, D, L, mode))
@@ -125,19 +137,31 @@ def rvq_forward(z, E, cache: CodebookCache, mode: int, idx_out, zq_out=None, zq_
 
 @_on_device
 def rvq_train_forward(z, E, cache: CodebookCache, mode, decay, eps, ema_cluster_size, ema_embedding, idx_out, zq_out,
-                      zq_st_out=None, sqerr_sum=None, hist=None):
-    """Training-mode residual forward with a local EMA update after every level, in one library call."""
+                      zq_st_out=None, sqerr_sum=None, hist=None, stats=None):
+    """Training-mode residual forward with a local EMA update after every level, in one library call (``stats`` as in
+    ``rvq_forward``)."""
     _need_cuda(z, E, idx_out, zq_out)
     _f32c(z, "z")
     N, D = z.shape
     K, L = cache.K_per, cache.levels
     ws_bytes = lib.vqb200_rvq_train_workspace_bytes(N, K, D, L, mode)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-    check(lib.vqb200_rvq_train_forward(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), ptr(cache.ee_half),
-                                       ptr(cache.level_meta), K, L, mode, float(decay), float(1 - decay), float(eps),
-                                       ptr(ema_cluster_size), ptr(ema_embedding), ptr(idx_out), ptr(zq_out),
-                                       ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws), ws_bytes, stream_ptr()),
-          "vqb200_rvq_train_forward")
+    if stats is not None:
+        count_add, inv_elems, ep_usage, ep_cnt, stats_out = stats
+        check(lib.vqb200_rvq_train_forward_stats(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), ptr(cache.ee_half),
+                                                 ptr(cache.level_meta), K, L, mode, float(decay), float(1 - decay),
+                                                 float(eps), ptr(ema_cluster_size), ptr(ema_embedding), ptr(idx_out),
+                                                 ptr(zq_out), ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws),
+                                                 ws_bytes, float(count_add), float(inv_elems), ptr(ep_usage), ptr(ep_cnt),
+                                                 ptr(stats_out), stream_ptr()), "vqb200_rvq_train_forward_stats")
+        if not lib.vqb200_rvq_train_fused_supported(N, K, D, L, mode):
+            _count(1)
+    else:
+        check(lib.vqb200_rvq_train_forward(ptr(z), N, D, ptr(E), ptr(cache.E_bf16), ptr(cache.ee_half),
+                                           ptr(cache.level_meta), K, L, mode, float(decay), float(1 - decay), float(eps),
+                                           ptr(ema_cluster_size), ptr(ema_embedding), ptr(idx_out), ptr(zq_out),
+                                           ptr(zq_st_out), ptr(sqerr_sum), ptr(hist), ptr(ws), ws_bytes, stream_ptr()),
+              "vqb200_rvq_train_forward")
     if lib.vqb200_rvq_train_fused_supported(N, K, D, L, mode):
         # persistent kernel: its counters follow the segment sums in the workspace (diagnostics, read lazily)
         global last_rvq_workspace

@@ -328,13 +328,19 @@ class VectorQuantizerEMA(nn.Module):
         ema_ok = do_ema and N > 0 and (valid_u8 is None or bool(valid_u8.any()))
 
         idx_all = torch.empty(L * N, dtype=torch.int64, device=dev)   # RVQ: level-major, global ids (:260)
+        # single-process statistics can ride in the library call that runs the levels (the persistent kernel's last CTA)
+        stats_req = None
+        if L > 1 and N > 0 and not (self.stats_sync and sharding.dist_ready()):
+            stats_req = {"args": (float(L * N), 1.0 / max(N * D, 1), self._ep_usage, self._ep_cnt, stats3), "done": False}
         if N > 0:
             self._quantize_rows(flat, [idx_all[l * N:(l + 1) * N] for l in range(L)], z_q, z_q_st, sqerr, hist,
-                                valid_u8, do_ema, ema_ok)
-        self._finalize_stats(hist, float(L * N), sqerr, N * D, stats3)
+                                valid_u8, do_ema, ema_ok, stats_req)
+        if stats_req is None or not stats_req["done"]:
+            self._finalize_stats(hist, float(L * N), sqerr, N * D, stats3)
         return z_q_st.view(B, M, D), z_q.view(B, M, D), (idx_all.view(B, M) if L == 1 else idx_all), stats3
 
-    def _quantize_rows(self, flat, idx_levels, z_q, z_q_st, sqerr, hist, valid_u8, do_ema=False, ema_ok=False):
+    def _quantize_rows(self, flat, idx_levels, z_q, z_q_st, sqerr, hist, valid_u8, do_ema=False, ema_ok=False,
+                       stats_req=None):
         """Search + gather (+ EMA) of the rows ``flat`` [n, D] into caller-allocated outputs; ``sqerr`` and
         ``hist`` ACCUMULATE, so a batch may be fed in several calls (``forward_host``).  ``z_q`` / ``z_q_st``
         may be None for a single-level codebook (codes only)."""
@@ -379,7 +385,9 @@ class VectorQuantizerEMA(nn.Module):
             # than their kernels cost GPU time).
             if lstride == n:
                 ops.rvq_forward(flat, E, cache, mode, idx_levels[0], zq_out=z_q, zq_st_out=z_q_st, sqerr_sum=sqerr,
-                                hist=hist)
+                                hist=hist, stats=stats_req["args"] if stats_req else None)
+                if stats_req:
+                    stats_req["done"] = True
                 return
             on_tc = bool(_cabi.lib.vqb200_search_path(n, self.K_per, D, mode)) and L > 1
             z16 = torch.empty(n, D, dtype=torch.bfloat16, device=flat.device) if on_tc else None
@@ -403,7 +411,10 @@ class VectorQuantizerEMA(nn.Module):
             # training, every rank updating from its own rows: all levels, their EMA updates and the
             # straight-through / loss pass in ONE library call
             ops.rvq_train_forward(flat, E, cache, mode, self.decay, self.eps, self.ema_cluster_size,
-                                  self.ema_embedding, idx_levels[0], z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist)
+                                  self.ema_embedding, idx_levels[0], z_q, zq_st_out=z_q_st, sqerr_sum=sqerr, hist=hist,
+                                  stats=stats_req["args"] if stats_req else None)
+            if stats_req:
+                stats_req["done"] = True
             cache.key = (self.embedding.data_ptr(), self.embedding._version)
             return
         if ema_ok and valid_u8 is None and n > 0 and self.ema_sync == "allreduce" and sharding.dist_ready():
