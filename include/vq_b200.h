@@ -112,7 +112,7 @@ VQB200_API int vqb200_search_prepped(const float* z, const uint16_t* z16, const 
  * (plane 1) and level_meta are the WHOLE cache arrays ([K_per * L, ...]); idx_out [L * N] level-major global ids. */
 VQB200_API size_t vqb200_rvq_forward_workspace_bytes(int64_t N, int K_per, int D, int L, int mode);
 VQB200_API int vqb200_rvq_forward_launches(int64_t N, int K_per, int D, int L, int mode);
-/* 1 when vqb200_rvq_forward runs the shape as ONE persistent kernel (csrc/vq_rvq_fused.cu: a CTA owns 128 rows and walks
+/* 1 when vqb200_rvq_forward runs the shape as ONE persistent kernel (csrc/vq_rvq_fused.cuh: a CTA owns 64 or 128 rows and walks
  * all levels -- operand tile of the residual in shared memory, tcgen05 scores in TMEM, candidate records in shared
  * memory, exact re-rank, residual update, outputs -- without a launch between levels): D in {128, 256, 384, 512},
  * K_per >= 128, 2 <= L <= 8. */

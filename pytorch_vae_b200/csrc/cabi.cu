@@ -306,7 +306,7 @@ int vqb200_rvq_train_forward_stats(const float* z, int64_t N, int D, float* E, u
 
 // ---- the same forward in two halves around the point where ranks exchange their segment sums (all-reduced EMA):
 // ONE exchange per step instead of one per level -- a level is searched against codes that have only seen decay-only
-// updates from the earlier levels of the step (csrc/vq_rvq_fused.cu), so no search waits for another rank's rows.
+// updates from the earlier levels of the step (csrc/vq_rvq_fused.cuh), so no search waits for another rank's rows.
 int vqb200_rvq_train_fused_supported(int64_t N, int K_per, int D, int L, int mode) {
   (void)mode;
   return rvq_fused_train_supported(N, K_per, D, L) ? 1 : 0;

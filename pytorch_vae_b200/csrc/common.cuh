@@ -220,7 +220,7 @@ struct RvqStatsTail {
   float count_add;
   double inv_elems;
 };
-// persistent residual-VQ forward, all levels in one kernel (vq_rvq_fused.cu)
+// persistent residual-VQ forward, all levels in one kernel (vq_rvq_fused.cuh; host side vq_rvq_fused.cu)
 bool rvq_fused_supported(int64_t N, int K_per, int D, int L);
 size_t rvq_fused_workspace_bytes(int64_t N, int D);
 int launch_rvq_fused(const float* z, int64_t N, int D, const float* E, const uint16_t* E_lp, const float* ee_half,

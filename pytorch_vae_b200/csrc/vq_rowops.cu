@@ -12,7 +12,7 @@ namespace vqb {
 // MODE 0: derive the cache from E.  MODE 1: EMA update (models/vq_vae.py:85-89) then the cache.
 // MODE 2: Lloyd step of the k-means initialiser -- E <- segment mean where the segment is non-empty (an empty
 // cluster keeps its centroid), then the cache.
-// MODE 1 with chain_phase != 0 (training forward of a residual codebook, vq_rvq_fused.cu): the reference runs one EMA
+// MODE 1 with chain_phase != 0 (training forward of a residual codebook, vq_rvq_fused.cuh): the reference runs one EMA
 // update per LEVEL and every update touches all K_total codes; for the codes of another level it is a decay-only step
 // (empty one-hot columns: n = 0, s = 0).  Phase 1 applies to a code of level l the l decay-only steps of the earlier
 // levels (the state the level is searched in; level 0 keeps its E untouched), phase 2 its own update from the segment
