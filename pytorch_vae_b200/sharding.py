@@ -60,14 +60,23 @@ class PeerStatsExchange:
     def get(cls, device, K_total: int):
         key = (str(device), int(K_total))
         if key not in cls._cache:
+            inst = None
             try:
                 if dist.get_backend() != "nccl" or torch.device(device).type != "cuda":
                     raise RuntimeError("peer memory needs CUDA devices")
-                cls._cache[key] = cls(device, K_total)
+                inst = cls(device, K_total)
             except Exception as e:                              # noqa: BLE001 -- any set-up failure: keep NCCL
                 import warnings
                 warnings.warn(f"peer-memory statistics exchange unavailable ({type(e).__name__}: {e}); using NCCL")
-                cls._cache[key] = None
+            # every rank must take the same route: one rank falling back alone would leave the others waiting for its flag
+            try:
+                ok = torch.tensor([1 if inst is not None else 0], dtype=torch.int32, device=device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0:
+                    inst = None
+            except Exception:                                   # noqa: BLE001
+                inst = None
+            cls._cache[key] = inst
         return cls._cache[key]
 
 

@@ -168,6 +168,7 @@ def test_persistent_training_kernel_matches_level_pipeline(vq, dev, monkeypatch,
     b = run()
     for step, (x, y) in enumerate(zip(a[0], b[0])):
         same = (x[0].reshape(L, N) == y[0].reshape(L, N)).all(0)
+        print(f"persistent vs level pipeline, {K_per}x{L} D={D} N={N} step {step}: {int((~same).sum())} of {N} rows differ")
         assert same.mean() > (0.999 if step == 0 else 0.99), f"step {step}: {(~same).sum()} rows differ"
         if step == 0:
             assert np.array_equal(x[1][same], y[1][same]) and np.array_equal(x[2][same], y[2][same])
