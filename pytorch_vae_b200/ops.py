@@ -443,7 +443,7 @@ def usage_probs_backward_from_probs(P, E, grad_p):
     """grad_z_n = (1/N) sum_j P_nj (g_j - sum_k P_nk g_k) e_j from the saved probabilities: elementwise passes over
     [N, K] and one plain fp32 GEMM."""
     N = P.shape[0]
-    rowdot = P @ grad_p                                   # [N]
+    rowdot = _matmul_fp32(P, grad_p.unsqueeze(1)).squeeze(1)   # [N]
     dS = P * (grad_p.unsqueeze(0) - rowdot.unsqueeze(1))
     dS.mul_(1.0 / max(N, 1))
     return _matmul_fp32(dS, E)
