@@ -411,10 +411,10 @@ def run_b200(args, w, with_cpu=True):
             loss_host[:2].copy_(o[3], non_blocking=True)
             loss_host[2:].copy_(q.last_commit.detach().reshape(1), non_blocking=True)
 
-    # warm-up of the end-to-end loop: two steps where a step moves >= 1 GiB (c3 / c4: 78 ms each); forty for the small
+    # warm-up of the end-to-end loop: two steps where a step moves >= 1 GiB (c3 / c4: 78 ms each); sixty for the small
     # workloads, whose back-to-back asynchronous calls otherwise spend the timed region growing the caching allocator's
     # pool (one cudaMalloc per call until ~40 calls are in flight: profiles/probes/forward_host_probe.py)
-    e2e_loop(2 if N * D * 4 >= (1 << 30) else 40)
+    e2e_loop(2 if N * D * 4 >= (1 << 30) else 60)
     sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

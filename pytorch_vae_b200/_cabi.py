@@ -122,5 +122,11 @@ def ptr(t):
 
 
 def stream_ptr():
+    """Raw handle of the current stream of the current device.  (torch.cuda.current_stream().cuda_stream builds a Stream
+    object and resolves the device through several Python layers: 10 us per call, two calls per training step of a
+    0.2 ms step; the raw query is one C call.)"""
     import torch
+    raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if raw is not None:
+        return raw(torch._C._cuda_getDevice())
     return torch.cuda.current_stream().cuda_stream

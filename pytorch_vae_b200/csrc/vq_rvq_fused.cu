@@ -150,8 +150,13 @@ int launch_rvq_train_begin(const float* z, int64_t N, int D, float* E, uint16_t*
   if (workspace_bytes < rvq_fused_workspace_bytes(N, D)) return VQB200_EWORKSPACE;
   const bool bf = mode == VQB200_MODE_BF16_INPUT;
   const int K_total = K_per * L;
-  cudaError_t e = cudaMemsetAsync(seg_sum, 0, static_cast<size_t>(K_total) * D * 4, s);
-  if (e == cudaSuccess) e = cudaMemsetAsync(seg_cnt, 0, static_cast<size_t>(K_total) * 4, s);
+  cudaError_t e;
+  if (seg_cnt == seg_sum + static_cast<size_t>(K_total) * D) {            // one buffer (the usual case): one memset
+    e = cudaMemsetAsync(seg_sum, 0, (static_cast<size_t>(K_total) * D + K_total) * 4, s);
+  } else {
+    e = cudaMemsetAsync(seg_sum, 0, static_cast<size_t>(K_total) * D * 4, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(seg_cnt, 0, static_cast<size_t>(K_total) * 4, s);
+  }
   if (e != cudaSuccess) return status_of(e);
   int st = launch_codebook_refresh(1, seg_sum, seg_cnt, decay, omd, eps, K_total, D, K_per, ema_cs, ema_emb, E, E_lp_planes,
                                    ee_half, level_meta, s, /*chain_phase=*/1);

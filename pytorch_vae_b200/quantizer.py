@@ -242,8 +242,10 @@ class VectorQuantizerEMA(nn.Module):
             raise RuntimeError(f"z_e has last dim {D}, the codebook has D={self.D}")
         do_ema = bool(self.training and do_ema_update)
         z_q_st, z_q, indices, stats, commit = _QuantizeFn.apply(z_e, self, do_ema, mask)
-        self.last_commit = commit
-        self._last_pair = (weakref.ref(z_q), weakref.ref(z_e))   # identity check only: keeps no graph alive
+        # plain attributes, set past nn.Module.__setattr__ (its parameter / buffer / module bookkeeping costs ~5 us per
+        # assignment: a tenth of the host time of a stage-2 step)
+        self.__dict__["last_commit"] = commit
+        self.__dict__["_last_pair"] = (weakref.ref(z_q), weakref.ref(z_e))   # identity check only: keeps no graph alive
         return z_q_st, z_q, indices, stats
 
     # transient per-forward / per-device state: autograd-attached tensors, CUDA streams and events, the derived
