@@ -507,7 +507,18 @@ class VectorQuantizerEMA(nn.Module):
         scratch = torch.zeros(4 + self.K, dtype=torch.int32, device=dev)
         sqerr, hist = scratch[:4].view(torch.float64), scratch[4:]
         stats3 = torch.empty(3, dtype=torch.float32, device=dev)
-        stage = torch.empty(ring, min(chunk_rows, max(N, 1)), D, dtype=torch.float32, device=dev)
+        # device staging buffers: persistent (one cudaMalloc per shape, not one block per call), and TWO sets when the
+        # whole batch is one chunk, so that with wait=False the H2D copy of the next call overlaps the kernels of this one
+        # (small-batch extraction: max(copy, kernels) per call instead of their sum)
+        skey = (ring, min(chunk_rows, max(N, 1)), D, 2 if n_chunks == 1 else 1)
+        if pipe.get("stage_key") != skey:
+            pipe["stage_key"] = skey
+            pipe["stage"] = [torch.empty(skey[0], skey[1], D, dtype=torch.float32, device=dev) for _ in range(skey[3])]
+            pipe["ev_free"] = [torch.cuda.Event() for _ in range(skey[3])]
+            pipe["calls"] = 0
+        sset = pipe["calls"] % skey[3]
+        pipe["calls"] += 1
+        stage, ev_free = pipe["stage"][sset], pipe["ev_free"][sset]
         z_q = torch.empty(N, D, dtype=torch.float32, device=dev) if want_all else None
         z_q_st = torch.empty(N, D, dtype=torch.float32, device=dev) if want_all else None
         idt = torch.int64 if token_major is None else token_major
@@ -522,7 +533,7 @@ class VectorQuantizerEMA(nn.Module):
         self._codebook_cache()                                # refresh on the caller's stream, before the fork
         fork = torch.cuda.Event()
         fork.record(main)
-        s_in.wait_event(fork)
+        s_in.wait_event(ev_free)                              # the call that last used this staging set has read it
         s_out.wait_event(fork)
 
         for c in range(n_chunks):
@@ -552,6 +563,7 @@ class VectorQuantizerEMA(nn.Module):
                 else:
                     for l in range(L):
                         idx_h[l * N + r0:l * N + r1].copy_(idx_all[l * N + r0:l * N + r1], non_blocking=True)
+        ev_free.record(main)                                  # every kernel that reads the staging set is enqueued
         self._finalize_stats(hist, float(L * N), sqerr, N * D, stats3)
         stats_h.copy_(stats3[:2], non_blocking=True)
         done = torch.cuda.Event()
